@@ -1,0 +1,100 @@
+"""ctypes binding of libfsn_b200.so (C ABI: include/fsn_b200.h).  PyTorch is used only for
+device memory and streams; every pointer handed to the library is ``tensor.data_ptr()``."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libfsn_b200.so")
+
+FSN_OK, FSN_ERR_SHAPE, FSN_ERR_UNSUPPORTED, FSN_ERR_CUDA, FSN_ERR_WORKSPACE = 0, 1, 2, 3, 4
+ACT = {None: 0, False: 0, "": 0, "ReLU": 1, "Tanh": 2, "ReLU6": 3}
+PREC = {"fp32": 0, "f16_tc": 1}
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "num_freqs", "look_ahead", "fb_num_neighbors", "sb_num_neighbors", "fb_hidden", "sb_hidden",
+        "fb_activation", "sb_activation", "norm_type", "num_groups_in_drop_band", "precision", "reserved")]
+
+
+class SeqWeights(C.Structure):
+    _fields_ = [("w_ih", C.c_void_p * 2), ("w_hh", C.c_void_p * 2), ("b_ih", C.c_void_p * 2),
+                ("b_hh", C.c_void_p * 2), ("fc_w", C.c_void_p), ("fc_b", C.c_void_p)]
+
+
+_P, _I, _L, _F, _S = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+_SIGNATURES = {
+    "fsn_version": (C.c_int, []),
+    "fsn_last_error": (C.c_char_p, []),
+    "fsn_built_arch": (C.c_int, []),
+    "fsn_stft": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P]),
+    "fsn_istft": (C.c_int, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "fsn_decompress_cirm": (C.c_int, [_P, _P, _L, _F, _F, _P]),
+    "fsn_compress_cirm": (C.c_int, [_P, _P, _L, _F, _F, _P]),
+    "fsn_build_cirm": (C.c_int, [_P, _P, _P, _P, _P, _L, _P]),
+    "fsn_drop_band": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "fsn_model_workspace_bytes": (_S, [C.POINTER(ModelDesc), _I, _I]),
+    "fsn_sb_packed_bytes": (_S, [C.POINTER(ModelDesc)]),
+    "fsn_pack_sb_weights": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(SeqWeights), _P, _P]),
+    "fsn_model_forward": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(SeqWeights), C.POINTER(SeqWeights), _P, _P,
+                                    _I, _I, _P, _P, _S, _P]),
+    "fsn_enhance_workspace_bytes": (_S, [C.POINTER(ModelDesc), _I, _I, _I, _I]),
+    "fsn_enhance": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(SeqWeights), C.POINTER(SeqWeights), _P, _P, _I, _I,
+                              _I, _I, _I, _P, _P, _P, _S, _P]),
+    "fsn_last_launch_count": (C.c_int64, []),
+    "fsn_set_profiling": (C.c_int, [_I]),
+    "fsn_last_stage_ms": (C.c_float, [_I]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; fail loudly if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"fullsubnet_b200: {LIB_PATH} is missing. Build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (nvcc, sm_100a). There is no CPU/PyTorch fallback for this path.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    """Map C-ABI status codes to the exception types the reference raises."""
+    if rc == FSN_OK:
+        return
+    msg = load().fsn_last_error().decode()
+    if rc == FSN_ERR_SHAPE:
+        raise AssertionError(msg)
+    if rc == FSN_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(f"libfsn_b200 error {rc}: {msg}")
+
+
+def require_cuda(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"fullsubnet_b200: {what} must be a CUDA tensor (got {t.device}); this package has no CPU path.")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,255 @@
+"""bench.py - FullSubNet inference throughput on B200 (BASELINE.json metric: frames/s and x real-time,
+16 kHz, n_fft=512, hop=256) for the workload `configs[1]`: batch = 256 x 4 s synthetic clips per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--precision auto|fp32|f16_tc]
+  python bench.py --impl reference      # the CPU arm (oracle port of the reference path, all host threads)
+
+One "step" = one pass of the hot path (stft -> model -> decompress/mask -> istft) over one batch.
+`value` is measured with the inputs resident in HBM; `e2e` goes through the public API with pinned HOST
+buffers, the H2D copy of the waveforms and the D2H copy of the result inside the timed region.
+Multi-GPU: one process per GPU (torchrun), clips sharded over ranks, no data-path collective (weak
+scaling: every rank enhances its own B clips); time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR, N_FFT, HOP, WIN = 16000, 512, 256, 512
+CLIP_SECONDS = 4
+FLOP_PER_FRAME_STEP_SB = 257 * 3_638_784  # sub-band stack, per clip per LSTM step
+FLOP_PER_FRAME_STEP_ALL = 942_774_784
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_oracle_time(n_clips: int, threads: int):
+    """Times the oracle port of Inferencer.full_band_crm_mask (B=1 loop, the reference's only batch)."""
+    from oracle import fullsubnet_oracle as O
+    torch.set_num_threads(threads)
+    sd = O.make_state_dict(seed=0)
+    y = O.make_noisy(n_clips, SR * CLIP_SECONDS, seed=0)
+    with torch.no_grad():
+        O.enhance(y[:1, :8000], sd, batched=False)  # warm-up
+        t0 = time.perf_counter()
+        O.enhance(y, sd, batched=False)
+        dt = time.perf_counter() - t0
+    frames = n_clips * (1 + (SR * CLIP_SECONDS) // HOP)
+    return frames / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_clips = 2
+    vals = []
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_oracle_time(1, cores)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        v, _ = cpu_oracle_time(n_clips, cores)
+        vals.append(v)
+    dt = time.perf_counter() - t_all
+    v = sorted(vals)[len(vals) // 2]
+    T = 1 + (SR * CLIP_SECONDS) // HOP
+    line = {
+        "impl": "reference", "metric": "frames_per_sec", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "rtf_x": v / (SR / HOP),
+        "config": {"workload": "fullsubnet inference, 4 s 16 kHz clips, n_fft=512 hop=256 N=15 (CPU: B=1 loop)",
+                   "clip_seconds": CLIP_SECONDS, "frames_per_clip": T},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_clips} x 4 s clips per step, B=1 loop, torch CPU fp32, {cores} threads"},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256, help="clips per GPU (configs[1]: 256)")
+    ap.add_argument("--precision", default="auto")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import ctypes as C
+    from fullsubnet_b200 import _lib
+    from fullsubnet_b200.fullsubnet.model import Model
+    from fullsubnet_b200.inferencer import Inferencer
+    from oracle import fullsubnet_oracle as O  # weights / inputs generator only (+ cpu_baseline leg)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+
+    lib = _lib.load()
+    B, L = args.batch, SR * CLIP_SECONDS
+    T = 1 + L // HOP
+    model = Model(**O.DEFAULT_MODEL_ARGS, precision=args.precision)
+    model.load_state_dict(O.make_state_dict(seed=0), strict=True)
+    model = model.to(dev).eval()
+    precision = model._resolve_precision()
+    inf = Inferencer(model=model, device=dev)
+    host_in = O.make_noisy(B, L, seed=rank).pin_memory()  # every rank enhances its own clips
+    host_out = torch.empty(B, L, dtype=torch.float32).pin_memory()
+    x_dev = host_in.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, prof=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        lib.fsn_set_profiling(1 if prof else 0)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage = [0.0] * 4
+        ev0.record()
+        for _ in range(steps):
+            flush.zero_()  # L2 flush between timed iterations (inside the region, ~0.1 ms)
+            fn()
+            if prof:
+                torch.cuda.synchronize()
+                for s in range(4):
+                    stage[s] += max(0.0, lib.fsn_last_stage_ms(s))
+        ev1.record()
+        barrier()
+        lib.fsn_set_profiling(0)
+        ms = ev0.elapsed_time(ev1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, [s / steps for s in stage]
+
+    def step_resident():
+        model.enhance(x_dev, N_FFT, HOP, WIN)
+
+    def step_e2e():
+        out = inf.enhance_batch(host_in)  # H2D inside
+        host_out.copy_(out, non_blocking=True)  # D2H inside
+        torch.cuda.current_stream().synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_step, _ = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop()
+    launches = int(lib.fsn_last_launch_count())
+    # second pass with stage events on (separate from the headline timing)
+    _, stage_ms = timed(step_resident, max(2, min(args.steps, 3)), 1, prof=True)
+    ms_e2e, _ = timed(step_e2e, args.steps, 1)
+
+    frames = B * T * world
+    value = frames / (ms_step * 1e-3)
+    e2e_value = frames / (ms_e2e * 1e-3)
+    peaks, peak_kind = load_peaks()
+    sb_ms = stage_ms[2]
+    sb_flops = B * (T + 2) * FLOP_PER_FRAME_STEP_SB
+    achieved = sb_flops / (sb_ms * 1e-3) / 1e12 if sb_ms > 0 else None
+    # tensor roofline: fp16 operands on tcgen05 (same dense rate as the measured bf16 cuBLAS peak);
+    # the fp32 path is FMA-bound and reported against the same denominator for comparability
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    line = {
+        "metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16xf32acc" if precision == "f16_tc" else "f32", "data": "synthetic",
+        "rtf_x": value / (SR / HOP),
+        "config": {"workload": f"fullsubnet inference, batch={B} x 4 s 16 kHz synthetic clips per GPU, "
+                               "n_fft=512 hop=256 N=15, 2xLSTM-512 fb + 2xLSTM-384 sb (BASELINE configs[1])",
+                   "clips_per_gpu": B, "frames_per_clip": T, "precision": precision,
+                   "l2": "256 MiB flush write between timed iterations", "parallelism": f"clips sharded x{world}"},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * L * 4, "rtf_x": e2e_value / (SR / HOP)},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "stage_ms": {"stft": stage_ms[0], "fullband": stage_ms[1], "subband": stage_ms[2], "mask_istft": stage_ms[3]},
+        "roofline": {"kernel": "sub-band LSTM stack", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+                     "peak_source": f"{peak_kind} bf16_tflops_sustained",
+                     "flops_per_launch": sb_flops, "ms_per_launch": sb_ms},
+    }
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        v, dt = cpu_oracle_time(4, cores)
+        line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": f"4 x 4 s clips, B=1 loop of the oracle port, torch CPU fp32, "
+                                          f"{cores} threads, {dt:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

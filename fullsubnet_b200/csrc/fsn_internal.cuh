@@ -1,0 +1,72 @@
+// Internal (non-ABI) declarations shared by the translation units of libfsn_b200.
+#pragma once
+#include "fsn_common.cuh"
+
+namespace fsn {
+
+// Sub-band row -> (clip, frequency) map.  Row r = b' * Fsub + f' of the sub-band batch.
+// G <= 1: identity (Fsub = F).  G > 1: drop_band (audio_zen/acoustics/feature.py:332-345):
+// output clip b' of group g is input clip g + G*i, frequency f' is input bin g + G*f'.
+struct RowMap {
+  int B, F, Fsub, G;
+};
+
+__host__ __device__ inline void row_to_unit(const RowMap& m, int r, int& b, int& f) {
+  int bq = r / m.Fsub;
+  const int fq = r - bq * m.Fsub;
+  if (m.G <= 1) { b = bq; f = fq; return; }
+  int g = 0;
+  for (; g < m.G; ++g) {
+    const int cnt = (m.B - g + m.G - 1) / m.G;
+    if (bq < cnt) break;
+    bq -= cnt;
+  }
+  b = g + m.G * bq;
+  f = g + m.G * fq;
+}
+
+enum { SEG0_DENSE = 0, SEG0_GATHER = 1 };
+
+struct StepParams {
+  int R, K0, H, first;
+  const float* w_ih; const float* w_hh; const float* b_ih; const float* b_hh;
+  const float* h_prev; size_t h_prev_stride;
+  float* h_out; size_t h_out_stride;
+  float* c;
+  // SEG0_DENSE: x = x0[row * x0_row_stride + k] * (row_scale ? row_scale[row] : 1)
+  const float* x0; size_t x0_row_stride; const float* row_scale;
+  // SEG0_GATHER: sub-band unit of row r at frame t (base_model.py:13-46 + model.py:98-111)
+  const float* magT; const float* fbT; const float* inv2;
+  int F, Tp, t, Ns, Nf;
+  RowMap map;
+};
+
+int lstm_step_launch(const StepParams& p, int mode, cudaStream_t st);
+int fc_gemm_launch(const float* A, const float* W, const float* bias, float* out, int M, int K, int O, int act,
+                   cudaStream_t st);
+int sb_fc_step_launch(const float* h, int R, int H, const float* W, const float* bias, int O, int act, float* crm,
+                      int Fsub, int T_out, int t_out, cudaStream_t st);
+int transpose_mag_launch(const float* in, float* out, int B, int F, int T, int T_pad, cudaStream_t st);
+int clip_stats_launch(const float* x, int B, int T_pad, int F, int N, float2* fs, float2* sums, cudaStream_t st);
+int norm_scales_launch(const float2* mag_sums, const float2* fb_sums, int B, float cnt1, float cnt2, float* inv1,
+                       float* inv2, cudaStream_t st);
+
+int stft_launch(const float* wav, int B, int L, int n_fft, int hop, int win_length, float* mag, float* phase,
+                float* real, float* imag, float* magT, int T_pad, cudaStream_t st);
+int istft_launch(const float* real, const float* imag, int cstride, const float* crm, int B, int T, int n_fft,
+                 int hop, int win_length, int length, float* wav, cudaStream_t st);
+
+// tcgen05 sub-band stack (fsn_subband_tc.cu)
+struct SbTcArgs {
+  const void* packed;       // tile-ordered fp16 weights (fsn_pack_sb_weights)
+  const float* magT; const float* fbT; const float* inv2;
+  float* crm;
+  int B, F, Tp, la, Ns, Nf, H, act;
+  RowMap map;
+};
+size_t sb_tc_packed_bytes(const fsn_model_desc* d);
+int sb_tc_pack(const fsn_model_desc* d, const fsn_seq_weights* sb, void* packed, cudaStream_t st);
+int sb_tc_forward(const SbTcArgs& a, cudaStream_t st);
+bool sb_tc_supported(const fsn_model_desc* d);
+
+}  // namespace fsn

@@ -1,0 +1,308 @@
+// Host-side orchestration of Model.forward and the fused wav->wav enhancement call, plus the
+// error / version entry points of the C ABI (include/fsn_b200.h).
+//
+// Reference: recipes/dns_interspeech_2020/fullsubnet/model.py:72-136 (Model.forward),
+//            recipes/dns_interspeech_2020/inferencer.py:130-145 (full_band_crm_mask).
+#include <string.h>
+
+#include "fsn_internal.cuh"
+
+namespace fsn {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int64_t& launch_counter() { return g_launches; }
+
+// opt-in stage timing (bench.py): 5 events bracket the 4 stages
+static thread_local bool g_prof = false;
+static thread_local cudaEvent_t g_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+static thread_local bool g_ev_valid[5] = {false, false, false, false, false};
+static void prof_mark(int i, cudaStream_t st) {
+  if (!g_prof) return;
+  if (!g_ev[i] && cudaEventCreate(&g_ev[i]) != cudaSuccess) return;
+  g_ev_valid[i] = (cudaEventRecord(g_ev[i], st) == cudaSuccess);
+}
+static void prof_reset() { for (int i = 0; i < 5; ++i) g_ev_valid[i] = false; }
+
+struct Carver {
+  char* base; size_t off;
+  explicit Carver(void* p) : base((char*)p), off(0) {}
+  template <class T> T* take(size_t n) {
+    T* r = base ? (T*)(base + off) : nullptr;
+    off = align_up(off + n * sizeof(T), 256);
+    return r;
+  }
+};
+
+struct ModelWs {
+  float *magT, *fbT, *inv1, *inv2;
+  float2 *fs, *sums_mag, *sums_fb;
+  float *fb_h0[2], *fb_c0, *fb_c1, *fb_h1all;
+  float *sb_h0[2], *sb_h1[2], *sb_c0, *sb_c1;
+  size_t bytes;
+};
+
+struct Dims {
+  int B, T, Tp, F, Fsub, G, R, Ksb;
+};
+
+static int make_dims(const fsn_model_desc* d, int B, int T, Dims& m) {
+  FSN_REQUIRE(d && d->num_freqs > 1 && d->fb_hidden > 0 && d->sb_hidden > 0 && d->look_ahead >= 0, FSN_ERR_SHAPE,
+              "model: bad descriptor");
+  FSN_REQUIRE(B > 0 && T > 0, FSN_ERR_SHAPE, "model: empty input (B=%d, T=%d)", B, T);
+  FSN_REQUIRE(d->norm_type == FSN_NORM_OFFLINE_LAPLACE, FSN_ERR_UNSUPPORTED,
+              "You must set up a type of Norm. (only offline_laplace_norm is built)");
+  FSN_REQUIRE(d->sb_num_neighbors >= 0 && d->fb_num_neighbors >= 0 && d->sb_num_neighbors < d->num_freqs &&
+                  d->fb_num_neighbors < d->num_freqs,
+              FSN_ERR_SHAPE, "model: reflect padding needs num_neighbors < num_freqs");
+  m.B = B; m.T = T; m.Tp = T + d->look_ahead; m.F = d->num_freqs;
+  m.G = (B > 1 && d->num_groups_in_drop_band > 1) ? d->num_groups_in_drop_band : 1;
+  if (B > 1)  // model.py:114-117 -> feature.py:317-319 (asserted even when G == 1)
+    FSN_REQUIRE(B > d->num_groups_in_drop_band, FSN_ERR_SHAPE,
+                "Batch size = %d, num_groups = %d. The batch size should larger than the num_groups.", B,
+                d->num_groups_in_drop_band);
+  m.Fsub = (m.G > 1) ? m.F / m.G : m.F;
+  FSN_REQUIRE(m.Fsub > 0, FSN_ERR_SHAPE, "model: num_freqs < num_groups");
+  m.R = B * m.Fsub;
+  m.Ksb = (2 * d->sb_num_neighbors + 1) + (2 * d->fb_num_neighbors + 1);
+  return FSN_OK;
+}
+
+static void carve_model(const fsn_model_desc* d, const Dims& m, void* base, ModelWs& w) {
+  Carver c(base);
+  const size_t BTF = (size_t)m.B * m.Tp * m.F;
+  w.magT = c.take<float>(BTF);
+  w.fbT = c.take<float>(BTF);
+  w.fs = c.take<float2>((size_t)m.B * m.Tp);
+  w.sums_mag = c.take<float2>(m.B);
+  w.sums_fb = c.take<float2>(m.B);
+  w.inv1 = c.take<float>(m.B);
+  w.inv2 = c.take<float>(m.B);
+  const size_t BH = (size_t)m.B * d->fb_hidden;
+  w.fb_h0[0] = c.take<float>(BH);
+  w.fb_h0[1] = c.take<float>(BH);
+  w.fb_c0 = c.take<float>(BH);
+  w.fb_c1 = c.take<float>(BH);
+  w.fb_h1all = c.take<float>(BH * m.Tp);
+  if (d->precision == FSN_PREC_FP32) {
+    const size_t RH = (size_t)m.R * d->sb_hidden;
+    for (int i = 0; i < 2; ++i) { w.sb_h0[i] = c.take<float>(RH); w.sb_h1[i] = c.take<float>(RH); }
+    w.sb_c0 = c.take<float>(RH);
+    w.sb_c1 = c.take<float>(RH);
+  }
+  w.bytes = c.off;
+}
+
+// everything after the time-major magnitude exists: norms, full-band stack, sub-band stack
+static int model_core(const fsn_model_desc* d, const fsn_seq_weights* fb, const fsn_seq_weights* sb,
+                      const void* sb_packed, const Dims& m, const ModelWs& w, float* crm, cudaStream_t st) {
+  int rc;
+  const int F = m.F, Tp = m.Tp, B = m.B, Hf = d->fb_hidden, Hs = d->sb_hidden;
+  // per-clip statistics of the look-ahead-padded magnitude (model.py:92, :111)
+  if ((rc = clip_stats_launch(w.magT, B, Tp, F, d->sb_num_neighbors, w.fs, w.sums_mag, st))) return rc;
+  if ((rc = norm_scales_launch(w.sums_mag, w.sums_mag, B, (float)F * Tp, 1.f, w.inv1, nullptr, st))) return rc;
+
+  // ---- full-band stack (model.py:92-95): 2-layer LSTM(F -> Hf -> Hf), rows = clips
+  for (int t = 0; t < Tp; ++t) {
+    StepParams p;
+    memset(&p, 0, sizeof(p));
+    p.R = B; p.H = Hf; p.first = (t == 0);
+    // layer 0: x_t = magT[b,t,:] * inv1[b]
+    p.K0 = F;
+    p.w_ih = fb->w_ih[0]; p.w_hh = fb->w_hh[0]; p.b_ih = fb->b_ih[0]; p.b_hh = fb->b_hh[0];
+    p.h_prev = w.fb_h0[(t + 1) & 1]; p.h_prev_stride = Hf;
+    p.h_out = w.fb_h0[t & 1]; p.h_out_stride = Hf;
+    p.c = w.fb_c0;
+    p.x0 = w.magT + (size_t)t * F; p.x0_row_stride = (size_t)Tp * F; p.row_scale = w.inv1;
+    if ((rc = lstm_step_launch(p, SEG0_DENSE, st))) return rc;
+    // layer 1: x_t = h0_t, output kept for every t (input of the Linear layer)
+    p.K0 = Hf;
+    p.w_ih = fb->w_ih[1]; p.w_hh = fb->w_hh[1]; p.b_ih = fb->b_ih[1]; p.b_hh = fb->b_hh[1];
+    p.x0 = w.fb_h0[t & 1]; p.x0_row_stride = Hf; p.row_scale = nullptr;
+    p.h_prev = w.fb_h1all + (size_t)(t > 0 ? t - 1 : 0) * Hf; p.h_prev_stride = (size_t)Tp * Hf;
+    p.h_out = w.fb_h1all + (size_t)t * Hf; p.h_out_stride = (size_t)Tp * Hf;
+    p.c = w.fb_c1;
+    if ((rc = lstm_step_launch(p, SEG0_DENSE, st))) return rc;
+  }
+  // Linear(Hf -> F) + activation over all (b,t): fbT[b,t,f]  (sequence_model.py:119-123)
+  if ((rc = fc_gemm_launch(w.fb_h1all, fb->fc_w, fb->fc_b, w.fbT, B * Tp, Hf, F, d->fb_activation, st))) return rc;
+
+  // ---- second norm (model.py:110-111) in closed form: never materialise [B,F,Ksb,T']
+  if ((rc = clip_stats_launch(w.fbT, B, Tp, F, d->fb_num_neighbors, w.fs, w.sums_fb, st))) return rc;
+  if ((rc = norm_scales_launch(w.sums_mag, w.sums_fb, B, 1.f, (float)F * m.Ksb * Tp, nullptr, w.inv2, st)))
+    return rc;
+
+  prof_mark(2, st);
+  RowMap map{B, F, m.Fsub, m.G};
+  if (d->precision == FSN_PREC_F16_TC) {
+    FSN_REQUIRE(sb_packed, FSN_ERR_SHAPE, "model: FSN_PREC_F16_TC needs packed sub-band weights");
+    SbTcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.packed = sb_packed; a.magT = w.magT; a.fbT = w.fbT; a.inv2 = w.inv2; a.crm = crm;
+    a.B = B; a.F = F; a.Tp = Tp; a.la = d->look_ahead; a.Ns = d->sb_num_neighbors; a.Nf = d->fb_num_neighbors;
+    a.H = Hs; a.act = d->sb_activation; a.map = map;
+    rc = sb_tc_forward(a, st);
+    prof_mark(3, st);
+    return rc;
+  }
+
+  // ---- sub-band stack, fp32 path (model.py:121-135): rows = (clip, frequency) units
+  for (int t = 0; t < Tp; ++t) {
+    StepParams p;
+    memset(&p, 0, sizeof(p));
+    p.R = m.R; p.H = Hs; p.first = (t == 0);
+    p.K0 = m.Ksb;
+    p.w_ih = sb->w_ih[0]; p.w_hh = sb->w_hh[0]; p.b_ih = sb->b_ih[0]; p.b_hh = sb->b_hh[0];
+    p.h_prev = w.sb_h0[(t + 1) & 1]; p.h_prev_stride = Hs;
+    p.h_out = w.sb_h0[t & 1]; p.h_out_stride = Hs;
+    p.c = w.sb_c0;
+    p.magT = w.magT; p.fbT = w.fbT; p.inv2 = w.inv2;
+    p.F = F; p.Tp = Tp; p.t = t; p.Ns = d->sb_num_neighbors; p.Nf = d->fb_num_neighbors; p.map = map;
+    if ((rc = lstm_step_launch(p, SEG0_GATHER, st))) return rc;
+    p.K0 = Hs;
+    p.w_ih = sb->w_ih[1]; p.w_hh = sb->w_hh[1]; p.b_ih = sb->b_ih[1]; p.b_hh = sb->b_hh[1];
+    p.x0 = w.sb_h0[t & 1]; p.x0_row_stride = Hs; p.row_scale = nullptr;
+    p.h_prev = w.sb_h1[(t + 1) & 1]; p.h_prev_stride = Hs;
+    p.h_out = w.sb_h1[t & 1]; p.h_out_stride = Hs;
+    p.c = w.sb_c1;
+    if ((rc = lstm_step_launch(p, SEG0_DENSE, st))) return rc;
+    if (t >= d->look_ahead)
+      if ((rc = sb_fc_step_launch(w.sb_h1[t & 1], m.R, Hs, sb->fc_w, sb->fc_b, 2, d->sb_activation, crm, m.Fsub,
+                                  m.T, t - d->look_ahead, st)))
+        return rc;
+  }
+  prof_mark(3, st);
+  return FSN_OK;
+}
+
+}  // namespace fsn
+
+using namespace fsn;
+
+extern "C" int fsn_version(void) { return 100; }
+extern "C" const char* fsn_last_error(void) { return g_err; }
+extern "C" int64_t fsn_last_launch_count(void) { return g_launches; }
+extern "C" int fsn_set_profiling(int enable) { g_prof = enable != 0; return FSN_OK; }
+extern "C" float fsn_last_stage_ms(int stage) {
+  if (stage < 0 || stage > 3 || !g_ev_valid[stage] || !g_ev_valid[stage + 1]) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, g_ev[stage], g_ev[stage + 1]) != cudaSuccess) return -1.0f;
+  return ms;
+}
+extern "C" int fsn_built_arch(void) {
+#ifdef FSN_BUILT_ARCH
+  return FSN_BUILT_ARCH;
+#else
+  return 0;
+#endif
+}
+
+extern "C" size_t fsn_model_workspace_bytes(const fsn_model_desc* d, int B, int T) {
+  Dims m;
+  if (make_dims(d, B, T, m)) return 0;
+  ModelWs w;
+  carve_model(d, m, nullptr, w);
+  return w.bytes;
+}
+
+extern "C" size_t fsn_sb_packed_bytes(const fsn_model_desc* d) { return sb_tc_packed_bytes(d); }
+
+extern "C" int fsn_pack_sb_weights(const fsn_model_desc* d, const fsn_seq_weights* sb, void* packed,
+                                   fsn_stream_t stream) {
+  return sb_tc_pack(d, sb, packed, (cudaStream_t)stream);
+}
+
+extern "C" int fsn_model_forward(const fsn_model_desc* d, const fsn_seq_weights* fb, const fsn_seq_weights* sb,
+                                 const void* sb_packed, const float* noisy_mag, int B, int T, float* crm,
+                                 void* workspace, size_t workspace_bytes, fsn_stream_t stream) {
+  g_launches = 0;
+  Dims m;
+  int rc = make_dims(d, B, T, m);
+  if (rc) return rc;
+  FSN_REQUIRE(d->precision == FSN_PREC_FP32 || sb_tc_supported(d), FSN_ERR_UNSUPPORTED,
+              "FSN_PREC_F16_TC needs sb_hidden %% 128 == 0 and sub-band input width <= 64");
+  ModelWs w;
+  carve_model(d, m, workspace, w);
+  FSN_REQUIRE(workspace && workspace_bytes >= w.bytes, FSN_ERR_WORKSPACE, "workspace too small: %zu < %zu",
+              workspace_bytes, w.bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_reset();
+  prof_mark(0, st);
+  if ((rc = transpose_mag_launch(noisy_mag, w.magT, B, m.F, T, m.Tp, st))) return rc;
+  prof_mark(1, st);
+  return model_core(d, fb, sb, sb_packed, m, w, crm, st);
+}
+
+struct EnhanceWs {
+  float *real, *imag, *crm;
+  void* model;
+  size_t bytes;
+};
+
+static int carve_enhance(const fsn_model_desc* d, int B, int L, int n_fft, int hop, void* base, EnhanceWs& e,
+                         Dims& m) {
+  FSN_REQUIRE(hop > 0 && n_fft > 0, FSN_ERR_SHAPE, "enhance: bad n_fft/hop");
+  const int T = 1 + L / hop;
+  int rc = make_dims(d, B, T, m);
+  if (rc) return rc;
+  FSN_REQUIRE(n_fft / 2 + 1 == d->num_freqs, FSN_ERR_SHAPE, "enhance: n_fft/2+1 = %d != num_freqs = %d",
+              n_fft / 2 + 1, d->num_freqs);
+  Carver c(base);
+  const size_t BFT = (size_t)B * m.F * T;
+  e.real = c.take<float>(BFT);
+  e.imag = c.take<float>(BFT);
+  e.crm = c.take<float>(2 * BFT);
+  ModelWs w;
+  carve_model(d, m, nullptr, w);
+  e.model = base ? (char*)base + c.off : nullptr;
+  e.bytes = c.off + w.bytes;
+  return FSN_OK;
+}
+
+extern "C" size_t fsn_enhance_workspace_bytes(const fsn_model_desc* d, int B, int L, int n_fft, int hop) {
+  EnhanceWs e;
+  Dims m;
+  fsn_model_desc dd = *d;
+  dd.num_groups_in_drop_band = 1;
+  if (carve_enhance(&dd, B, L, n_fft, hop, nullptr, e, m)) return 0;
+  return e.bytes;
+}
+
+extern "C" int fsn_enhance(const fsn_model_desc* d, const fsn_seq_weights* fb, const fsn_seq_weights* sb,
+                           const void* sb_packed, const float* wav, int B, int L, int n_fft, int hop,
+                           int win_length, float* enhanced, float* crm_out, void* workspace,
+                           size_t workspace_bytes, fsn_stream_t stream) {
+  g_launches = 0;
+  // batched inference == loop of B=1 calls of the reference inferencer: drop_band off
+  // (audio_zen/inferencer/base_inferencer.py:78,173)
+  fsn_model_desc dd = *d;
+  dd.num_groups_in_drop_band = 1;
+  EnhanceWs e;
+  Dims m;
+  int rc = carve_enhance(&dd, B, L, n_fft, hop, workspace, e, m);
+  if (rc) return rc;
+  FSN_REQUIRE(dd.precision == FSN_PREC_FP32 || sb_tc_supported(&dd), FSN_ERR_UNSUPPORTED,
+              "FSN_PREC_F16_TC needs sb_hidden %% 128 == 0 and sub-band input width <= 64");
+  FSN_REQUIRE(workspace && workspace_bytes >= e.bytes, FSN_ERR_WORKSPACE, "workspace too small: %zu < %zu",
+              workspace_bytes, e.bytes);
+  ModelWs w;
+  carve_model(&dd, m, e.model, w);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* crm = crm_out ? crm_out : e.crm;
+  prof_reset();
+  prof_mark(0, st);
+  if ((rc = stft_launch(wav, B, L, n_fft, hop, win_length, nullptr, nullptr, e.real, e.imag, w.magT, m.Tp, st)))
+    return rc;
+  prof_mark(1, st);
+  if ((rc = model_core(&dd, fb, sb, sb_packed, m, w, crm, st))) return rc;
+  rc = istft_launch(e.real, e.imag, 1, crm, B, m.T, n_fft, hop, win_length, L, enhanced, st);
+  prof_mark(4, st);
+  return rc;
+}

@@ -1,0 +1,132 @@
+"""Drop-in for recipes/dns_interspeech_2020/fullsubnet/model.py:9-136 (class Model).
+
+Same constructor kwargs, same 20 ``state_dict`` entries, same ``forward`` contract
+(``noisy_mag [B,1,F,T] -> cRM [B,2,F',T]``, incl. drop_band when B > 1), but the whole forward
+is one call into libfsn_b200 (``fsn_model_forward``): look-ahead pad, both laplace norms (second
+in closed form), full-band 2xLSTM + Linear + ReLU, sub-band unfold (never materialised),
+sub-band 2xLSTM + Linear, output re-layout."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from .. import _lib
+from ..model.base_model import BaseModel
+from ..model.module.sequence_model import SequenceModel
+
+
+class Model(BaseModel):
+    def __init__(self, num_freqs, look_ahead, sequence_model, fb_num_neighbors, sb_num_neighbors,
+                 fb_output_activate_function, sb_output_activate_function, fb_model_hidden_size,
+                 sb_model_hidden_size, norm_type="offline_laplace_norm", num_groups_in_drop_band=2,
+                 weight_init=True, precision=None):
+        super().__init__()
+        assert sequence_model in ("GRU", "LSTM"), f"{self.__class__.__name__} only support GRU and LSTM."
+        self.fb_model = SequenceModel(
+            input_size=num_freqs, output_size=num_freqs, hidden_size=fb_model_hidden_size, num_layers=2,
+            bidirectional=False, sequence_model=sequence_model, output_activate_function=fb_output_activate_function)
+        self.sb_model = SequenceModel(
+            input_size=(sb_num_neighbors * 2 + 1) + (fb_num_neighbors * 2 + 1), output_size=2,
+            hidden_size=sb_model_hidden_size, num_layers=2, bidirectional=False, sequence_model=sequence_model,
+            output_activate_function=sb_output_activate_function)
+        self.num_freqs = num_freqs
+        self.sb_num_neighbors = sb_num_neighbors
+        self.fb_num_neighbors = fb_num_neighbors
+        self.look_ahead = look_ahead
+        self.norm_type = norm_type
+        self.norm = self.norm_wrapper(norm_type)
+        self.num_groups_in_drop_band = num_groups_in_drop_band
+        # arithmetic of the sub-band stack: "fp32" or "f16_tc" (tcgen05, fp16 operands / fp32 accumulate)
+        self.precision = precision or os.environ.get("FSN_PRECISION", "auto")
+        self._packed = None
+        self._packed_key = None
+        if weight_init:
+            self.apply(self.weight_init)
+
+    # ---------------------------------------------------------------- C-ABI plumbing
+    def _resolve_precision(self) -> str:
+        if self.precision != "auto":
+            if self.precision not in _lib.PREC:
+                raise ValueError(f"precision must be one of {list(_lib.PREC)} or 'auto'")
+            return self.precision
+        d = self._desc("f16_tc", 1)
+        return "f16_tc" if _lib.load().fsn_sb_packed_bytes(C.byref(d)) > 0 else "fp32"
+
+    def _desc(self, precision: str, num_groups: int) -> "_lib.ModelDesc":
+        return _lib.ModelDesc(
+            num_freqs=self.num_freqs, look_ahead=self.look_ahead, fb_num_neighbors=self.fb_num_neighbors,
+            sb_num_neighbors=self.sb_num_neighbors, fb_hidden=self.fb_model.hidden_size,
+            sb_hidden=self.sb_model.hidden_size, fb_activation=_lib.ACT[self.fb_model.output_activate_function],
+            sb_activation=_lib.ACT[self.sb_model.output_activate_function], norm_type=self.norm,
+            num_groups_in_drop_band=num_groups, precision=_lib.PREC[precision], reserved=0)
+
+    def _packed_sb(self, desc, sb_w, device):
+        """Tile-ordered fp16 image of the sub-band weights, rebuilt when any parameter changes."""
+        key = (self.sb_model.version_key(), str(device))
+        if self._packed is None or self._packed_key != key:
+            lib = _lib.load()
+            n = lib.fsn_sb_packed_bytes(C.byref(desc))
+            buf = torch.empty(n, dtype=torch.uint8, device=device)
+            _lib.check(lib.fsn_pack_sb_weights(C.byref(desc), C.byref(sb_w), buf.data_ptr(), _lib.stream_ptr(device)))
+            self._packed, self._packed_key = buf, key
+        return self._packed
+
+    def _prepare(self, device, num_groups):
+        prec = self._resolve_precision()
+        desc = self._desc(prec, num_groups)
+        fb_w, sb_w = self.fb_model.weight_struct(), self.sb_model.weight_struct()
+        packed = self._packed_sb(desc, sb_w, device) if prec == "f16_tc" else None
+        return desc, fb_w, sb_w, packed
+
+    # ---------------------------------------------------------------- reference API
+    def forward(self, noisy_mag):
+        """noisy_mag [B,1,F,T] -> [B,2,F,T]  (or [B,2,F//G,T], batch order 0,2,4,..,1,3,5,.. when B>1, G>1)."""
+        assert noisy_mag.dim() == 4
+        batch_size, num_channels, num_freqs, num_frames = noisy_mag.size()
+        assert num_channels == 1, f"{self.__class__.__name__} takes the mag feature as inputs."
+        assert num_freqs == self.num_freqs, f"num_freqs {num_freqs} != {self.num_freqs}"
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "fullsubnet_b200: the backward (BPTT) kernels are not built yet; call under torch.no_grad() / "
+                "model.eval().  (SURVEY 8a row A11, next round)")
+        x = _lib.require_cuda(noisy_mag, "noisy_mag")
+        device = x.device
+        lib = _lib.load()
+        with torch.cuda.device(device):
+            desc, fb_w, sb_w, packed = self._prepare(device, int(self.num_groups_in_drop_band))
+            G = desc.num_groups_in_drop_band if batch_size > 1 and desc.num_groups_in_drop_band > 1 else 1
+            f_out = num_freqs // G if G > 1 else num_freqs
+            ws_bytes = lib.fsn_model_workspace_bytes(C.byref(desc), batch_size, num_frames)
+            if ws_bytes == 0:
+                _lib.check(_lib.FSN_ERR_SHAPE)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+            out = torch.empty(batch_size, 2, f_out, num_frames, dtype=torch.float32, device=device)
+            _lib.check(lib.fsn_model_forward(C.byref(desc), C.byref(fb_w), C.byref(sb_w), _lib.ptr(packed),
+                                             x.data_ptr(), batch_size, num_frames, out.data_ptr(), ws.data_ptr(),
+                                             ws_bytes, _lib.stream_ptr(device)))
+        return out
+
+    @torch.no_grad()
+    def enhance(self, noisy, n_fft=512, hop_length=256, win_length=512, return_crm=False):
+        """Fused wav -> wav path of Inferencer.full_band_crm_mask (recipes/.../inferencer.py:130-145),
+        batched over independent clips: noisy [B,L] -> enhanced [B,L]."""
+        assert noisy.dim() == 2, "noisy must be [B, L]"
+        x = _lib.require_cuda(noisy, "noisy")
+        B, L = x.shape
+        device = x.device
+        lib = _lib.load()
+        with torch.cuda.device(device):
+            desc, fb_w, sb_w, packed = self._prepare(device, 1)
+            ws_bytes = lib.fsn_enhance_workspace_bytes(C.byref(desc), B, L, n_fft, hop_length)
+            if ws_bytes == 0:
+                _lib.check(_lib.FSN_ERR_SHAPE)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+            out = torch.empty(B, L, dtype=torch.float32, device=device)
+            crm = torch.empty(B, 2, n_fft // 2 + 1, 1 + L // hop_length, dtype=torch.float32,
+                              device=device) if return_crm else None
+            _lib.check(lib.fsn_enhance(C.byref(desc), C.byref(fb_w), C.byref(sb_w), _lib.ptr(packed), x.data_ptr(),
+                                       B, L, n_fft, hop_length, win_length, out.data_ptr(), _lib.ptr(crm),
+                                       ws.data_ptr(), ws_bytes, _lib.stream_ptr(device)))
+        return (out, crm) if return_crm else out

@@ -1,0 +1,60 @@
+"""Parameter container mirroring audio_zen/model/module/sequence_model.py:26-125.
+
+The ``nn.LSTM`` / ``nn.Linear`` members exist only to own the parameters with PyTorch's names,
+shapes and default initialisation, so ``state_dict`` keys (``sequence_model.weight_ih_l0`` ...,
+``fc_output_layer.weight``), checkpoints, ``torch.optim.Adam`` and DDP behave exactly as with the
+reference.  Their ``forward`` is never called: the arithmetic runs in libfsn_b200."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from ... import _lib
+
+
+class SequenceModel(nn.Module):
+    def __init__(self, input_size, output_size, hidden_size, num_layers, bidirectional,
+                 sequence_model="GRU", output_activate_function="Tanh"):
+        super().__init__()
+        if sequence_model == "LSTM":
+            self.sequence_model = nn.LSTM(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers,
+                                          batch_first=True, bidirectional=bidirectional)
+        else:
+            # sequence_model.py:59-79: GRU exists upstream; this build covers the LSTM configs only
+            raise NotImplementedError(f"Not implemented {sequence_model}")
+        if bidirectional or num_layers != 2:
+            raise NotImplementedError("libfsn_b200 builds the uni-directional 2-layer LSTM stack of FullSubNet")
+        if not int(output_size):
+            raise NotImplementedError("libfsn_b200 expects the Linear output layer (output_size > 0)")
+        self.fc_output_layer = nn.Linear(hidden_size, output_size)
+        if output_activate_function:
+            if output_activate_function not in ("Tanh", "ReLU", "ReLU6"):
+                raise NotImplementedError(f"Not implemented activation function {output_activate_function}")
+        self.output_activate_function = output_activate_function
+        self.output_size = output_size
+        self.input_size, self.hidden_size = input_size, hidden_size
+
+    def weight_struct(self) -> "_lib.SeqWeights":
+        """Raw device pointers into the parameter storage (fsn_seq_weights)."""
+        w = _lib.SeqWeights()
+        lstm = self.sequence_model
+        for l in range(2):
+            for field, name in (("w_ih", "weight_ih"), ("w_hh", "weight_hh"), ("b_ih", "bias_ih"), ("b_hh", "bias_hh")):
+                p = getattr(lstm, f"{name}_l{l}")
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError(f"fullsubnet_b200: parameter {name}_l{l} must be a contiguous fp32 CUDA tensor "
+                                       f"(got {p.device}, {p.dtype}); call model.cuda() first - there is no CPU path.")
+                getattr(w, field)[l] = p.data_ptr()
+        for field, p in (("fc_w", self.fc_output_layer.weight), ("fc_b", self.fc_output_layer.bias)):
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("fullsubnet_b200: fc_output_layer parameters must be contiguous fp32 CUDA tensors")
+            setattr(w, field, p.data_ptr())
+        return w
+
+    def version_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def forward(self, x):  # pragma: no cover - never on the product path
+        raise RuntimeError("SequenceModel is a parameter container in fullsubnet_b200; call Model.forward")

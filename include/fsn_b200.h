@@ -1,0 +1,157 @@
+/*
+ * fsn_b200.h - C ABI of libfsn_b200.so: the B200 (sm_100a) implementation of FullSubNet's
+ * enhancement hot path.
+ *
+ * The reference (Audio-WestlakeU/FullSubNet) is pure Python and has no FFI; its "operator"
+ * boundary is the set of Python callables listed below.  Each entry point here replaces the
+ * device work of one of them and is what `fullsubnet_b200/` (the Python host mirroring the
+ * reference API) binds through ctypes.  Paths are relative to the upstream repository.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 unless noted; the caller allocates
+ *     all buffers including the workspace; the library never allocates, frees or retains
+ *     pointers across calls and keeps no mutable global state (re-entrant across streams);
+ *   - `stream` is a cudaStream_t; nothing synchronises the host;
+ *   - return value 0 = ok, non-zero = error; fsn_last_error() gives a thread-local message.
+ *     Shape-contract violations that are AssertionError / NotImplementedError in the reference
+ *     come back as FSN_ERR_SHAPE / FSN_ERR_UNSUPPORTED and the Python host re-raises them as
+ *     the reference's exception types.
+ */
+#ifndef FSN_B200_H
+#define FSN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fsn_stream_t; /* cudaStream_t */
+
+enum {
+  FSN_OK = 0,
+  FSN_ERR_SHAPE = 1,       /* reference: AssertionError */
+  FSN_ERR_UNSUPPORTED = 2, /* reference: NotImplementedError */
+  FSN_ERR_CUDA = 3,
+  FSN_ERR_WORKSPACE = 4
+};
+
+enum { FSN_ACT_NONE = 0, FSN_ACT_RELU = 1, FSN_ACT_TANH = 2, FSN_ACT_RELU6 = 3 };
+enum { FSN_NORM_OFFLINE_LAPLACE = 0 };
+/* arithmetic of the sub-band LSTM stack (99 % of the FLOPs):
+ *   FSN_PREC_FP32     - fp32 FMA everywhere (bit-for-bit class of the reference CPU path, ~1e-6)
+ *   FSN_PREC_F16_TC   - fp16 operands (11-bit significand, like TF32) x fp32 accumulate on the
+ *                       tcgen05 tensor cores, fp32 cell state; cRM within 1e-3 rel (tests) */
+enum { FSN_PREC_FP32 = 0, FSN_PREC_F16_TC = 1 };
+
+int fsn_version(void);
+const char* fsn_last_error(void);
+/* compile-time facts for the host (sm arch the kernels were built for, e.g. 100) */
+int fsn_built_arch(void);
+
+/* ------------------------------------------------------------------------------------------
+ * audio_zen/acoustics/feature.py:9-50  stft(y, n_fft, hop_length, win_length)
+ *   wav [B,L] -> mag, phase, real, imag, each [B,F,T]; F = n_fft/2+1, T = 1 + L/hop.
+ *   torch.stft semantics: center=True reflect pad n_fft/2, periodic hann (zero-padded to n_fft
+ *   when win_length < n_fft), one-sided, un-normalised.  `phase` may be NULL (not computed).
+ *   `magT` (optional, may be NULL): a second, time-major copy [B, T_pad, F] with rows
+ *   T..T_pad-1 zeroed - the layout the model kernels consume (look-ahead pad fused,
+ *   recipes/dns_interspeech_2020/fullsubnet/model.py:85).
+ * ---------------------------------------------------------------------------------------- */
+int fsn_stft(const float* wav, int B, int L, int n_fft, int hop, int win_length,
+             float* mag, float* phase, float* real, float* imag,
+             float* magT, int T_pad, fsn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * audio_zen/acoustics/feature.py:53-91  istft(features, n_fft, hop, win, length, input_type)
+ *   real/imag [B,F,T] with element stride `cstride` (1 = planar "real_imag", 2 = interleaved
+ *   complex64) -> wav [B,out_len].  torch.istft semantics: irfft (1/N), window, overlap-add,
+ *   divide by the window-square envelope, trim n_fft/2, cut/zero-pad to `length`
+ *   (length <= 0: hop*(T-1)).
+ *   If `crm` != NULL ([B,2,F,T], recipes/dns_interspeech_2020/inferencer.py:130-145) the
+ *   spectrum is first multiplied by decompress_cIRM(crm) (audio_zen/acoustics/mask.py:47-64,
+ *   K=10, limit=9.9) as a complex mask - rows A9 of SURVEY 8a in one kernel.
+ * ---------------------------------------------------------------------------------------- */
+int fsn_istft(const float* real, const float* imag, int cstride, const float* crm,
+              int B, int T, int n_fft, int hop, int win_length, int length,
+              float* wav, fsn_stream_t stream);
+
+/* audio_zen/acoustics/mask.py:47-64 / :32-44 / :7-29 (elementwise, n = number of elements) */
+int fsn_decompress_cirm(const float* in, float* out, int64_t n, float K, float limit, fsn_stream_t stream);
+int fsn_compress_cirm(const float* in, float* out, int64_t n, float K, float C, fsn_stream_t stream);
+/* noisy/clean real/imag [n] -> cIRM [n,2] (compressed, K=10, C=0.1) */
+int fsn_build_cirm(const float* nr, const float* ni, const float* cr, const float* ci,
+                   float* out, int64_t n, fsn_stream_t stream);
+/* audio_zen/acoustics/feature.py:309-345  drop_band: in [B,C,F,T] -> out [B,C,F/G,T] */
+int fsn_drop_band(const float* in, float* out, int B, int C, int F, int T, int G, fsn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * recipes/dns_interspeech_2020/fullsubnet/model.py:9-136  Model
+ * ---------------------------------------------------------------------------------------- */
+typedef struct fsn_model_desc {
+  int32_t num_freqs;        /* F */
+  int32_t look_ahead;
+  int32_t fb_num_neighbors; /* Nf */
+  int32_t sb_num_neighbors; /* Ns */
+  int32_t fb_hidden;        /* 512 */
+  int32_t sb_hidden;        /* 384 */
+  int32_t fb_activation;    /* FSN_ACT_* (fb_output_activate_function) */
+  int32_t sb_activation;    /* FSN_ACT_* (sb_output_activate_function) */
+  int32_t norm_type;        /* FSN_NORM_* */
+  int32_t num_groups_in_drop_band; /* applied when B > 1 (model.py:114), 1 = off */
+  int32_t precision;        /* FSN_PREC_* for the sub-band stack */
+  int32_t reserved;
+} fsn_model_desc;
+
+/* One SequenceModel (audio_zen/model/module/sequence_model.py:26-125): 2-layer nn.LSTM +
+ * Linear, PyTorch parameter layout (gate order i,f,g,o; weight [4H,K] row-major).  Pointers
+ * go straight into the nn.Parameter storage so Adam / checkpoints / DDP keep working. */
+typedef struct fsn_seq_weights {
+  const float* w_ih[2];
+  const float* w_hh[2];
+  const float* b_ih[2];
+  const float* b_hh[2];
+  const float* fc_w; /* [out, H] */
+  const float* fc_b; /* [out] */
+} fsn_seq_weights;
+
+/* bytes of caller-provided scratch for fsn_model_forward / fsn_enhance at batch B, T frames */
+size_t fsn_model_workspace_bytes(const fsn_model_desc* d, int B, int T);
+
+/* FSN_PREC_F16_TC only: bytes of, and packer for, the tile-ordered fp16 image of the sub-band
+ * weights that the tcgen05 kernel streams (cache it keyed on the parameters' version). */
+size_t fsn_sb_packed_bytes(const fsn_model_desc* d);
+int fsn_pack_sb_weights(const fsn_model_desc* d, const fsn_seq_weights* sb, void* packed, fsn_stream_t stream);
+
+/* Model.forward (model.py:72-136): noisy_mag [B,1,F,T] -> crm [B,2,F',T]
+ *   F' = F, or F/G with the drop_band batch permutation when B > 1 and G > 1.
+ *   sb_packed: NULL for FSN_PREC_FP32. */
+int fsn_model_forward(const fsn_model_desc* d, const fsn_seq_weights* fb, const fsn_seq_weights* sb,
+                      const void* sb_packed, const float* noisy_mag, int B, int T, float* crm,
+                      void* workspace, size_t workspace_bytes, fsn_stream_t stream);
+
+/* recipes/dns_interspeech_2020/inferencer.py:130-145  Inferencer.full_band_crm_mask, batched
+ * over independent clips (drop_band off): wav [B,L] -> enhanced [B,L]; crm_out (optional,
+ * [B,2,F,T]) receives the mask.  One call = stft -> model -> decompress/mask -> istft. */
+size_t fsn_enhance_workspace_bytes(const fsn_model_desc* d, int B, int L, int n_fft, int hop);
+int fsn_enhance(const fsn_model_desc* d, const fsn_seq_weights* fb, const fsn_seq_weights* sb,
+                const void* sb_packed, const float* wav, int B, int L, int n_fft, int hop, int win_length,
+                float* enhanced, float* crm_out, void* workspace, size_t workspace_bytes,
+                fsn_stream_t stream);
+
+/* Opt-in stage timing for bench.py: when enabled, fsn_model_forward / fsn_enhance bracket their
+ * stages with CUDA events on `stream` (thread-local, created lazily).  After the caller has
+ * synchronised the stream, fsn_last_stage_ms(stage) returns the device time of the last call:
+ * stage 0 = stft (or mag transpose), 1 = norms + full-band stack, 2 = sub-band stack, 3 = mask+istft. */
+int fsn_set_profiling(int enable);
+float fsn_last_stage_ms(int stage);
+
+/* number of kernel launches issued by the last fsn_model_forward / fsn_enhance on this thread
+ * (bench.py reports it as gpu_launches) */
+int64_t fsn_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSN_B200_H */

@@ -1,0 +1,96 @@
+"""CPU-only checks: the C-ABI library builds, loads and exports every symbol declared in
+include/fsn_b200.h; host-side logic (state_dict contract, error behaviour, sharding)."""
+import os
+import re
+import shutil
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from fullsubnet_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+            pytest.skip("no nvcc and no prebuilt library")
+        from fullsubnet_b200.csrc.build import build
+        build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from fullsubnet_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "fsn_b200.h")).read()
+    declared = set(re.findall(r"\b(fsn_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.fsn_version() >= 100
+    assert lib.fsn_built_arch() == 100  # compiled for sm_100a
+
+
+def test_workspace_queries_need_no_gpu(lib):
+    import ctypes as C
+    from fullsubnet_b200 import _lib
+    d = _lib.ModelDesc(257, 2, 0, 15, 512, 384, 1, 0, 0, 2, 0, 0)
+    n1 = lib.fsn_model_workspace_bytes(C.byref(d), 1, 251)
+    n8 = lib.fsn_model_workspace_bytes(C.byref(d), 8, 251)
+    assert 0 < n1 < n8
+    assert lib.fsn_enhance_workspace_bytes(C.byref(d), 2, 64000, 512, 256) > n1
+    # B == num_groups violates the reference's drop_band assertion (feature.py:317-319)
+    assert lib.fsn_model_workspace_bytes(C.byref(d), 2, 251) == 0
+    assert b"Batch size = 2" in lib.fsn_last_error()
+
+
+def test_state_dict_contract_matches_reference():
+    from fullsubnet_b200.fullsubnet.model import Model
+    from oracle import fullsubnet_oracle as O
+    m = Model(**O.DEFAULT_MODEL_ARGS)
+    sd = m.state_dict()
+    want = O.state_dict_shapes()
+    assert list(sd.keys()) == [k for k, _ in want]
+    assert [tuple(v.shape) for v in sd.values()] == [s for _, s in want]
+    assert sum(v.numel() for v in sd.values()) == 5637635  # SURVEY: "5.6 M"
+    # reference checkpoints (incl. DDP 'module.' prefix handling of base_inferencer.py:154-156) load strictly
+    ref_sd = {"module." + k: v for k, v in O.make_state_dict(0).items()}
+    m.load_state_dict({k.replace("module.", ""): v for k, v in ref_sd.items()}, strict=True)
+    assert m.num_groups_in_drop_band == 2 and hasattr(m, "fb_model") and hasattr(m, "sb_model")
+    # usable by the reference's optimizer / clip path (train.py:55-59, trainer.py:65-67)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, betas=(0.9, 0.999))
+    assert len(opt.param_groups[0]["params"]) == 20
+
+
+def test_host_error_behaviour_matches_reference():
+    from fullsubnet_b200.fullsubnet.model import Model
+    from fullsubnet_b200.acoustics import feature
+    from oracle import fullsubnet_oracle as O
+    with pytest.raises(AssertionError):
+        Model(**dict(O.DEFAULT_MODEL_ARGS, sequence_model="SRU"))
+    with pytest.raises(NotImplementedError):
+        Model(**dict(O.DEFAULT_MODEL_ARGS, norm_type="bogus"))
+    m = Model(**O.DEFAULT_MODEL_ARGS).eval()
+    with pytest.raises(AssertionError):
+        m(torch.zeros(1, 257, 5))  # model.py:84
+    with pytest.raises(AssertionError):
+        m(torch.zeros(1, 2, 257, 5))  # model.py:87-89
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 1, 257, 5))  # no silent CPU fallback
+    with pytest.raises(AssertionError):
+        feature.stft(torch.zeros(4), 512, 256, 512)  # feature.py:25
+    with pytest.raises(AssertionError):
+        feature.drop_band(torch.zeros(2, 1, 8, 3), 2)  # feature.py:317-319
+    with pytest.raises(NotImplementedError):
+        feature.istft((torch.zeros(1, 257, 3), torch.zeros(1, 257, 3)), 512, 256, 512, input_type="bogus")
+
+
+def test_initialize_module_plugin_mechanism():
+    from fullsubnet_b200.utils import initialize_module
+    from oracle import fullsubnet_oracle as O
+    m = initialize_module("fullsubnet_b200.fullsubnet.model.Model", args=dict(O.DEFAULT_MODEL_ARGS))
+    assert type(m).__name__ == "Model"
+    cls = initialize_module("fullsubnet_b200.inferencer.Inferencer", initialize=False)
+    assert cls.__name__ == "Inferencer"

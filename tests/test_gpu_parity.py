@@ -1,0 +1,160 @@
+"""GPU parity: libfsn_b200 (through the reference-API host) vs. the golden fixtures produced by
+the unmodified reference and vs. the oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): cRM <= 1e-3 relative to max|ref| (and rel-L2 <= 1e-3);
+enhanced waveform <= 1e-4 absolute.  The fp32 path is held to much tighter bounds."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_max, rel_l2, WB_GAIN
+
+pytestmark = pytest.mark.gpu
+
+CRM_TOL = 1e-3
+WAV_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def T(x, dev):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+def small_args():
+    return dict(num_freqs=33, look_ahead=2, sequence_model="LSTM", fb_num_neighbors=0, sb_num_neighbors=3,
+                fb_output_activate_function="ReLU", sb_output_activate_function=False,
+                fb_model_hidden_size=32, sb_model_hidden_size=24, norm_type="offline_laplace_norm",
+                num_groups_in_drop_band=2, weight_init=False)
+
+
+def make_model(args, sd, dev, precision):
+    from fullsubnet_b200.fullsubnet.model import Model
+    m = Model(**args, precision=precision)
+    m.load_state_dict(sd, strict=True)
+    return m.to(dev).eval()
+
+
+# ------------------------------------------------------------------ A1 / A9: STFT, iSTFT
+def test_stft_matches_reference(golden, dev):
+    from fullsubnet_b200.acoustics.feature import stft
+    g = golden("dsp")
+    mag, phase, real, imag = stft(T(g["y"], dev), 512, 256, 512)
+    assert mag.shape == g["mag"].shape
+    assert rel_max(real.cpu(), g["real"]) < 5e-6 and rel_max(imag.cpu(), g["imag"]) < 5e-6
+    assert rel_max(mag.cpu(), g["mag"]) < 5e-6
+    sel = g["mag"] > 1e-2 * g["mag"].max()
+    d = np.angle(np.exp(1j * (phase.cpu().numpy() - g["phase"])))
+    assert np.abs(d[sel]).max() < 1e-4
+    mag3 = stft(T(g["y3"], dev), 512, 256, 512)[0]  # [B,C,T] input (feature.py:30-31,43-44)
+    assert mag3.shape == g["mag3"].shape and rel_max(mag3.cpu(), g["mag3"]) < 5e-6
+    _, _, rs, is_ = stft(T(g["y"], dev), 64, 32, 64)
+    assert rel_max(rs.cpu(), g["real_s"]) < 5e-6 and rel_max(is_.cpu(), g["imag_s"]) < 5e-6
+
+
+def test_istft_matches_reference(golden, dev):
+    from fullsubnet_b200.acoustics.feature import istft
+    g = golden("dsp")
+    L = g["y"].shape[-1]
+    w = istft((T(g["real"], dev), T(g["imag"], dev)), 512, 256, 512, length=L, input_type="real_imag")
+    assert rel_max(w.cpu(), g["wav_rt"]) < 1e-5
+    w2 = istft(torch.complex(T(g["real"], dev), T(g["imag"], dev)), 512, 256, 512)
+    assert w2.shape == g["wav_nolen"].shape and rel_max(w2.cpu(), g["wav_nolen"]) < 1e-5
+    mag = np.hypot(g["real"], g["imag"]).astype(np.float32)
+    w3 = istft((T(mag, dev), T(g["phase"], dev)), 512, 256, 512, length=L, input_type="mag_phase")
+    assert rel_max(w3.cpu(), g["wav_rt"]) < 1e-5
+    w4 = istft((T(g["real_s"], dev), T(g["imag_s"], dev)), 64, 32, 64, length=L, input_type="real_imag")
+    assert rel_max(w4.cpu(), g["wav_s"]) < 1e-5
+
+
+@pytest.mark.parametrize("L", [257, 511, 4096, 64000])
+def test_stft_istft_roundtrip_and_oracle(dev, L):
+    from fullsubnet_b200.acoustics.feature import stft, istft
+    from oracle import fullsubnet_oracle as O
+    y = O.make_noisy(2, L, seed=L)
+    mag, _, re, im = stft(y.to(dev), 512, 256, 512)
+    om, _, ore, oim = O.stft(y, 512, 256, 512)
+    assert mag.shape == om.shape
+    assert rel_max(re.cpu(), ore) < 5e-6 and rel_max(im.cpu(), oim) < 5e-6 and rel_max(mag.cpu(), om) < 5e-6
+    back = istft((re, im), 512, 256, 512, length=L, input_type="real_imag")
+    assert np.abs(back.cpu().numpy() - y.numpy()).max() < 5e-6  # size-independent property: identity
+
+
+# ------------------------------------------------------------------ masks, drop_band
+def test_masks_and_drop_band_match_reference(golden, dev):
+    from fullsubnet_b200.acoustics import mask, feature
+    g = golden("dsp")
+    assert rel_max(mask.decompress_cIRM(T(g["m"], dev)).cpu(), g["dec"]) < 2e-6
+    assert rel_max(mask.compress_cIRM(T(g["big"], dev)).cpu(), g["comp"]) < 2e-6
+    _, _, cr, ci = feature.stft(T(g["yc"], dev), 512, 256, 512)
+    cirm = mask.build_complex_ideal_ratio_mask(T(g["real"], dev), T(g["imag"], dev), cr, ci)
+    assert cirm.shape == g["cirm"].shape
+    assert np.abs(cirm.cpu().numpy() - g["cirm"]).max() < 5e-3  # ill-conditioned where |noisy| ~ 0
+    assert np.median(np.abs(cirm.cpu().numpy() - g["cirm"])) < 1e-5
+    assert np.array_equal(feature.drop_band(T(g["xb"], dev), 2).cpu().numpy(), g["db2"])  # bit-exact index op
+    assert np.array_equal(feature.drop_band(T(g["xb"], dev), 3).cpu().numpy(), g["db3"])
+    nan = torch.tensor([float("nan"), 20.0, -20.0, 0.0], device=dev)
+    ref = np.array([0.0, 52.93305, -52.93305, 0.0], dtype=np.float32)
+    assert np.allclose(mask.decompress_cIRM(nan).cpu().numpy(), ref, rtol=1e-5)
+
+
+# ------------------------------------------------------------------ Model.forward
+@pytest.mark.parametrize("precision", ["fp32"])
+def test_small_model_matches_reference(golden, dev, precision):
+    g = golden("model_small")
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    m = make_model(small_args(), sd, dev, precision)
+    mag = T(g["mag"], dev).unsqueeze(1)
+    with torch.no_grad():
+        assert rel_max(m(mag[:1]).cpu(), g["crm_b1"]) < 2e-5
+        out = m(mag)  # B=3 -> drop_band G=2, batch order [0,2,1], 16 of 33 bins
+        assert out.shape == g["crm_g2"].shape
+        assert rel_max(out.cpu(), g["crm_g2"]) < 2e-5
+        m.num_groups_in_drop_band = 1
+        assert rel_max(m(mag).cpu(), g["crm_g1"]) < 2e-5
+        m.num_groups_in_drop_band = 3
+        with pytest.raises(AssertionError):
+            m(mag)  # B == G (feature.py:317-319)
+
+
+def _full_model(dev, gain, precision):
+    from oracle import fullsubnet_oracle as O
+    return make_model(dict(O.DEFAULT_MODEL_ARGS), O.make_state_dict(seed=0, sb_fc_gain=gain), dev, precision)
+
+
+@pytest.mark.parametrize("precision,crm_tol", [("fp32", 5e-5)])
+@pytest.mark.parametrize("tag,gain", [("wa", 1.0), ("wb", WB_GAIN)])
+def test_full_model_and_inferencer_match_reference(golden, dev, tag, gain, precision, crm_tol):
+    from fullsubnet_b200.acoustics.feature import stft
+    from fullsubnet_b200.inferencer import Inferencer
+    g = golden("model_full")
+    m = _full_model(dev, gain, precision)
+    y = T(g["y"], dev)
+    ref_crm, ref_wav = g[f"{tag}_crm"], g[f"{tag}_wav"]
+    with torch.no_grad():
+        mag = stft(y, 512, 256, 512)[0]
+        crm = torch.cat([m(mag[i:i + 1].unsqueeze(1)) for i in range(2)], 0)
+    assert rel_max(crm.cpu(), ref_crm) < crm_tol and rel_l2(crm.cpu(), ref_crm) < crm_tol
+    inf = Inferencer(model=m, device=dev)
+    wav = np.stack([inf.full_band_crm_mask(y[i:i + 1], {}) for i in range(2)])  # op-by-op reference flow
+    scale = max(1.0, float(np.abs(ref_wav).max()))
+    assert np.abs(wav - ref_wav).max() < WAV_TOL * scale
+    fused, crm2 = m.enhance(y, return_crm=True)  # one fsn_enhance call, batched
+    assert rel_max(crm2.cpu(), ref_crm) < crm_tol
+    assert np.abs(fused.cpu().numpy() - ref_wav).max() < WAV_TOL * scale
+
+
+def test_batched_equals_loop_of_single_clips(dev):
+    """batched inference == loop of B=1 calls (drop_band off)."""
+    from oracle import fullsubnet_oracle as O
+    m = _full_model(dev, 1.0, "fp32")
+    y = O.make_noisy(3, 4000, seed=11, speechlike=True).to(dev)
+    batched = m.enhance(y)
+    single = torch.cat([m.enhance(y[i:i + 1]) for i in range(3)], 0)
+    assert np.abs(batched.cpu().numpy() - single.cpu().numpy()).max() < 2e-6
+    ref = O.enhance(y.cpu(), O.make_state_dict(0))
+    assert np.abs(batched.cpu().numpy() - ref.numpy()).max() < 2e-5

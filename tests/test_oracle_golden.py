@@ -1,0 +1,110 @@
+"""CPU: the oracle restatement vs. fixtures produced by the unmodified reference
+(oracle/make_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fullsubnet_oracle as O
+from conftest import rel_max, WB_GAIN
+
+T = torch.from_numpy
+
+
+def test_stft_matches_reference(golden):
+    g = golden("dsp")
+    mag, phase, real, imag = O.stft(T(g["y"]), 512, 256, 512)
+    assert mag.shape == g["mag"].shape
+    assert rel_max(real, g["real"]) < 2e-6 and rel_max(imag, g["imag"]) < 2e-6
+    assert rel_max(mag, g["mag"]) < 2e-6
+    # phase only where the magnitude is not tiny
+    sel = g["mag"] > 1e-2 * g["mag"].max()
+    d = np.angle(np.exp(1j * (phase.numpy() - g["phase"])))
+    assert np.abs(d[sel]).max() < 1e-4
+    mag3 = O.stft(T(g["y3"]), 512, 256, 512)[0]
+    assert mag3.shape == g["mag3"].shape and rel_max(mag3, g["mag3"]) < 2e-6
+    ms, _, rs, is_ = O.stft(T(g["y"]), 64, 32, 64)
+    assert rel_max(rs, g["real_s"]) < 2e-6 and rel_max(is_, g["imag_s"]) < 2e-6
+
+
+def test_istft_matches_reference(golden):
+    g = golden("dsp")
+    w = O.istft((T(g["real"]), T(g["imag"])), 512, 256, 512, length=g["y"].shape[-1], input_type="real_imag")
+    assert rel_max(w, g["wav_rt"]) < 5e-6
+    assert rel_max(w, g["y"]) < 5e-6  # round trip
+    w2 = O.istft(torch.complex(T(g["real"]), T(g["imag"])), 512, 256, 512)
+    assert w2.shape == g["wav_nolen"].shape and rel_max(w2, g["wav_nolen"]) < 5e-6
+    w3 = O.istft((T(g["real_s"]), T(g["imag_s"])), 64, 32, 64, length=g["y"].shape[-1], input_type="real_imag")
+    assert rel_max(w3, g["wav_s"]) < 5e-6
+    with pytest.raises(NotImplementedError):
+        O.istft((T(g["real"]), T(g["imag"])), 512, 256, 512, input_type="bogus")
+
+
+def test_masks_match_reference(golden):
+    g = golden("dsp")
+    assert rel_max(O.decompress_cIRM(T(g["m"])), g["dec"]) < 1e-6
+    assert rel_max(O.compress_cIRM(T(g["big"])), g["comp"]) < 1e-6
+    _, _, cr, ci = O.stft(T(g["yc"]), 512, 256, 512)
+    cirm = O.build_complex_ideal_ratio_mask(T(g["real"]), T(g["imag"]), cr, ci)
+    assert cirm.shape == g["cirm"].shape
+    assert np.abs(cirm.numpy() - g["cirm"]).max() < 2e-3  # cIRM is ill-conditioned where |noisy|~0
+
+
+def test_drop_band_matches_reference(golden):
+    g = golden("dsp")
+    assert np.array_equal(O.drop_band(T(g["xb"]), 2).numpy(), g["db2"])
+    assert np.array_equal(O.drop_band(T(g["xb"]), 3).numpy(), g["db3"])
+    sb, sf = O.drop_band_index_map(5, 9, 2)
+    x = g["xb"]
+    rebuilt = np.stack([x[b][:, f, :] for b, f in zip(sb, sf)])
+    assert np.array_equal(rebuilt, g["db2"])
+    with pytest.raises(AssertionError):
+        O.drop_band(T(g["xb"][:2]), 2)
+
+
+def _small_args():
+    return dict(num_freqs=33, look_ahead=2, sequence_model="LSTM", fb_num_neighbors=0, sb_num_neighbors=3,
+                fb_output_activate_function="ReLU", sb_output_activate_function=False,
+                fb_model_hidden_size=32, sb_model_hidden_size=24, norm_type="offline_laplace_norm",
+                num_groups_in_drop_band=2, weight_init=False)
+
+
+def test_small_model_matches_reference(golden):
+    g = golden("model_small")
+    sd = {k[3:]: T(g[k]) for k in g.files if k.startswith("sd.")}
+    a = _small_args()
+    regen = O.make_state_dict(seed=7, args=a)
+    for k in sd:
+        assert torch.equal(sd[k], regen[k]), k  # weight generator is version-stable
+    mag = T(g["mag"]).unsqueeze(1)
+    assert rel_max(O.model_forward(mag[:1], sd, a), g["crm_b1"]) < 1e-5
+    assert rel_max(O.model_forward(mag, sd, a), g["crm_g2"]) < 1e-5
+    a1 = dict(a, num_groups_in_drop_band=1)
+    out, mid = O.model_forward(mag, sd, a1, return_intermediates=True)
+    assert rel_max(out, g["crm_g1"]) < 1e-5
+    assert rel_max(mid["fb_output"][:, 0], g["fb_out"]) < 1e-5
+
+
+def test_full_model_and_inferencer_match_reference(golden):
+    g = golden("model_full")
+    y = T(g["y"])
+    for tag, gain in (("wa", 1.0), ("wb", WB_GAIN)):
+        sd = O.make_state_dict(seed=0, sb_fc_gain=gain)
+        wav, crm = O.enhance(y, sd, batched=True, return_crm=True)
+        assert rel_max(crm, g[f"{tag}_crm"]) < 2e-5, tag
+        assert np.abs(wav.numpy() - g[f"{tag}_wav"]).max() < 2e-5 * max(1.0, np.abs(g[f"{tag}_wav"]).max()), tag
+        wav1 = O.enhance(y, sd, batched=False)
+        assert np.abs(wav1.numpy() - g[f"{tag}_wav"]).max() < 2e-5 * max(1.0, np.abs(g[f"{tag}_wav"]).max())
+    assert np.abs(g["wb_crm"]).max() > 9.9  # the wb set exercises the clip of decompress_cIRM
+
+
+def test_reflect_count_closed_form():
+    c = O.reflect_count(257, 15)
+    assert c.sum() == 257 * 31 and c[0] == 16 and c[256] == 16
+    assert (c[1:16] == 32).all() and (c[241:256] == 32).all() and (c[16:241] == 31).all()
+    # closed form of the 2nd laplace norm mean
+    mag = torch.rand(2, 1, 257, 9)
+    fb = torch.rand(2, 1, 257, 9)
+    cat = torch.cat([O.freq_unfold(mag, 15).reshape(2, 257, 31, 9), O.freq_unfold(fb, 0).reshape(2, 257, 1, 9)], 2)
+    mu = cat.mean(dim=(1, 2, 3))
+    closed = ((mag[:, 0].sum(-1) * torch.from_numpy(c).float()).sum(-1) + fb.sum(dim=(1, 2, 3))) / (257 * 32 * 9)
+    assert rel_max(closed, mu) < 1e-5
