@@ -232,9 +232,11 @@ def lstm_stack(x: torch.Tensor, sd: Dict[str, torch.Tensor], prefix: str, num_la
         h = torch.zeros(B, H)
         c = torch.zeros(B, H)
         outs = []
-        xin = rnd(inp)
+        # input projection for every step at once (it does not depend on the recurrence), as ATen's
+        # CPU LSTM does; the recurrent half stays a serial loop over t
+        xproj = torch.addmm(bias, rnd(inp).reshape(B * T, -1), w_ih).reshape(B, T, 4 * H)
         for t in range(T):
-            g = torch.addmm(bias, xin[:, t], w_ih) + rnd(h) @ w_hh
+            g = torch.addmm(xproj[:, t], rnd(h), w_hh)
             i, f, gg, o = g.split(H, dim=1)
             c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
             h = torch.sigmoid(o) * torch.tanh(c)

@@ -79,7 +79,10 @@ def test_stft_istft_roundtrip_and_oracle(dev, L):
     mag, _, re, im = stft(y.to(dev), 512, 256, 512)
     om, _, ore, oim = O.stft(y, 512, 256, 512)
     assert mag.shape == om.shape
-    assert rel_max(re.cpu(), ore) < 5e-6 and rel_max(im.cpu(), oim) < 5e-6 and rel_max(mag.cpu(), om) < 5e-6
+    scale = float(om.max())  # Im can be identically ~0 (L=257: the reflect-padded frame is symmetric)
+    assert np.abs(re.cpu().numpy() - ore.numpy()).max() < 5e-6 * scale
+    assert np.abs(im.cpu().numpy() - oim.numpy()).max() < 5e-6 * scale
+    assert rel_max(mag.cpu(), om) < 5e-6
     back = istft((re, im), 512, 256, 512, length=L, input_type="real_imag")
     assert np.abs(back.cpu().numpy() - y.numpy()).max() < 5e-6  # size-independent property: identity
 
