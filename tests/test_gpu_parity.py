@@ -129,7 +129,7 @@ def _full_model(dev, gain, precision):
     return make_model(dict(O.DEFAULT_MODEL_ARGS), O.make_state_dict(seed=0, sb_fc_gain=gain), dev, precision)
 
 
-@pytest.mark.parametrize("precision,crm_tol", [("fp32", 5e-5)])
+@pytest.mark.parametrize("precision,crm_tol", [("fp32", 5e-5), ("f16_tc", CRM_TOL)])
 @pytest.mark.parametrize("tag,gain", [("wa", 1.0), ("wb", WB_GAIN)])
 def test_full_model_and_inferencer_match_reference(golden, dev, tag, gain, precision, crm_tol):
     from fullsubnet_b200.acoustics.feature import stft
@@ -144,20 +144,47 @@ def test_full_model_and_inferencer_match_reference(golden, dev, tag, gain, preci
     assert rel_max(crm.cpu(), ref_crm) < crm_tol and rel_l2(crm.cpu(), ref_crm) < crm_tol
     inf = Inferencer(model=m, device=dev)
     wav = np.stack([inf.full_band_crm_mask(y[i:i + 1], {}) for i in range(2)])  # op-by-op reference flow
-    scale = max(1.0, float(np.abs(ref_wav).max()))
-    assert np.abs(wav - ref_wav).max() < WAV_TOL * scale
     fused, crm2 = m.enhance(y, return_crm=True)  # one fsn_enhance call, batched
     assert rel_max(crm2.cpu(), ref_crm) < crm_tol
-    assert np.abs(fused.cpu().numpy() - ref_wav).max() < WAV_TOL * scale
+    scale = max(1.0, float(np.abs(ref_wav).max()))
+    if precision == "f16_tc" and tag == "wb":
+        # adversarial weight set: |cRM| reaches the +-9.9 clip where decompress_cIRM has gain 2K^2/(K^2-m^2) ~ 100,
+        # so the 11-bit-significand operand rounding (cRM still within 1e-3) is amplified in the waveform.
+        # The fp32 path meets 1e-4 here; the tensor-core path is held to 1 % of the waveform's L2 norm.
+        assert rel_l2(wav, ref_wav) < 1e-2 and rel_l2(fused.cpu(), ref_wav) < 1e-2
+    else:
+        assert np.abs(wav - ref_wav).max() < WAV_TOL * scale
+        assert np.abs(fused.cpu().numpy() - ref_wav).max() < WAV_TOL * scale
 
 
-def test_batched_equals_loop_of_single_clips(dev):
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("f16_tc", WAV_TOL)])
+def test_batched_equals_loop_of_single_clips(dev, precision, tol):
     """batched inference == loop of B=1 calls (drop_band off)."""
     from oracle import fullsubnet_oracle as O
-    m = _full_model(dev, 1.0, "fp32")
+    m = _full_model(dev, 1.0, precision)
     y = O.make_noisy(3, 4000, seed=11, speechlike=True).to(dev)
     batched = m.enhance(y)
     single = torch.cat([m.enhance(y[i:i + 1]) for i in range(3)], 0)
-    assert np.abs(batched.cpu().numpy() - single.cpu().numpy()).max() < 2e-6
+    assert np.abs(batched.cpu().numpy() - single.cpu().numpy()).max() < 2e-6  # tiling-independent
     ref = O.enhance(y.cpu(), O.make_state_dict(0))
-    assert np.abs(batched.cpu().numpy() - ref.numpy()).max() < 2e-5
+    assert np.abs(batched.cpu().numpy() - ref.numpy()).max() < tol
+
+
+def test_tc_drop_band_training_layout_and_unsupported_shapes(golden, dev):
+    """f16_tc with B>1, G=2 reproduces the drop_band batch permutation; unsupported hidden sizes raise."""
+    from oracle import fullsubnet_oracle as O
+    m = _full_model(dev, 1.0, "f16_tc")
+    y = O.make_noisy(3, 3000, seed=21, speechlike=True)
+    mag = O.stft(y, 512, 256, 512)[0].unsqueeze(1)
+    ref = O.model_forward(mag, O.make_state_dict(0))  # G=2 -> [3,2,128,T], batch order [0,2,1]
+    with torch.no_grad():
+        out = m(mag.to(dev))
+    assert out.shape == ref.shape
+    assert rel_max(out.cpu(), ref) < CRM_TOL and rel_l2(out.cpu(), ref) < CRM_TOL
+    g = golden("model_small")
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    small = make_model(small_args(), sd, dev, "f16_tc")  # hidden 24: not a multiple of 128
+    with pytest.raises(NotImplementedError):
+        small(T(g["mag"], dev).unsqueeze(1)[:1])
+    auto = make_model(small_args(), sd, dev, "auto")  # auto falls back to the fp32 kernels
+    assert rel_max(auto(T(g["mag"], dev).unsqueeze(1)[:1]).cpu(), g["crm_b1"]) < 2e-5
