@@ -227,7 +227,7 @@ extern "C" int fsn_model_forward(const fsn_model_desc* d, const fsn_seq_weights*
   int rc = make_dims(d, B, T, m);
   if (rc) return rc;
   FSN_REQUIRE(d->precision == FSN_PREC_FP32 || sb_tc_supported(d), FSN_ERR_UNSUPPORTED,
-              "FSN_PREC_F16_TC needs sb_hidden %% 128 == 0 and sub-band input width <= 64");
+              "FSN_PREC_F16_TC needs sb_hidden %% 128 == 0 and sub-band input width <= 32");
   ModelWs w;
   carve_model(d, m, workspace, w);
   FSN_REQUIRE(workspace && workspace_bytes >= w.bytes, FSN_ERR_WORKSPACE, "workspace too small: %zu < %zu",
@@ -289,7 +289,7 @@ extern "C" int fsn_enhance(const fsn_model_desc* d, const fsn_seq_weights* fb, c
   int rc = carve_enhance(&dd, B, L, n_fft, hop, workspace, e, m);
   if (rc) return rc;
   FSN_REQUIRE(dd.precision == FSN_PREC_FP32 || sb_tc_supported(&dd), FSN_ERR_UNSUPPORTED,
-              "FSN_PREC_F16_TC needs sb_hidden %% 128 == 0 and sub-band input width <= 64");
+              "FSN_PREC_F16_TC needs sb_hidden %% 128 == 0 and sub-band input width <= 32");
   FSN_REQUIRE(workspace && workspace_bytes >= e.bytes, FSN_ERR_WORKSPACE, "workspace too small: %zu < %zu",
               workspace_bytes, e.bytes);
   ModelWs w;

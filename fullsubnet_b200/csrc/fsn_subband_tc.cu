@@ -26,6 +26,8 @@
 // (+ TMEM alloc), 3 = Linear(H->2) + output staging, 4..15 = epilogue (3 warpgroups, one per
 // 128-unit slice m).
 #include <cuda_fp16.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "fsn_internal.cuh"
 
@@ -34,9 +36,11 @@ namespace tc {
 
 constexpr int NB = 32;                 // sub-band units per CTA (MMA N)
 constexpr int KB = 64;                 // fp16 elements per 128-byte swizzle row
-constexpr int W_TILE = 128 * KB * 2;   // 16384 B: [128 gate rows x 64 k]
+constexpr int KS = 32;                 // k elements per weight stage
+constexpr int W_SUB = 128 * KS * 2;    // 8192 B: [128 gate rows x 32 k] of one gate, 64B-swizzled
+constexpr int W_TILE = 4 * W_SUB;      // 32768 B: one ring stage = the 4 gates (i,f,g,o) of one (slice m, k range)
 constexpr int S_KBLK = NB * KB * 2;    // 4096 B: one k-block of the state operand
-constexpr int STAGES = 6;
+constexpr int MAX_STAGES = 4;        // weight ring depth is a launch parameter (default 3)
 constexpr int MAX_MT = 3;
 constexpr int OUT_T = 8;               // output frames staged before a store
 constexpr int NTHREADS = 128 + 128 * MAX_MT;
@@ -64,6 +68,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {  // non-blocking probe
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // spin with a watchdog: a protocol bug traps (launch error) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
@@ -75,11 +90,57 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// same, for warps that are off the critical issue path: back off between probes so the spinning does not
+// steal issue slots from the MMA-issuing warp that shares the SM sub-partition
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > (1u << 24)) {
+      printf("fsn sb_tc: mbarrier timeout (block %d thread %d bar %p parity %u)\n", blockIdx.x, threadIdx.x,
+             (void*)bar, parity);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+// one lane of a converged warp (the tcgen05 / TMA issue idiom: the warp stays converged so that the
+// operands live in uniform registers, only the issuing instruction is predicated)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -112,6 +173,14 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// same for the 64B-swizzled weight sub-tiles (rows of 64 B, 8-row groups 512 B apart): SWIZZLE_64B = 4
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+// byte offset of element (row, k<32) inside a [128 x 32] K-major 64B-swizzled sub-tile (Swizzle<2,4,3>)
+__host__ __device__ __forceinline__ int swz64_off(int row, int k) {
+  return (row >> 3) * 512 + (row & 7) * 64 + ((((k >> 3) ^ ((row >> 1) & 3)) & 3) << 4) + (k & 7) * 2;
+}
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, both K-major, M=128, N=NB
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -132,10 +201,10 @@ struct PackedLayout {
 __host__ __device__ inline PackedLayout packed_layout(int H, int Ksb) {
   PackedLayout L;
   L.H = H; L.MT = H / 128;
-  L.nkb0 = 1 + H / KB; L.nkb1 = 2 * H / KB;
+  L.nkb0 = 1 + H / KS; L.nkb1 = 2 * H / KS;  // stages (k ranges of 32) per slice m
   L.kx16 = (Ksb + 15) / 16;
-  L.tiles0 = (size_t)L.MT * 4 * L.nkb0;
-  L.tiles1 = (size_t)L.MT * 4 * L.nkb1;
+  L.tiles0 = (size_t)L.MT * L.nkb0;          // stages per step, layer 0 / layer 1
+  L.tiles1 = (size_t)L.MT * L.nkb1;
   L.off_bias = (L.tiles0 + L.tiles1) * W_TILE;
   L.off_fcw = L.off_bias + (size_t)2 * 4 * H * sizeof(float);
   L.off_fcb = L.off_fcw + (size_t)2 * H * sizeof(float);
@@ -144,7 +213,7 @@ __host__ __device__ inline PackedLayout packed_layout(int H, int Ksb) {
 }
 
 // ---------------------------------------------------------------- weight packer
-// tile order = consumption order: layer, m (128-unit slice), gate, k-block
+// stage order = consumption order: layer, m (128-unit slice), k range of 32; 4 gate sub-tiles per stage
 __global__ void pack_kernel(const float* __restrict__ wih0, const float* __restrict__ whh0,
                             const float* __restrict__ wih1, const float* __restrict__ whh1,
                             const float* __restrict__ bih0, const float* __restrict__ bhh0,
@@ -152,18 +221,19 @@ __global__ void pack_kernel(const float* __restrict__ wih0, const float* __restr
                             const float* __restrict__ fcw, const float* __restrict__ fcb, int H, int Ksb,
                             uint8_t* __restrict__ out) {
   const PackedLayout L = packed_layout(H, Ksb);
-  const size_t ntiles = L.tiles0 + L.tiles1;
-  const size_t total = ntiles * 128 * 8;  // one thread per (tile, row, 16-byte chunk)
+  const size_t nstages = L.tiles0 + L.tiles1;
+  const size_t total = nstages * 4 * 128 * 4;  // one thread per (stage, gate, row, 16-byte chunk)
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i & 7);
-    const int r = (int)((i >> 3) & 127);
-    size_t tile = i >> 10;
-    const int layer = tile >= L.tiles0;
-    if (layer) tile -= L.tiles0;
+    const int c = (int)(i & 3);
+    const int r = (int)((i >> 2) & 127);
+    const int g = (int)((i >> 9) & 3);
+    const size_t st_abs = i >> 11;
+    size_t st = st_abs;
+    const int layer = st >= L.tiles0;
+    if (layer) st -= L.tiles0;
     const int nkb = layer ? L.nkb1 : L.nkb0;
-    const int kb = (int)(tile % nkb);
-    const int g = (int)((tile / nkb) & 3);
-    const int m = (int)(tile / ((size_t)nkb * 4));
+    const int kb = (int)(st % nkb);
+    const int m = (int)(st / nkb);
     const int wrow = g * H + m * 128 + r;
     __half v[8];
 #pragma unroll
@@ -172,15 +242,14 @@ __global__ void pack_kernel(const float* __restrict__ wih0, const float* __restr
       float w = 0.f;
       if (layer == 0) {
         if (kb == 0) { if (kk < Ksb) w = wih0[(size_t)wrow * Ksb + kk]; }
-        else w = whh0[(size_t)wrow * H + (kb - 1) * KB + kk];
+        else w = whh0[(size_t)wrow * H + (kb - 1) * KS + kk];
       } else {
-        const int k = kb * KB + kk;
+        const int k = kb * KS + kk;
         w = (k < H) ? wih1[(size_t)wrow * H + k] : whh1[(size_t)wrow * H + (k - H)];
       }
       v[e] = __float2half_rn(w);
     }
-    const size_t t_abs = (i >> 10);
-    uint8_t* dst = out + t_abs * W_TILE + swz_off(r, c * 8);
+    uint8_t* dst = out + st_abs * W_TILE + g * W_SUB + swz64_off(r, c * 8);
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
   }
   // biases (b_ih + b_hh, fp32) and the Linear layer
@@ -199,11 +268,11 @@ __global__ void pack_kernel(const float* __restrict__ wih0, const float* __restr
 struct Smem {
   uint32_t w, x, h0, h1, fcw, outst, rows, bars, total;
 };
-__host__ __device__ inline Smem smem_plan(int H) {
+__host__ __device__ inline Smem smem_plan(int H, int stages) {
   Smem s;
   const int nkh = H / KB;
   uint32_t o = 0;
-  s.w = o; o += STAGES * W_TILE;
+  s.w = o; o += stages * W_TILE;
   s.x = o; o += 2 * S_KBLK;
   s.h0 = o; o += 2 * nkh * S_KBLK;
   s.h1 = o; o += 2 * nkh * S_KBLK;
@@ -216,7 +285,7 @@ __host__ __device__ inline Smem smem_plan(int H) {
 }
 
 struct Bars {
-  uint64_t w_full[STAGES], w_empty[STAGES];
+  uint64_t w_full[MAX_STAGES], w_empty[MAX_STAGES];
   uint64_t x_full[2], x_empty[2];
   uint64_t acc_full[MAX_MT], acc_empty[MAX_MT];
   uint64_t h0_ready, h1_ready, fc_done;
@@ -230,11 +299,17 @@ struct RowInfo {
   int out_idx;        // crm index of (b', o=0, f', t=0) divided by T  (= (b'*2)*Fsub + f')
 };
 
+// debug event trace: rec = (event id << 48) | (it << 32 ... ) kept simple: [slot] = clock, ids fixed per slot
+__device__ __forceinline__ void trace_ev(long long* tr, int it, int ev) {
+  if (tr && blockIdx.x == 0 && it >= 8 && it < 16) tr[(it - 8) * 32 + ev] = clock64();
+}
+
 struct KArgs {
   const uint8_t* packed;
   const float* magT; const float* fbT; const float* inv2;
   float* crm;
-  int R, F, Tp, la, T, Ns, Nf, H, Ksb, act, Fsub;
+  int R, F, Tp, la, T, Ns, Nf, H, Ksb, act, Fsub, stages, cluster;
+  long long* trace;  // debug: clock64 event trace of CTA 0 (FSN_TC_TRACE), else nullptr
   RowMap map;
 };
 
@@ -254,7 +329,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
   const int H = a.H;
   const int MT = H / 128;
   const int nkh = H / KB;
-  const Smem sp = smem_plan(H);
+  const int STAGES = a.stages;
+  // CL CTAs of a cluster consume the same weight stream in lock step: each loads 1/CL of every tile and
+  // multicasts it to all of them, so one L2 read feeds CL SMs
+  const int CL = a.cluster;
+  const uint16_t cl_mask = (uint16_t)((1u << CL) - 1u);
+  const uint32_t cl_rank = (CL > 1) ? cluster_ctarank() : 0u;
+  const Smem sp = smem_plan(H, STAGES);
   const PackedLayout PL = packed_layout(H, a.Ksb);
   Bars& bars = *reinterpret_cast<Bars*>(smem + sp.bars);
   RowInfo* rows = reinterpret_cast<RowInfo*>(smem + sp.rows);
@@ -266,7 +347,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
 
   // ---------------- one-time setup
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.w_full[s], 1); mbar_init(&bars.w_empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.w_full[s], 1); mbar_init(&bars.w_empty[s], CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars.x_full[i], 1); mbar_init(&bars.x_empty[i], 1); }
     for (int m = 0; m < MAX_MT; ++m) { mbar_init(&bars.acc_full[m], 1); mbar_init(&bars.acc_empty[m], 4); }
     mbar_init(&bars.h0_ready, 4 * MT);
@@ -298,6 +379,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast reaches them
   tc_fence_after();
   const uint32_t tmem_base = bars.tmem_base;
 
@@ -306,23 +388,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ================= weight-tile producer: the same (layer 0, layer 1) tile stream every step
-    if (lane == 0) {
-      uint32_t n = 0;
+    {
+      uint32_t stage = 0, phase = 0;
       for (int it = 0; it <= Tp; ++it) {
         const size_t t_begin = (it < Tp) ? 0 : PL.tiles0;
         const size_t t_end = (it >= 1) ? PL.tiles0 + PL.tiles1 : PL.tiles0;
-        for (size_t tile = t_begin; tile < t_end; ++tile, ++n) {
-          const uint32_t s = n % STAGES, use = n / STAGES;
-          mbar_wait(&bars.w_empty[s], (use & 1) ^ 1);
-          mbar_expect_tx(&bars.w_full[s], W_TILE);
-          bulk_g2s(smem + sp.w + s * W_TILE, a.packed + tile * W_TILE, W_TILE, &bars.w_full[s]);
+        const uint8_t* src = a.packed + t_begin * W_TILE;
+        for (size_t tile = t_begin; tile < t_end; ++tile, src += W_TILE) {
+          mbar_wait_relaxed(&bars.w_empty[stage], phase ^ 1);  // all CL consumers have drained this stage
+          if (elect_one()) {
+            mbar_expect_tx(&bars.w_full[stage], W_TILE);
+            if (CL == 1) {
+              bulk_g2s(smem + sp.w + stage * W_TILE, src, W_TILE, &bars.w_full[stage]);
+            } else {
+              const uint32_t slice = W_TILE / CL, off = cl_rank * slice;
+              bulk_g2s_mc(smem + sp.w + stage * W_TILE + off, src + off, slice, &bars.w_full[stage], cl_mask);
+            }
+          }
+          __syncwarp();
+          if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (one thread).  Order per iteration: layer0(step it), layer1(step it-1)
-    if (lane == 0) {
-      uint32_t n = 0;
+    // ================= MMA issuer (converged warp, one elected lane issues).  Order per iteration:
+    // layer0(step it), layer1(step it-1)
+    {
+      uint32_t stage = 0, phase = 0;
+      bool w_ready = false;
+      const uint64_t adesc0 = make_desc_sw64(smem_u32(smem + sp.w));
       uint32_t jobs[MAX_MT] = {0, 0, 0};
       // every mbarrier phase is waited on exactly once, in order (a parity wait on a phase that is two
       // behind the barrier would block on the wrong phase), so count the phases already observed
@@ -340,39 +434,63 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
             for (; h1_seen < t; ++h1_seen) mbar_wait(&bars.h1_ready, h1_seen & 1);      // h1_{t-1}
           }
           tc_fence_after();
-          const int nkb = layer ? PL.nkb1 : PL.nkb0;
           const uint32_t x_addr = smem_u32(smem + sp.x + (t & 1) * S_KBLK);
           const uint32_t h0_cur = smem_u32(smem + sp.h0 + (t & 1) * nkh * S_KBLK);        // h0_t
           const uint32_t h0_prev = smem_u32(smem + sp.h0 + ((t + 1) & 1) * nkh * S_KBLK);  // h0_{t-1}
           const uint32_t h1_prev = smem_u32(smem + sp.h1 + ((t + 1) & 1) * nkh * S_KBLK);  // h1_{t-1}
+          // B operand (state, K-major 128B-swizzled blocks of 64 k): layer 0: [x_t (32 k)] [h0_{t-1} (H)];
+          // layer 1: [h0_t (H)] [h1_{t-1} (H)].  One weight stage covers 32 k = half a block.
+          const uint64_t bd_a = make_desc(layer ? h0_cur : x_addr);
+          const uint64_t bd_b = make_desc(layer ? h1_prev : h0_prev);
+          const int n_a = layer ? H / KS : 1;
+          const int n_b = H / KS;
+          // one stage: 2 k16 slices x 4 gates; consecutive MMAs hit different accumulators, so the
+          // accumulate dependency of each gate is 4 instructions apart
+          auto issue_stage = [&](uint32_t d0, uint64_t bd, bool first) {
+            if (!w_ready) mbar_wait(&bars.w_full[stage], phase);
+            tc_fence_after();
+            const uint64_t ad = adesc0 + (uint64_t)(stage * (W_TILE >> 4));
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                  tc_mma_f16(d0 + (uint32_t)(g * NB), ad + (uint64_t)(g * (W_SUB >> 4) + 2 * k), bd + (uint64_t)(2 * k),
+                             kIdesc, (first && k == 0) ? 0u : 1u);
+              // stage free (in every CTA that fills it) once these MMAs have read it
+              if (CL == 1) tc_commit(&bars.w_empty[stage]); else tc_commit_mc(&bars.w_empty[stage], cl_mask);
+            }
+            __syncwarp();
+            if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
+            w_ready = mbar_test_wait(&bars.w_full[stage], phase);  // probe the next stage early
+          };
           for (int m = 0; m < MT; ++m) {
+            if (lane == 0) trace_ev(a.trace, it, (layer * 3 + m) * 2);
             mbar_wait(&bars.acc_empty[m], (jobs[m] & 1) ^ 1);
             tc_fence_after();
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t d = tmem_base + (uint32_t)(m * 4 * NB + g * NB);
-              for (int kb = 0; kb < nkb; ++kb, ++n) {
-                const uint32_t s = n % STAGES, use = n / STAGES;
-                mbar_wait(&bars.w_full[s], use & 1);
-                tc_fence_after();
-                uint32_t b_addr;
-                int nk16 = KB / 16;
-                if (layer == 0) {
-                  if (kb == 0) { b_addr = x_addr; nk16 = PL.kx16; }
-                  else b_addr = h0_prev + (kb - 1) * S_KBLK;
-                } else {
-                  b_addr = (kb < nkh) ? h0_cur + kb * S_KBLK : h1_prev + (kb - nkh) * S_KBLK;
-                }
-                const uint64_t ad = make_desc(smem_u32(smem + sp.w + s * W_TILE));
-                const uint64_t bd = make_desc(b_addr);
-                for (int k = 0; k < nk16; ++k)
-                  tc_mma_f16(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kIdesc, (kb | k) ? 1u : 0u);
-                tc_commit(&bars.w_empty[s]);  // stage free once these MMAs have read it
-              }
+            if (lane == 0) trace_ev(a.trace, it, 24 + layer * 3 + m);
+            const uint32_t d0 = tmem_base + (uint32_t)(m * 4 * NB);
+            uint64_t bd = bd_a;
+#pragma unroll 1
+            for (int j = 0; j < n_a; ++j) {
+              issue_stage(d0, bd, j == 0);
+              bd += (j & 1) ? (uint64_t)((S_KBLK >> 4) - 4) : 4ull;  // +64 B inside a block, then next block
             }
-            tc_commit(&bars.acc_full[m]);
+            bd = bd_b;
+#pragma unroll 1
+            for (int j = 0; j < n_b; ++j) {
+              issue_stage(d0, bd, false);
+              bd += (j & 1) ? (uint64_t)((S_KBLK >> 4) - 4) : 4ull;
+            }
+            if (elect_one()) tc_commit(&bars.acc_full[m]);
+            __syncwarp();
+            if (lane == 0) trace_ev(a.trace, it, (layer * 3 + m) * 2 + 1);
             jobs[m]++;
           }
-          if (layer == 0) tc_commit(&bars.x_empty[t & 1]);
+          if (layer == 0) {
+            if (elect_one()) tc_commit(&bars.x_empty[t & 1]);
+            __syncwarp();
+          }
         }
       }
     }
@@ -381,7 +499,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
     // scaled by 1/(mu'+1e-5)  (base_model.py:35-44, model.py:98-111), fp16, B-operand layout
     const int nmag = 2 * a.Ns + 1;
     for (int t = 0; t < Tp; ++t) {
-      mbar_wait(&bars.x_empty[t & 1], ((t >> 1) & 1) ^ 1);
+      mbar_wait_relaxed(&bars.x_empty[t & 1], ((t >> 1) & 1) ^ 1);
       uint8_t* xb = smem + sp.x + (t & 1) * S_KBLK;
 #pragma unroll 4
       for (int n = 0; n < NB; ++n) {
@@ -411,7 +529,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
     const RowInfo ri = rows[lane];
     int staged = 0, t_stage0 = 0;
     for (int t = 0; t < Tp; ++t) {
-      mbar_wait(&bars.h1_ready, t & 1);
+      mbar_wait_relaxed(&bars.h1_ready, t & 1);
       if (t >= a.la) {
         float s0 = fcb0, s1 = fcb1;
         for (int w = 0; w < 4 * MT; ++w) {
@@ -462,10 +580,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
         for (int layer = 0; layer < 2; ++layer) {
           const int t = it - layer;
           if (t < 0 || t >= Tp) continue;
-          mbar_wait(&bars.acc_full[m], job & 1);
+          mbar_wait_relaxed(&bars.acc_full[m], job & 1);
           ++job;
           tc_fence_after();
-          if (layer == 1 && t >= 1) mbar_wait(&bars.fc_done, (t - 1) & 1);  // FC(t-1) has read h1[(t+1)&1]
+          if (q == 0 && lane == 0) trace_ev(a.trace, it, 12 + (layer * 3 + m) * 2);
+          if (layer == 1 && t >= 1) mbar_wait_relaxed(&bars.fc_done, (t - 1) & 1);  // FC(t-1) has read h1[(t+1)&1]
           uint8_t* hb = smem + (layer ? sp.h1 : sp.h0) + (t & 1) * nkh * S_KBLK + kbu * S_KBLK + el * 2;
 #pragma unroll
           for (int j0 = 0; j0 < NB; j0 += 8) {
@@ -514,6 +633,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
           if (lane == 0) {
             mbar_arrive(&bars.acc_empty[m]);
             mbar_arrive(layer ? &bars.h1_ready : &bars.h0_ready);
+            if (q == 0) trace_ev(a.trace, it, 12 + (layer * 3 + m) * 2 + 1);
           }
         }
       }
@@ -523,6 +643,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
   // ---------------- teardown
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
@@ -533,7 +654,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
 
 bool sb_tc_supported(const fsn_model_desc* d) {
   const int Ksb = (2 * d->sb_num_neighbors + 1) + (2 * d->fb_num_neighbors + 1);
-  return d->sb_hidden % 128 == 0 && d->sb_hidden / 128 <= tc::MAX_MT && d->sb_hidden >= 128 && Ksb <= tc::KB;
+  return d->sb_hidden % 128 == 0 && d->sb_hidden / 128 <= tc::MAX_MT && d->sb_hidden >= 128 && Ksb <= tc::KS;
 }
 
 size_t sb_tc_packed_bytes(const fsn_model_desc* d) {
@@ -544,7 +665,7 @@ size_t sb_tc_packed_bytes(const fsn_model_desc* d) {
 
 int sb_tc_pack(const fsn_model_desc* d, const fsn_seq_weights* sb, void* packed, cudaStream_t st) {
   FSN_REQUIRE(sb_tc_supported(d), FSN_ERR_UNSUPPORTED,
-              "FSN_PREC_F16_TC needs sb_hidden in {128,256,384} and sub-band input width <= 64");
+              "FSN_PREC_F16_TC needs sb_hidden in {128,256,384} and sub-band input width <= 32");
   const int Ksb = (2 * d->sb_num_neighbors + 1) + (2 * d->fb_num_neighbors + 1);
   tc::pack_kernel<<<148 * 4, 256, 0, st>>>(sb->w_ih[0], sb->w_hh[0], sb->w_ih[1], sb->w_hh[1], sb->b_ih[0],
                                            sb->b_hh[0], sb->b_ih[1], sb->b_hh[1], sb->fc_w, sb->fc_b, d->sb_hidden,
@@ -560,15 +681,64 @@ int sb_tc_forward(const SbTcArgs& s, cudaStream_t st) {
   a.R = s.map.B * s.map.Fsub; a.F = s.F; a.Tp = s.Tp; a.la = s.la; a.T = s.Tp - s.la;
   a.Ns = s.Ns; a.Nf = s.Nf; a.H = s.H; a.Ksb = (2 * s.Ns + 1) + (2 * s.Nf + 1); a.act = s.act;
   a.Fsub = s.map.Fsub; a.map = s.map;
-  const tc::Smem sp = tc::smem_plan(s.H);
+  static int stages_env = -1;
+  if (stages_env < 0) {
+    const char* e = getenv("FSN_TC_STAGES");
+    stages_env = e ? atoi(e) : 3;
+    if (stages_env < 2) stages_env = 2;
+    if (stages_env > tc::MAX_STAGES) stages_env = tc::MAX_STAGES;
+  }
+  a.stages = stages_env;
+  static int cluster_env = -1;
+  if (cluster_env < 0) {
+    const char* e = getenv("FSN_TC_CLUSTER");
+    cluster_env = e ? atoi(e) : 2;
+    if (cluster_env != 1 && cluster_env != 2 && cluster_env != 4) cluster_env = 2;
+  }
+  a.cluster = cluster_env;
+  a.trace = nullptr;
+  static long long* trace_buf = nullptr;
+  if (getenv("FSN_TC_TRACE")) {  // debug only: 8 iterations x 32 event slots of clock64
+    if (!trace_buf) { cudaMalloc(&trace_buf, 8 * 32 * sizeof(long long)); cudaMemset(trace_buf, 0, 8 * 32 * sizeof(long long)); }
+    a.trace = trace_buf;
+  }
+  const tc::Smem sp = tc::smem_plan(s.H, a.stages);
   const size_t smem = sp.total + 1024;  // slack for the 1024-byte alignment of the dynamic segment
   int rc = check_cuda(cudaFuncSetAttribute(tc::sb_lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem), "sb_lstm_tc smem attr");
   if (rc) return rc;
-  const int tiles = cdiv(a.R, tc::NB);
+  const int tiles = cdiv(cdiv(a.R, tc::NB), a.cluster) * a.cluster;  // padding CTAs own no valid row
   const int threads = 128 + 128 * (s.H / 128);
-  tc::sb_lstm_tc_kernel<<<tiles, threads, smem, st>>>(a);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(tiles);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = a.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  rc = check_cuda(cudaLaunchKernelEx(&cfg, tc::sb_lstm_tc_kernel, a), "sb_lstm_tc_kernel launch");
+  if (rc) return rc;
   FSN_CHECK_LAUNCH("sb_lstm_tc_kernel");
+  if (a.trace) {
+    long long h[8 * 32];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, a.trace, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long t0 = h[0];
+    static const char* names[6] = {"L0m0", "L0m1", "L0m2", "L1m0", "L1m1", "L1m2"};
+    for (int it = 0; it < 3; ++it) {
+      fprintf(stderr, "[trace it=%d]\n", it + 8);
+      for (int j = 0; j < 6; ++j)
+        fprintf(stderr, "  %s issue_begin %7lld acc_empty_ok %7lld issue_end %7lld | epi_begin %7lld epi_end %7lld\n", names[j],
+                h[it * 32 + j * 2] - t0, h[it * 32 + 24 + j] - t0, h[it * 32 + j * 2 + 1] - t0,
+                h[it * 32 + 12 + j * 2] - t0, h[it * 32 + 12 + j * 2 + 1] - t0);
+    }
+  }
   return FSN_OK;
 }
 

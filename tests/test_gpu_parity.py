@@ -83,8 +83,13 @@ def test_stft_istft_roundtrip_and_oracle(dev, L):
     assert np.abs(re.cpu().numpy() - ore.numpy()).max() < 5e-6 * scale
     assert np.abs(im.cpu().numpy() - oim.numpy()).max() < 5e-6 * scale
     assert rel_max(mag.cpu(), om) < 5e-6
-    back = istft((re, im), 512, 256, 512, length=L, input_type="real_imag")
-    assert np.abs(back.cpu().numpy() - y.numpy()).max() < 5e-6  # size-independent property: identity
+    back = istft((re, im), 512, 256, 512, length=L, input_type="real_imag").cpu().numpy()
+    # size-independent property: identity.  Only on the samples covered by full window overlap, hop*(T-1):
+    # past that the window-square envelope tends to 0 and y*w^2/w^2 is ill-conditioned (in torch.istft too).
+    n_ok = 256 * (mag.shape[-1] - 1)
+    assert np.abs(back[:, :n_ok] - y.numpy()[:, :n_ok]).max() < 5e-6
+    oback = O.istft((ore, oim), 512, 256, 512, length=L, input_type="real_imag").numpy()
+    assert np.abs(back - oback)[:, :n_ok].max() < 5e-6 and back.shape == oback.shape
 
 
 # ------------------------------------------------------------------ masks, drop_band
