@@ -56,6 +56,11 @@ int stft_launch(const float* wav, int B, int L, int n_fft, int hop, int win_leng
 int istft_launch(const float* real, const float* imag, int cstride, const float* crm, int B, int T, int n_fft,
                  int hop, int win_length, int length, float* wav, cudaStream_t st);
 
+// persistent cooperative full-band LSTM (fsn_fullband.cu)
+bool fb_persistent_supported(int F, int H);
+int fb_persistent_launch(const fsn_seq_weights* w, const float* magT_chunk, const float* inv1_chunk, float* h0buf,
+                         float* h1all_chunk, unsigned int* barrier, int nb, int F, int H, int Tp, cudaStream_t st);
+
 // tcgen05 sub-band stack (fsn_subband_tc.cu)
 struct SbTcArgs {
   const void* packed;       // tile-ordered fp16 weights (fsn_pack_sb_weights)

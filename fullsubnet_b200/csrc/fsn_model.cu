@@ -3,6 +3,7 @@
 //
 // Reference: recipes/dns_interspeech_2020/fullsubnet/model.py:72-136 (Model.forward),
 //            recipes/dns_interspeech_2020/inferencer.py:130-145 (full_band_crm_mask).
+#include <stdlib.h>
 #include <string.h>
 
 #include "fsn_internal.cuh"
@@ -44,7 +45,8 @@ struct Carver {
 struct ModelWs {
   float *magT, *fbT, *inv1, *inv2;
   float2 *fs, *sums_mag, *sums_fb;
-  float *fb_h0[2], *fb_c0, *fb_c1, *fb_h1all;
+  float *fb_h0[2], *fb_c0, *fb_c1, *fb_h1all, *fb_pp;
+  unsigned int* fb_barrier;
   float *sb_h0[2], *sb_h1[2], *sb_c0, *sb_c1;
   size_t bytes;
 };
@@ -91,6 +93,8 @@ static void carve_model(const fsn_model_desc* d, const Dims& m, void* base, Mode
   w.fb_c0 = c.take<float>(BH);
   w.fb_c1 = c.take<float>(BH);
   w.fb_h1all = c.take<float>(BH * m.Tp);
+  w.fb_pp = c.take<float>((size_t)2 * 256 * d->fb_hidden);  // h0 ping-pong of the persistent kernel
+  w.fb_barrier = c.take<unsigned int>(64);
   if (d->precision == FSN_PREC_FP32) {
     const size_t RH = (size_t)m.R * d->sb_hidden;
     for (int i = 0; i < 2; ++i) { w.sb_h0[i] = c.take<float>(RH); w.sb_h1[i] = c.take<float>(RH); }
@@ -110,6 +114,17 @@ static int model_core(const fsn_model_desc* d, const fsn_seq_weights* fb, const 
   if ((rc = norm_scales_launch(w.sums_mag, w.sums_mag, B, (float)F * Tp, 1.f, w.inv1, nullptr, st))) return rc;
 
   // ---- full-band stack (model.py:92-95): 2-layer LSTM(F -> Hf -> Hf), rows = clips
+  static const bool fb_stepwise = getenv("FSN_FB_STEPWISE") != nullptr;  // debug: force the per-step kernels
+  if (!fb_stepwise && fb_persistent_supported(F, Hf)) {
+    // one persistent cooperative kernel per chunk of <= 256 clips: weights resident in shared memory,
+    // layer wavefront, one grid barrier per time step
+    for (int b0 = 0; b0 < B; b0 += 256) {
+      const int nb = (B - b0 < 256) ? B - b0 : 256;
+      if ((rc = fb_persistent_launch(fb, w.magT + (size_t)b0 * Tp * F, w.inv1 + b0, w.fb_pp,
+                                     w.fb_h1all + (size_t)b0 * Tp * Hf, w.fb_barrier, nb, F, Hf, Tp, st)))
+        return rc;
+    }
+  } else {
   for (int t = 0; t < Tp; ++t) {
     StepParams p;
     memset(&p, 0, sizeof(p));
@@ -130,6 +145,7 @@ static int model_core(const fsn_model_desc* d, const fsn_seq_weights* fb, const 
     p.h_out = w.fb_h1all + (size_t)t * Hf; p.h_out_stride = (size_t)Tp * Hf;
     p.c = w.fb_c1;
     if ((rc = lstm_step_launch(p, SEG0_DENSE, st))) return rc;
+  }
   }
   // Linear(Hf -> F) + activation over all (b,t): fbT[b,t,f]  (sequence_model.py:119-123)
   if ((rc = fc_gemm_launch(w.fb_h1all, fb->fc_w, fb->fc_b, w.fbT, B * Tp, Hf, F, d->fb_activation, st))) return rc;
