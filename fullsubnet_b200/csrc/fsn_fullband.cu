@@ -22,9 +22,12 @@ namespace fsn {
 namespace fb {
 
 constexpr int ROWS = 256;      // clips per launch (host loops over chunks)
-constexpr int THREADS = 512;
-constexpr int KC = 32;         // k-chunk staged in shared memory
+constexpr int THREADS = 256;
+constexpr int KC = 16;         // k-chunk staged in shared memory
+constexpr int RS = KC + 4;      // row stride (floats) of the A tile [row][k]: 80 B keeps 16-byte cp.async aligned and,
+                               // with rows rq+8i per thread, makes the 128-bit reads bank-conflict free
 constexpr int MAX_UPC = 4;     // hidden units per CTA (=> 16 gate columns)
+constexpr int NSTAGE = 5;      // cp.async ring depth of the A tiles
 
 struct Args {
   const float* w_ih[2]; const float* w_hh[2]; const float* b_ih[2]; const float* b_hh[2];
@@ -51,136 +54,182 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
-// shared-memory weight slice layout: Ws[layer][k][16] (gate column c = unit_local*4 + gate), k over
+// 4 rows x 4 gate columns (one hidden unit) per thread and layer: acc[r][g] += a[r] * w[g]
+__device__ __forceinline__ void fma_4x4(float (&acc)[16], const float (&av)[4], const float4 w) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    acc[r * 4 + 0] = fmaf(av[r], w.x, acc[r * 4 + 0]);
+    acc[r * 4 + 1] = fmaf(av[r], w.y, acc[r * 4 + 1]);
+    acc[r * 4 + 2] = fmaf(av[r], w.z, acc[r * 4 + 2]);
+    acc[r * 4 + 3] = fmaf(av[r], w.w, acc[r * 4 + 3]);
+  }
+}
+
+// shared-memory weight slice layout: W[layer][k][16] (gate column c = unit_local*4 + gate), k over
 // [x | h_prev] of that layer; zero for units beyond H.
+// Thread mapping (256 threads): warp w, rq = lane/4 -> rows 32w+rq+8i (i<4), cq = lane%4 -> unit u0+cq (4 gates),
+// both layers: a 256x16(x2) register-tiled GEMM per phase, FMA-pipe bound.
 __global__ void __launch_bounds__(THREADS, 1) fb_lstm_kernel(const Args a) {
   extern __shared__ __align__(16) float smem_f[];
   const int F = a.F, H = a.H, Tp = a.Tp, B = a.B;
   const int K0 = F + H, K1 = 2 * H;
   float* W0 = smem_f;                 // [K0][16]
   float* W1 = W0 + (size_t)K0 * 16;   // [K1][16]
-  float* At = W1 + (size_t)K1 * 16;   // [ROWS][KC+1]
+  float* At = W1 + (size_t)K1 * 16;   // [NSTAGE][ROWS][RS]
   const int tid = threadIdx.x;
-  const int row = tid >> 1, half = tid & 1;
+  const int cq = tid & 3;
+  const int row_base = (tid >> 5) * 32 + ((tid & 31) >> 2);  // thread rows: row_base + 8*i
   const int u0 = blockIdx.x * a.upc;  // first hidden unit of this CTA
+  const int u = u0 + cq;
+  const bool unit_ok = cq < a.upc && u < H;
 
-  // ---- one-time: weight slice -> shared memory (gate column c: unit u0 + c/4, gate c%4)
+  // ---- one-time: weight slice -> shared memory
   for (int idx = tid; idx < K0 * 16; idx += THREADS) {
     const int k = idx >> 4, c = idx & 15;
-    const int ul = c >> 2, g = c & 3, u = u0 + ul;
+    const int ul = c >> 2, g = c & 3, uu = u0 + ul;
     float w = 0.f;
-    if (ul < a.upc && u < H) {
-      const size_t wr = (size_t)g * H + u;
+    if (ul < a.upc && uu < H) {
+      const size_t wr = (size_t)g * H + uu;
       w = (k < F) ? a.w_ih[0][wr * F + k] : a.w_hh[0][wr * H + (k - F)];
     }
     W0[idx] = w;
   }
   for (int idx = tid; idx < K1 * 16; idx += THREADS) {
     const int k = idx >> 4, c = idx & 15;
-    const int ul = c >> 2, g = c & 3, u = u0 + ul;
+    const int ul = c >> 2, g = c & 3, uu = u0 + ul;
     float w = 0.f;
-    if (ul < a.upc && u < H) {
-      const size_t wr = (size_t)g * H + u;
+    if (ul < a.upc && uu < H) {
+      const size_t wr = (size_t)g * H + uu;
       w = (k < H) ? a.w_ih[1][wr * H + k] : a.w_hh[1][wr * H + (k - H)];
     }
     W1[idx] = w;
   }
-  float bias0[8], bias1[8];
+  float bias0[4], bias1[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = half * 8 + j, ul = c >> 2, g = c & 3, u = u0 + ul;
-    const bool ok = ul < a.upc && u < H;
-    bias0[j] = ok ? a.b_ih[0][g * H + u] + a.b_hh[0][g * H + u] : 0.f;
-    bias1[j] = ok ? a.b_ih[1][g * H + u] + a.b_hh[1][g * H + u] : 0.f;
+  for (int g = 0; g < 4; ++g) {
+    bias0[g] = unit_ok ? a.b_ih[0][g * H + u] + a.b_hh[0][g * H + u] : 0.f;
+    bias1[g] = unit_ok ? a.b_ih[1][g * H + u] + a.b_hh[1][g * H + u] : 0.f;
   }
-  float c0[2] = {0.f, 0.f}, c1[2] = {0.f, 0.f};  // cell state of the thread's 2 units, both layers
-  const float scale = (row < B) ? a.inv1[row] : 0.f;
-  __syncthreads();
+  float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};  // cell state: 4 rows, both layers
+  float rs[4];  // 1/(mu+1e-5) of the thread's 4 clips (model.py:92), applied to the x segment
+#pragma unroll
+  for (int r = 0; r < 4; ++r) rs[r] = (row_base + 8 * r < B) ? a.inv1[row_base + 8 * r] : 0.f;
 
-  // A-tile loader: thread -> (row = tid/2, 16 consecutive k of the 32-chunk)
-  const int l_row = tid >> 1, l_k = (tid & 1) * 16;
+  // A-tile loader: 16-byte cp.async for the h segments (thread -> rows tid/4 + 64 j, k = 4*(tid%4));
+  // 4-byte cp.async for the x segment whose rows (F floats) are not 16-byte aligned
+  const int l_row0 = (tid >> 5) * 32 + ((tid & 31) >> 4), l_k = tid & 15;
+  const int v_row0 = tid >> 2, v_k = (tid & 3) * 4;
+  const bool vec_ok = (H % 4) == 0;
+  __syncthreads();
 
   for (int p = 0; p <= Tp; ++p) {
     const bool do0 = p < Tp;    // layer 0 at step p
     const bool do1 = p >= 1;    // layer 1 at step p-1
-    float acc0[8], acc1[8];
+    float acc0[16], acc1[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc0[j] = bias0[j]; acc1[j] = bias1[j]; }
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) { acc0[r * 4 + g] = bias0[g]; acc1[r * 4 + g] = bias1[g]; }
     const float* h0_prev = a.h0buf + (size_t)((p + 1) & 1) * B * H;       // h0_{p-1}
     const float* h1_prev = a.h1all + (size_t)(p >= 2 ? p - 2 : 0) * H;    // h1_{p-2}, row stride Tp*H
-    // three k segments: x_p (F, layer 0), h0_{p-1} (H, both layers), h1_{p-2} (H, layer 1)
-    for (int seg = 0; seg < 3; ++seg) {
-      if (seg == 0 && !do0) continue;
-      if (seg == 1 && p == 0) continue;           // h0_{-1} = 0
-      if (seg == 2 && p < 2) continue;            // h1_{-1} = 0
-      const int klen = (seg == 0) ? F : H;
-      const float* w0 = (seg == 0) ? W0 : W0 + (size_t)F * 16;          // layer-0 rows of this segment
-      const float* w1 = (seg == 1) ? W1 : W1 + (size_t)H * 16;          // layer-1 rows of this segment
-      const bool use0 = (seg <= 1) && do0, use1 = (seg >= 1) && do1;
-      for (int k0 = 0; k0 < klen; k0 += KC) {
-        __syncthreads();
-        if (l_row < B) {
+    // three k segments: x_p (F, layer 0), h0_{p-1} (H, both layers), h1_{p-2} (H, layer 1), walked as one
+    // flat list of KC-wide chunks through a cp.async ring of NSTAGE tiles (NSTAGE-1 chunks in flight hide
+    // the L2 latency; out-of-range elements are zero-filled with src-size 0).  Plain (non-.cg) loads are
+    // correct here: every phase starts after the acquire of the grid barrier.
+    const int nch_f = (F + KC - 1) / KC, nch_h = (H + KC - 1) / KC;
+    const int c_begin = do0 ? 0 : nch_f;                       // skip x when layer 0 is finished
+    const int c_end = nch_f + (p >= 1 ? nch_h : 0) + (p >= 2 ? nch_h : 0);
+    auto issue = [&](int ci) {
+      if (ci < c_end) {
+        int seg = 0, k0 = ci * KC;
+        if (ci >= nch_f) { seg = 1; k0 = (ci - nch_f) * KC; }
+        if (ci >= nch_f + nch_h) { seg = 2; k0 = (ci - nch_f - nch_h) * KC; }
+        const int klen = seg ? H : F;
+        float* Ab = At + (size_t)((ci - c_begin) % NSTAGE) * ROWS * RS;
+        if (seg != 0 && vec_ok) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int r = v_row0 + 64 * j, k = k0 + v_k;
+            const bool ok = r < B && k < klen;  // H % 4 == 0: a 4-wide group is entirely in or out
+            const float* src = a.x;
+            if (ok) src = (seg == 1) ? h0_prev + (size_t)r * H + k : h1_prev + (size_t)r * Tp * H + k;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(Ab + r * RS + v_k)),
+                         "l"(src), "r"(ok ? 16 : 0)
+                         : "memory");
+          }
+        } else {
+          const int k = k0 + l_k;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int k = k0 + l_k + j;
-            float v = 0.f;
-            if (k < klen) {
-              if (seg == 0) v = a.x[((size_t)l_row * Tp + p) * F + k] * scale;
-              else if (seg == 1) v = __ldcg(h0_prev + (size_t)l_row * H + k);
-              else v = __ldcg(h1_prev + (size_t)l_row * Tp * H + k);
+            const int r = l_row0 + 2 * j;
+            const bool ok = r < B && k < klen;
+            const float* src = a.x;  // any valid address when the element is zero-filled
+            if (ok) {
+              if (seg == 0) src = a.x + ((size_t)r * Tp + p) * F + k;
+              else if (seg == 1) src = h0_prev + (size_t)r * H + k;
+              else src = h1_prev + (size_t)r * Tp * H + k;
             }
-            At[l_row * (KC + 1) + l_k + j] = v;
-          }
-        }
-        __syncthreads();
-        const int kmax = min(KC, klen - k0);
-        const float* ar = At + row * (KC + 1);
-        if (use0 && use1) {
-          for (int kk = 0; kk < kmax; ++kk) {
-            const float av = ar[kk];
-            const float4* p0 = reinterpret_cast<const float4*>(w0 + (size_t)(k0 + kk) * 16 + half * 8);
-            const float4* p1 = reinterpret_cast<const float4*>(w1 + (size_t)(k0 + kk) * 16 + half * 8);
-            const float4 wa = p0[0], wb = p0[1], wc = p1[0], wd = p1[1];
-            acc0[0] = fmaf(av, wa.x, acc0[0]); acc0[1] = fmaf(av, wa.y, acc0[1]);
-            acc0[2] = fmaf(av, wa.z, acc0[2]); acc0[3] = fmaf(av, wa.w, acc0[3]);
-            acc0[4] = fmaf(av, wb.x, acc0[4]); acc0[5] = fmaf(av, wb.y, acc0[5]);
-            acc0[6] = fmaf(av, wb.z, acc0[6]); acc0[7] = fmaf(av, wb.w, acc0[7]);
-            acc1[0] = fmaf(av, wc.x, acc1[0]); acc1[1] = fmaf(av, wc.y, acc1[1]);
-            acc1[2] = fmaf(av, wc.z, acc1[2]); acc1[3] = fmaf(av, wc.w, acc1[3]);
-            acc1[4] = fmaf(av, wd.x, acc1[4]); acc1[5] = fmaf(av, wd.y, acc1[5]);
-            acc1[6] = fmaf(av, wd.z, acc1[6]); acc1[7] = fmaf(av, wd.w, acc1[7]);
-          }
-        } else if (use0 || use1) {
-          const float* w = use0 ? w0 : w1;
-          float* acc = use0 ? acc0 : acc1;
-          for (int kk = 0; kk < kmax; ++kk) {
-            const float av = ar[kk];
-            const float4* pw = reinterpret_cast<const float4*>(w + (size_t)(k0 + kk) * 16 + half * 8);
-            const float4 wa = pw[0], wb = pw[1];
-            acc[0] = fmaf(av, wa.x, acc[0]); acc[1] = fmaf(av, wa.y, acc[1]);
-            acc[2] = fmaf(av, wa.z, acc[2]); acc[3] = fmaf(av, wa.w, acc[3]);
-            acc[4] = fmaf(av, wb.x, acc[4]); acc[5] = fmaf(av, wb.y, acc[5]);
-            acc[6] = fmaf(av, wb.z, acc[6]); acc[7] = fmaf(av, wb.w, acc[7]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(Ab + r * RS + l_k)),
+                         "l"(src), "r"(ok ? 4 : 0)
+                         : "memory");
           }
         }
       }
-    }
-    // ---- cell updates of the thread's 2 units (gate order i,f,g,o), write h
-    if (row < B) {
+      asm volatile("cp.async.commit_group;" ::: "memory");  // (empty groups keep the wait count uniform)
+    };
+#pragma unroll 1
+    for (int i = 0; i < NSTAGE - 1; ++i) issue(c_begin + i);
+    for (int ci = c_begin; ci < c_end; ++ci) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(NSTAGE - 2) : "memory");
+      __syncthreads();                 // chunk ci landed for everyone; buffer of chunk ci-1 is free
+      issue(ci + NSTAGE - 1);
+      const float* Ab = At + (size_t)((ci - c_begin) % NSTAGE) * ROWS * RS;
+      if (row_base >= B) continue;
+      int seg = 0, k0 = ci * KC;
+      if (ci >= nch_f) { seg = 1; k0 = (ci - nch_f) * KC; }
+      if (ci >= nch_f + nch_h) { seg = 2; k0 = (ci - nch_f - nch_h) * KC; }
+      const float* w0 = ((seg == 0) ? W0 : W0 + (size_t)F * 16) + (size_t)k0 * 16 + cq * 4;   // layer-0 rows
+      const float* w1 = ((seg == 1) ? W1 : W1 + (size_t)H * 16) + (size_t)k0 * 16 + cq * 4;   // layer-1 rows
+      const bool use0 = (seg <= 1) && do0, use1 = (seg >= 1) && do1;
+      const float* ar = Ab + row_base * RS;
+      // rows beyond klen inside the chunk are zero-filled, so the full KC is always safe to consume
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int u = u0 + half * 2 + q;
-        if (half * 2 + q < a.upc && u < H) {
-          if (do0) {
-            const float c = sigmoidf_(acc0[q * 4 + 1]) * c0[q] + sigmoidf_(acc0[q * 4 + 0]) * tanhf(acc0[q * 4 + 2]);
-            c0[q] = c;
-            a.h0buf[(size_t)(p & 1) * B * H + (size_t)row * H + u] = sigmoidf_(acc0[q * 4 + 3]) * tanhf(c);
-          }
-          if (do1) {
-            const float c = sigmoidf_(acc1[q * 4 + 1]) * c1[q] + sigmoidf_(acc1[q * 4 + 0]) * tanhf(acc1[q * 4 + 2]);
-            c1[q] = c;
-            a.h1all[((size_t)row * Tp + (p - 1)) * H + u] = sigmoidf_(acc1[q * 4 + 3]) * tanhf(c);
-          }
+      for (int k4 = 0; k4 < KC; k4 += 4) {
+        float4 a4[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a4[r] = *reinterpret_cast<const float4*>(ar + (8 * r) * RS + k4);
+        if (seg == 0) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) { a4[r].x *= rs[r]; a4[r].y *= rs[r]; a4[r].z *= rs[r]; a4[r].w *= rs[r]; }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float av[4] = {q == 0 ? a4[0].x : q == 1 ? a4[0].y : q == 2 ? a4[0].z : a4[0].w,
+                               q == 0 ? a4[1].x : q == 1 ? a4[1].y : q == 2 ? a4[1].z : a4[1].w,
+                               q == 0 ? a4[2].x : q == 1 ? a4[2].y : q == 2 ? a4[2].z : a4[2].w,
+                               q == 0 ? a4[3].x : q == 1 ? a4[3].y : q == 2 ? a4[3].z : a4[3].w};
+          if (use0) fma_4x4(acc0, av, *reinterpret_cast<const float4*>(w0 + (k4 + q) * 16));
+          if (use1) fma_4x4(acc1, av, *reinterpret_cast<const float4*>(w1 + (k4 + q) * 16));
+        }
+      }
+    }
+    // ---- cell updates of the thread's unit for its 4 rows (gate order i,f,g,o), write h
+    if (unit_ok) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int row = row_base + 8 * r;
+        if (row >= B) continue;
+        if (do0) {
+          const float c = sigmoidf_(acc0[r * 4 + 1]) * c0[r] + sigmoidf_(acc0[r * 4 + 0]) * tanhf(acc0[r * 4 + 2]);
+          c0[r] = c;
+          a.h0buf[(size_t)(p & 1) * B * H + (size_t)row * H + u] = sigmoidf_(acc0[r * 4 + 3]) * tanhf(c);
+        }
+        if (do1) {
+          const float c = sigmoidf_(acc1[r * 4 + 1]) * c1[r] + sigmoidf_(acc1[r * 4 + 0]) * tanhf(acc1[r * 4 + 2]);
+          c1[r] = c;
+          a.h1all[((size_t)row * Tp + (p - 1)) * H + u] = sigmoidf_(acc1[r * 4 + 3]) * tanhf(c);
         }
       }
     }
@@ -191,7 +240,7 @@ __global__ void __launch_bounds__(THREADS, 1) fb_lstm_kernel(const Args a) {
 }  // namespace fb
 
 size_t fb_persistent_smem(int F, int H) {
-  return ((size_t)(F + H) * 16 + (size_t)2 * H * 16 + (size_t)fb::ROWS * (fb::KC + 1)) * sizeof(float);
+  return ((size_t)(F + H) * 16 + (size_t)2 * H * 16 + (size_t)fb::NSTAGE * fb::ROWS * fb::RS) * sizeof(float);
 }
 
 bool fb_persistent_supported(int F, int H) {
