@@ -246,6 +246,10 @@ def main():
     # tensor roofline: fp16 operands on tcgen05 (same dense rate as the measured bf16 cuBLAS peak);
     # the fp32 path is FMA-bound and reported against the same denominator for comparability
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if precision == "f16_tc" and B == 256 and os.path.exists(tpath):  # ncu capture of this exact workload
+        traffic = json.load(open(tpath))["sb_lstm_tc_kernel"]["dram_bytes_per_launch"]
     line = {
         "metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -261,7 +265,7 @@ def main():
         "clocks": clocks,
         "stage_ms": {"stft": stage_ms[0], "fullband": stage_ms[1], "subband": stage_ms[2], "mask_istft": stage_ms[3]},
         "roofline": {"kernel": "sub-band LSTM stack", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+                     "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
                      "peak_source": f"{peak_kind} bf16_tflops_sustained",
                      "flops_per_launch": sb_flops, "ms_per_launch": sb_ms},
     }
