@@ -193,3 +193,27 @@ def test_tc_drop_band_training_layout_and_unsupported_shapes(golden, dev):
         small(T(g["mag"], dev).unsqueeze(1)[:1])
     auto = make_model(small_args(), sd, dev, "auto")  # auto falls back to the fp32 kernels
     assert rel_max(auto(T(g["mag"], dev).unsqueeze(1)[:1]).cpu(), g["crm_b1"]) < 2e-5
+
+
+def test_full_size_batch_properties(dev):
+    """BASELINE configs[1] size (256 x 4 s) through size-independent properties: finite output, tiling
+    independence (a clip's result does not depend on where it sits in the batch / which CTA tile its
+    sub-band units land in), duplicate clips give bit-identical outputs, first/middle/last clip match the
+    oracle within the north-star tolerances."""
+    from oracle import fullsubnet_oracle as O
+    m = _full_model(dev, 1.0, "auto")
+    B, L = 256, 64000
+    y = O.make_noisy(B, L, seed=77)
+    y[200] = y[7]  # duplicate clip at another batch position (different tile alignment: 7*257 vs 200*257 mod 32)
+    yd = y.to(dev)
+    out, crm = m.enhance(yd, return_crm=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all() and torch.isfinite(crm).all()
+    assert torch.equal(out[7], out[200]) and torch.equal(crm[7], crm[200])
+    for i in (0, 131, 255):
+        single, crm1 = m.enhance(yd[i:i + 1], return_crm=True)
+        assert torch.equal(single[0], out[i]) and torch.equal(crm1[0], crm[i])
+    sd = O.make_state_dict(0)
+    ref_wav, ref_crm = O.enhance(y[255:256], sd, return_crm=True)
+    assert rel_max(crm[255:256].cpu(), ref_crm) < CRM_TOL and rel_l2(crm[255:256].cpu(), ref_crm) < CRM_TOL
+    assert np.abs(out[255:256].cpu().numpy() - ref_wav.numpy()).max() < WAV_TOL
