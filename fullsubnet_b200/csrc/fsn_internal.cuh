@@ -67,11 +67,18 @@ struct SbTcArgs {
   const float* magT; const float* fbT; const float* inv2;
   float* crm;
   int B, F, Tp, la, Ns, Nf, H, act;
+  bool pair;              // packed for / run by the CTA-pair kernel
   RowMap map;
 };
 size_t sb_tc_packed_bytes(const fsn_model_desc* d);
 int sb_tc_pack(const fsn_model_desc* d, const fsn_seq_weights* sb, void* packed, cudaStream_t st);
 int sb_tc_forward(const SbTcArgs& a, cudaStream_t st);
 bool sb_tc_supported(const fsn_model_desc* d);
+
+// CTA-pair (cta_group::2) variant (fsn_subband_tc2.cu); preferred when the shape allows (H = 384)
+bool sb_tc2_supported(const fsn_model_desc* d);
+size_t sb_tc2_packed_bytes();
+int sb_tc2_pack(const fsn_model_desc* d, const fsn_seq_weights* sb, void* packed, cudaStream_t st);
+int sb_tc2_forward(const SbTcArgs& a, cudaStream_t st);
 
 }  // namespace fsn

@@ -163,7 +163,7 @@ static int model_core(const fsn_model_desc* d, const fsn_seq_weights* fb, const 
     memset(&a, 0, sizeof(a));
     a.packed = sb_packed; a.magT = w.magT; a.fbT = w.fbT; a.inv2 = w.inv2; a.crm = crm;
     a.B = B; a.F = F; a.Tp = Tp; a.la = d->look_ahead; a.Ns = d->sb_num_neighbors; a.Nf = d->fb_num_neighbors;
-    a.H = Hs; a.act = d->sb_activation; a.map = map;
+    a.H = Hs; a.act = d->sb_activation; a.map = map; a.pair = sb_tc2_supported(d);
     rc = sb_tc_forward(a, st);
     prof_mark(3, st);
     return rc;

@@ -1,0 +1,574 @@
+// Sub-band LSTM stack, CTA-PAIR variant: tcgen05.mma.cta_group::2 (sm_100a).
+//
+// Same mathematics and reference rows as fsn_subband_tc.cu (model.py:98-135), different mapping onto the
+// machine.  A cluster of two CTAs (two SMs of one TPC) owns 64 sub-band units (rows): CTA r holds the
+// recurrent state (x_t, h0, h1; fp16, UMMA K-major layout) of rows [32r, 32r+32) and HALF of the hidden
+// units of both layers.  The leader CTA issues every MMA for the pair:
+//     J1: M = 256 (CTA0: units 0..127, CTA1: units 128..255), N = 64, 4 gate accumulators x 64 TMEM columns
+//     J2: M = 128 (CTA0: units 256..319, CTA1: units 320..383), N = 64, 4 x 32 columns
+//         (2-CTA M=128 accumulator layout: lane = unit + 64*(n/32), column = n%32)
+// so that every 4 KB weight tile an SM reads from shared memory is multiplied against 64 rows instead of 32,
+// and each SM streams only its own half of the weights (1.78 MB per step instead of 3.55 MB): the tensor pipe,
+// bound by the shared-memory read of the weight operand, does half the work per row.
+// The epilogue thread that owns (hidden unit, 32-row half) keeps c in registers and writes h_t (fp16) into
+// the state buffer of the CTA that owns those rows - its own or the peer's, through distributed shared memory
+// (st.shared::cluster + fence.proxy.async), and publishes it with cluster-scope mbarrier arrives on the leader.
+//
+// Warp roles per CTA (512 threads): 0 = weight producer (own half of the stream), 1 = MMA issuer (leader) /
+// stage relay (peer), 2 = x gather + TMEM alloc, 3 = Linear(H->2) reduce + output, 4-7 = epilogue J1 rows 0..31
+// (-> CTA0), 8-11 = epilogue J1 rows 32..63 (-> CTA1), 12-15 = epilogue J2.
+#include <stdlib.h>
+#include <string.h>
+
+#include "fsn_internal.cuh"
+#include "fsn_tc_ptx.cuh"
+
+namespace fsn {
+namespace tc2 {
+using namespace ptx;
+
+constexpr int H = 384;                 // hidden size this variant is built for
+constexpr int NB = 32;                 // rows per CTA (64 per pair)
+constexpr int KB = 64, KS = 32;
+constexpr int S_KBLK = NB * KB * 2;    // 4096 B: one 64-k block of the state operand
+constexpr int NKH = H / KB;            // 6 blocks per h
+constexpr int W_SUB1 = 128 * KS * 2;   // J1 gate sub-tile (128 units x 32 k)
+constexpr int W_ST1 = 4 * W_SUB1;      // 32 KB
+constexpr int W_SUB2 = 64 * KS * 2;    // J2 gate sub-tile (64 units x 32 k)
+constexpr int W_ST2 = 4 * W_SUB2;      // 16 KB
+constexpr int NK0 = 1 + H / KS;        // 13 k-ranges: x, h0_{t-1}
+constexpr int NK1 = 2 * H / KS;        // 24 k-ranges: h0_t, h1_{t-1}
+constexpr int STAGES = 3;
+constexpr int OUT_T = 8;
+constexpr int NTHREADS = 512;
+constexpr int FC_SLOTS = 12;
+
+constexpr size_t STREAM_BYTES = (size_t)(NK0 + NK1) * (W_ST1 + W_ST2);  // per rank and step
+constexpr size_t OFF_L0J1 = 0;
+constexpr size_t OFF_L0J2 = OFF_L0J1 + (size_t)NK0 * W_ST1;
+constexpr size_t OFF_L1J1 = OFF_L0J2 + (size_t)NK0 * W_ST2;
+constexpr size_t OFF_L1J2 = OFF_L1J1 + (size_t)NK1 * W_ST1;
+constexpr size_t OFF_BIAS = 2 * STREAM_BYTES;
+constexpr size_t OFF_FCW = OFF_BIAS + (size_t)2 * 4 * H * sizeof(float);
+constexpr size_t OFF_FCB = OFF_FCW + (size_t)2 * H * sizeof(float);
+constexpr size_t PACKED_BYTES = OFF_FCB + 256;
+
+constexpr uint32_t kIdesc256 = (1u << 4) | ((64u >> 3) << 17) | ((256u >> 4) << 24);  // f16 x f16 -> f32, N=64
+constexpr uint32_t kIdesc128 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+// ---------------------------------------------------------------- weight packer
+// per rank r: [L0 J1 stages][L0 J2 stages][L1 J1 stages][L1 J2 stages]; a stage = 4 gate sub-tiles of one k range
+__global__ void pack2_kernel(const float* __restrict__ wih0, const float* __restrict__ whh0,
+                             const float* __restrict__ wih1, const float* __restrict__ whh1,
+                             const float* __restrict__ bih0, const float* __restrict__ bhh0,
+                             const float* __restrict__ bih1, const float* __restrict__ bhh1,
+                             const float* __restrict__ fcw, const float* __restrict__ fcb, int Ksb,
+                             uint8_t* __restrict__ out) {
+  // one thread per 16-byte chunk (8 halves): chunks per rank = STREAM_BYTES / 16
+  const size_t chunks_per_rank = STREAM_BYTES / 16;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < 2 * chunks_per_rank;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int rank = (int)(i / chunks_per_rank);
+    size_t off = (i % chunks_per_rank) * 16;  // byte offset inside the rank's stream
+    int layer, j2;
+    if (off < OFF_L0J2) { layer = 0; j2 = 0; }
+    else if (off < OFF_L1J1) { layer = 0; j2 = 1; off -= OFF_L0J2; }
+    else if (off < OFF_L1J2) { layer = 1; j2 = 0; off -= OFF_L1J1; }
+    else { layer = 1; j2 = 1; off -= OFF_L1J2; }
+    const int st_bytes = j2 ? W_ST2 : W_ST1, sub_bytes = j2 ? W_SUB2 : W_SUB1;
+    const int kb = (int)(off / st_bytes);
+    const int in_st = (int)(off % st_bytes);
+    const int g = in_st / sub_bytes;
+    const int in_sub = in_st % sub_bytes;
+    // invert swz64_off: 512-byte groups of 8 rows, 64-byte rows, 16-byte chunks XOR-ed with (row>>1)&3
+    const int grp = in_sub / 512, rr = (in_sub % 512) / 64, cx = (in_sub % 64) / 16;
+    const int row = grp * 8 + rr;
+    const int c = cx ^ ((row >> 1) & 3);
+    const int unit = j2 ? 256 + rank * 64 + row : rank * 128 + row;
+    const int wrow = g * H + unit;
+    __half v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int kk = c * 8 + e;
+      float w = 0.f;
+      if (layer == 0) {
+        if (kb == 0) { if (kk < Ksb) w = wih0[(size_t)wrow * Ksb + kk]; }
+        else w = whh0[(size_t)wrow * H + (kb - 1) * KS + kk];
+      } else {
+        const int k = kb * KS + kk;
+        w = (k < H) ? wih1[(size_t)wrow * H + k] : whh1[(size_t)wrow * H + (k - H)];
+      }
+      v[e] = __float2half_rn(w);
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)rank * STREAM_BYTES + (i % chunks_per_rank) * 16) =
+        *reinterpret_cast<const uint4*>(v);
+  }
+  float* bias = reinterpret_cast<float*>(out + OFF_BIAS);
+  float* pfcw = reinterpret_cast<float*>(out + OFF_FCW);
+  float* pfcb = reinterpret_cast<float*>(out + OFF_FCB);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * H; i += gridDim.x * blockDim.x) {
+    bias[i] = bih0[i] + bhh0[i];
+    bias[4 * H + i] = bih1[i] + bhh1[i];
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * H; i += gridDim.x * blockDim.x) pfcw[i] = fcw[i];
+  if (blockIdx.x == 0 && threadIdx.x < 2) pfcb[threadIdx.x] = fcb[threadIdx.x];
+}
+
+// ---------------------------------------------------------------- shared-memory plan (identical in both CTAs)
+constexpr uint32_t SM_W = 0;
+constexpr uint32_t SM_X = SM_W + STAGES * W_ST1;
+constexpr uint32_t SM_H0 = SM_X + 2 * S_KBLK;
+constexpr uint32_t SM_H1 = SM_H0 + 2 * NKH * S_KBLK;
+constexpr uint32_t SM_FC = SM_H1 + 2 * NKH * S_KBLK;           // [FC_SLOTS][2][NB] float
+constexpr uint32_t SM_OUT = SM_FC + FC_SLOTS * 2 * NB * 4;     // [NB][2][OUT_T] float
+constexpr uint32_t SM_ROWS = SM_OUT + NB * 2 * OUT_T * 4;
+constexpr uint32_t SM_BARS = SM_ROWS + NB * 16;
+constexpr uint32_t SM_TOTAL = SM_BARS + 256;
+
+struct Bars {
+  uint64_t w_full[STAGES], w_peer[STAGES], w_empty[STAGES];
+  uint64_t x_full[2], x_empty[2];
+  uint64_t accf_j1, accf_j2[2];     // MMA -> epilogue (multicast commit)
+  uint64_t acce_j1, acce_j2[2];     // epilogue (both CTAs) -> leader MMA
+  uint64_t h0_ready, h1_ready;      // epilogue (both CTAs) -> leader MMA
+  uint64_t fc_ready, fc_done;       // Linear partials ready (12 writer warps) / consumed (both FC warps)
+  uint32_t tmem_base;
+};
+static_assert(sizeof(Bars) <= 256, "barrier block too large");
+
+struct RowInfo {
+  int src_b, src_f;
+  float scale;
+  int out_idx;
+};
+
+struct KArgs {
+  const uint8_t* packed;
+  const float* magT; const float* fbT; const float* inv2;
+  float* crm;
+  int R, F, Tp, la, T, Ns, Nf, Ksb, act, Fsub;
+  long long* dbg;  // FSN_TC_TRACE: cycle accounting of the leader's MMA warp (block 0)
+  RowMap map;
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case FSN_ACT_RELU: return fmaxf(v, 0.f);
+    case FSN_ACT_TANH: return tanhf(v);
+    case FSN_ACT_RELU6: return fminf(fmaxf(v, 0.f), 6.f);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ void st_cluster_b16(uint32_t addr, __half v) {
+  asm volatile("st.shared::cluster.b16 [%0], %1;" ::"r"(addr), "h"(__half_as_ushort(v)) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm_tc2_kernel(const KArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  Bars& bars = *reinterpret_cast<Bars*>(smem + SM_BARS);
+  RowInfo* rows = reinterpret_cast<RowInfo*>(smem + SM_ROWS);
+  float* fc_part = reinterpret_cast<float*>(smem + SM_FC);
+  float* outst = reinterpret_cast<float*>(smem + SM_OUT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int row0 = (blockIdx.x >> 1) * (2 * NB) + (int)rank * NB;  // first row of this CTA
+  const int Tp = a.Tp;
+  const uint8_t* my_stream = a.packed + (size_t)rank * STREAM_BYTES;
+
+  // ---------------- one-time setup
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.w_full[s], 1); mbar_init(&bars.w_peer[s], 1); mbar_init(&bars.w_empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars.x_full[i], 2); mbar_init(&bars.x_empty[i], 1); }
+    mbar_init(&bars.accf_j1, 1);
+    mbar_init(&bars.acce_j1, 16);
+    for (int l = 0; l < 2; ++l) { mbar_init(&bars.accf_j2[l], 1); mbar_init(&bars.acce_j2[l], 8); }
+    mbar_init(&bars.h0_ready, 24);
+    mbar_init(&bars.h1_ready, 24);
+    mbar_init(&bars.fc_ready, FC_SLOTS);
+    mbar_init(&bars.fc_done, 2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars.tmem_base)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  if (threadIdx.x < NB) {
+    RowInfo ri;
+    const int r = row0 + threadIdx.x;
+    ri.src_b = -1; ri.src_f = 0; ri.scale = 0.f; ri.out_idx = 0;
+    if (r < a.R) {
+      row_to_unit(a.map, r, ri.src_b, ri.src_f);
+      ri.scale = a.inv2[ri.src_b];
+      const int bq = r / a.Fsub, fq = r - bq * a.Fsub;
+      ri.out_idx = bq * 2 * a.Fsub + fq;
+    }
+    rows[threadIdx.x] = ri;
+  }
+  {  // zero the state (h_{-1} = 0, x padding)
+    uint4* z = reinterpret_cast<uint4*>(smem + SM_X);
+    const int n16 = (SM_FC - SM_X) / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers, state and TMEM are ready before any cross-CTA traffic
+  tc_fence_after();
+  const uint32_t tmem_base = bars.tmem_base;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      // ================= weight producer: this CTA's half of the stream, same sequence every step
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it <= Tp; ++it) {
+        for (int layer = 0; layer < 2; ++layer) {
+          const int t = it - layer;
+          if (t < 0 || t >= Tp) continue;
+          const int nk = layer ? NK1 : NK0;
+          for (int j2 = 0; j2 < 2; ++j2) {
+            const uint8_t* src = my_stream + (layer ? (j2 ? OFF_L1J2 : OFF_L1J1) : (j2 ? OFF_L0J2 : OFF_L0J1));
+            const uint32_t bytes = j2 ? W_ST2 : W_ST1;
+            for (int k = 0; k < nk; ++k, src += bytes) {
+              mbar_wait<true>(&bars.w_empty[stage], phase ^ 1);
+              if (elect_one()) {
+                mbar_expect_tx(&bars.w_full[stage], bytes);
+                bulk_g2s(smem + SM_W + stage * W_ST1, src, bytes, &bars.w_full[stage]);
+              }
+              __syncwarp();
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    } else if (warp == 1 && !leader) {
+      // ================= peer: relay "my half of stage s has landed" to the leader
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it <= Tp; ++it) {
+        for (int layer = 0; layer < 2; ++layer) {
+          const int t = it - layer;
+          if (t < 0 || t >= Tp) continue;
+          const int n = 2 * (layer ? NK1 : NK0);
+          for (int k = 0; k < n; ++k) {
+            mbar_wait<false>(&bars.w_full[stage], phase);
+            if (elect_one()) mbar_arrive_cluster(&bars.w_peer[stage], 0);
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ================= leader: MMA issuer for the pair (converged warp, one elected lane issues)
+      uint32_t stage = 0, phase = 0;
+      const uint64_t adesc0 = desc_sw64(smem_u32(smem + SM_W));
+      int h0_seen = 0, h1_seen = 0;
+      uint32_t j1_uses = 0, j2_uses[2] = {0, 0};
+      long long c_full = 0, c_peer = 0, c_acce = 0, c_h = 0, c_issue = 0;
+      const long long c_start = clock64();
+      for (int it = 0; it <= Tp; ++it) {
+        for (int layer = 0; layer < 2; ++layer) {
+          const int t = it - layer;
+          if (t < 0 || t >= Tp) continue;
+          long long c0 = clock64();
+          if (layer == 0) {
+            mbar_wait<false>(&bars.x_full[t & 1], (t >> 1) & 1);
+            for (; h0_seen < t; ++h0_seen) mbar_wait<false>(&bars.h0_ready, h0_seen & 1);
+          } else {
+            for (; h0_seen < t + 1; ++h0_seen) mbar_wait<false>(&bars.h0_ready, h0_seen & 1);
+            for (; h1_seen < t; ++h1_seen) mbar_wait<false>(&bars.h1_ready, h1_seen & 1);
+          }
+          c_h += clock64() - c0;
+          tc_fence_after();
+          const uint32_t x_addr = smem_u32(smem + SM_X + (t & 1) * S_KBLK);
+          const uint32_t h0_cur = smem_u32(smem + SM_H0 + (t & 1) * NKH * S_KBLK);
+          const uint32_t h0_prev = smem_u32(smem + SM_H0 + ((t + 1) & 1) * NKH * S_KBLK);
+          const uint32_t h1_prev = smem_u32(smem + SM_H1 + ((t + 1) & 1) * NKH * S_KBLK);
+          const uint64_t bd_a = desc_sw128(layer ? h0_cur : x_addr);
+          const uint64_t bd_b = desc_sw128(layer ? h1_prev : h0_prev);
+          const int n_a = layer ? H / KS : 1;
+          const int n_b = H / KS;
+          // one stage: 2 k16 slices x 4 gates (8 MMAs on 4 different accumulators)
+          auto issue_stage = [&](uint32_t d0, uint32_t dstep, uint32_t sub16, uint32_t idesc, uint64_t bd, bool first) {
+            long long c1 = clock64();
+            mbar_wait<false>(&bars.w_full[stage], phase);
+            long long c2 = clock64();
+            mbar_wait<false>(&bars.w_peer[stage], phase);
+            long long c3 = clock64();
+            c_full += c2 - c1; c_peer += c3 - c2;
+            tc_fence_after();
+            const uint64_t ad = adesc0 + (uint64_t)(stage * (W_ST1 >> 4));
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                  tc_mma2_f16(d0 + (uint32_t)g * dstep, ad + (uint64_t)(g * sub16 + 2 * k), bd + (uint64_t)(2 * k), idesc,
+                              (first && k == 0) ? 0u : 1u);
+              tc_commit2_mc(&bars.w_empty[stage], 3);  // frees the stage in both CTAs
+            }
+            __syncwarp();
+            c_issue += clock64() - c3;
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          };
+          auto run_job = [&](uint32_t d0, uint32_t dstep, uint32_t sub16, uint32_t idesc) {
+            uint64_t bd = bd_a;
+#pragma unroll 1
+            for (int j = 0; j < n_a; ++j) {
+              issue_stage(d0, dstep, sub16, idesc, bd, j == 0);
+              bd += (j & 1) ? (uint64_t)((S_KBLK >> 4) - 4) : 4ull;
+            }
+            bd = bd_b;
+#pragma unroll 1
+            for (int j = 0; j < n_b; ++j) {
+              issue_stage(d0, dstep, sub16, idesc, bd, false);
+              bd += (j & 1) ? (uint64_t)((S_KBLK >> 4) - 4) : 4ull;
+            }
+          };
+          // ---- J1: M=256, accumulators at columns [0,256): gate g at g*64
+          c0 = clock64();
+          mbar_wait<false>(&bars.acce_j1, (j1_uses & 1) ^ 1);
+          c_acce += clock64() - c0;
+          tc_fence_after();
+          run_job(tmem_base, 64, W_SUB1 >> 4, kIdesc256);
+          if (elect_one()) tc_commit2_mc(&bars.accf_j1, 3);
+          __syncwarp();
+          ++j1_uses;
+          // ---- J2: M=128 over the pair, accumulators at columns 256 + layer*128: gate g at g*32
+          c0 = clock64();
+          mbar_wait<false>(&bars.acce_j2[layer], (j2_uses[layer] & 1) ^ 1);
+          c_acce += clock64() - c0;
+          tc_fence_after();
+          run_job(tmem_base + 256 + layer * 128, 32, W_SUB2 >> 4, kIdesc128);
+          if (elect_one()) {
+            tc_commit2_mc(&bars.accf_j2[layer], 3);
+            if (layer == 0) tc_commit2_mc(&bars.x_empty[t & 1], 3);
+          }
+          __syncwarp();
+          ++j2_uses[layer];
+        }
+      }
+      if (a.dbg && blockIdx.x == 0 && lane == 0) {
+        a.dbg[0] = clock64() - c_start; a.dbg[1] = c_full; a.dbg[2] = c_peer; a.dbg[3] = c_acce; a.dbg[4] = c_h; a.dbg[5] = c_issue;
+      }
+    } else if (warp == 2) {
+      // ================= x_t gather for this CTA's 32 rows (base_model.py:35-44, model.py:98-111)
+      const int nmag = 2 * a.Ns + 1;
+      for (int t = 0; t < Tp; ++t) {
+        mbar_wait<true>(&bars.x_empty[t & 1], ((t >> 1) & 1) ^ 1);
+        uint8_t* xb = smem + SM_X + (t & 1) * S_KBLK;
+#pragma unroll 4
+        for (int n = 0; n < NB; ++n) {
+          const RowInfo ri = rows[n];
+          float v = 0.f;
+          if (ri.src_b >= 0 && lane < a.Ksb) {
+            const size_t base = ((size_t)ri.src_b * Tp + t) * a.F;
+            if (lane < nmag) v = a.magT[base + reflect_idx(ri.src_f + lane - a.Ns, a.F)];
+            else             v = a.fbT[base + reflect_idx(ri.src_f + (lane - nmag) - a.Nf, a.F)];
+            v *= ri.scale;
+          }
+          *reinterpret_cast<__half*>(xb + swz128_off(n, lane)) = __float2half_rn(v);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&bars.x_full[t & 1], 0);
+      }
+    } else {
+      // ================= Linear(H -> 2): sum the 12 fp32 partials of this CTA's rows, bias, stage, store
+      const float fcb0 = reinterpret_cast<const float*>(a.packed + OFF_FCB)[0];
+      const float fcb1 = reinterpret_cast<const float*>(a.packed + OFF_FCB)[1];
+      const RowInfo ri = rows[lane];
+      int staged = 0, t_stage0 = 0;
+      for (int t = 0; t < Tp; ++t) {
+        mbar_wait<true>(&bars.fc_ready, t & 1);
+        if (t >= a.la) {
+          float s0 = fcb0, s1 = fcb1;
+#pragma unroll
+          for (int w = 0; w < FC_SLOTS; ++w) {
+            s0 += fc_part[(w * 2 + 0) * NB + lane];
+            s1 += fc_part[(w * 2 + 1) * NB + lane];
+          }
+          if (staged == 0) t_stage0 = t - a.la;
+          outst[(lane * 2 + 0) * OUT_T + staged] = act_apply(s0, a.act);
+          outst[(lane * 2 + 1) * OUT_T + staged] = act_apply(s1, a.act);
+          ++staged;
+        }
+        __syncwarp();
+        if (lane == 0) { mbar_arrive_cluster(&bars.fc_done, 0); mbar_arrive_cluster(&bars.fc_done, 1); }
+        if (staged == OUT_T || (t == Tp - 1 && staged > 0)) {
+          if (ri.src_b >= 0) {
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+              float* dst = a.crm + ((size_t)ri.out_idx + (size_t)o * a.Fsub) * a.T + t_stage0;
+              for (int i = 0; i < staged; ++i) dst[i] = outst[(lane * 2 + o) * OUT_T + i];
+            }
+          }
+          staged = 0;
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warpgroups
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    const int wg = (warp - 4) >> 2;   // 0: J1 rows 0..31, 1: J1 rows 32..63, 2: J2
+    const int q = warp & 3;           // TMEM lane quadrant
+    const bool is_j2 = wg == 2;
+    const int L = q * 32 + lane;      // TMEM lane
+    const int u = is_j2 ? 256 + (int)rank * 64 + (L & 63) : (int)rank * 128 + L;   // hidden unit
+    const uint32_t dest = is_j2 ? (uint32_t)(L >> 6) : (uint32_t)wg;               // CTA that owns the rows
+    const float* bias_g = reinterpret_cast<const float*>(a.packed + OFF_BIAS);
+    float b0[4], b1[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) { b0[g] = bias_g[g * H + u]; b1[g] = bias_g[4 * H + g * H + u]; }
+    const float wfc0 = reinterpret_cast<const float*>(a.packed + OFF_FCW)[u];
+    const float wfc1 = reinterpret_cast<const float*>(a.packed + OFF_FCW)[H + u];
+    float c0[NB], c1[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) c0[i] = c1[i] = 0.f;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int kbu = u >> 6, chunk = (u & 63) >> 3, el = u & 7;
+    // state / partial-sum addresses in the destination CTA (distributed shared memory)
+    const uint32_t dst_base = mapa(smem_u32(smem), dest);
+    const int slot = (int)rank * 6 + (is_j2 ? 4 + (q & 1) : q);
+    const uint32_t part_addr = dst_base + SM_FC + (uint32_t)slot * 2 * NB * 4;
+    uint64_t* accf = is_j2 ? nullptr : &bars.accf_j1;
+    uint32_t job = 0, job2[2] = {0, 0};
+    for (int it = 0; it <= Tp; ++it) {
+      for (int layer = 0; layer < 2; ++layer) {
+        const int t = it - layer;
+        if (t < 0 || t >= Tp) continue;
+        uint32_t tacc;
+        if (is_j2) {
+          mbar_wait<true>(&bars.accf_j2[layer], job2[layer] & 1);
+          ++job2[layer];
+          tacc = tmem_base + lane_addr + 256 + layer * 128;
+        } else {
+          mbar_wait<true>(accf, job & 1);
+          ++job;
+          tacc = tmem_base + lane_addr + (uint32_t)wg * 32;
+        }
+        tc_fence_after();
+        if (layer == 1 && t >= 1) mbar_wait<true>(&bars.fc_done, (t - 1) & 1);  // both Linear warps read step t-1
+        const uint32_t gstep = is_j2 ? 32u : 64u;
+        const uint32_t hb = dst_base + (layer ? SM_H1 : SM_H0) + (uint32_t)((t & 1) * NKH * S_KBLK + kbu * S_KBLK + el * 2);
+#pragma unroll
+        for (int j0 = 0; j0 < NB; j0 += 8) {
+          float gi[8], gf[8], gg[8], go[8];
+          tc_ld8(tacc + 0 * gstep + j0, gi);
+          tc_ld8(tacc + 1 * gstep + j0, gf);
+          tc_ld8(tacc + 2 * gstep + j0, gg);
+          tc_ld8(tacc + 3 * gstep + j0, go);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float cp, bi, bf, bg, bo;
+            if (layer == 0) { cp = c0[j0 + j]; bi = b0[0]; bf = b0[1]; bg = b0[2]; bo = b0[3]; }
+            else            { cp = c1[j0 + j]; bi = b1[0]; bf = b1[1]; bg = b1[2]; bo = b1[3]; }
+            const float cn = fast_sigmoid(gf[j] + bf) * cp + fast_sigmoid(gi[j] + bi) * fast_tanh(gg[j] + bg);
+            if (layer == 0) c0[j0 + j] = cn; else c1[j0 + j] = cn;
+            const float h = fast_sigmoid(go[j] + bo) * fast_tanh(cn);
+            // row n = j0 + j of the destination CTA: (n>>3)*1024 + (n&7)*128 + ((chunk ^ (n&7)) << 4)
+            st_cluster_b16(hb + (uint32_t)((j0 >> 3) * 1024 + j * 128 + ((chunk ^ j) << 4)), __float2half_rn(h));
+            go[j] = h;
+          }
+          if (layer == 1) {
+            // Linear(H->2) in fp32: 2 outputs x 8 rows, summed over the warp's 32 hidden units
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v[j] = go[j] * wfc0; v[8 + j] = go[j] * wfc1; }
+#pragma unroll
+            for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < half; ++i) {
+                const float send = up ? v[i] : v[i + half];
+                const float keep = up ? v[i + half] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+            if ((lane & 1) == 0)
+              st_cluster_f32(part_addr + (uint32_t)((((lane >> 4) & 1) * NB + j0 + ((lane >> 1) & 7)) * 4), v[0]);
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_cluster(is_j2 ? &bars.acce_j2[layer] : &bars.acce_j1, 0);
+          mbar_arrive_cluster(layer ? &bars.h1_ready : &bars.h0_ready, 0);
+          if (layer == 1) mbar_arrive_cluster(&bars.fc_ready, dest);
+        }
+      }
+    }
+  }
+
+  // ---------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  }
+}
+
+}  // namespace tc2
+
+bool sb_tc2_supported(const fsn_model_desc* d) {
+  static int pair_env = -1;
+  if (pair_env < 0) {
+    const char* e = getenv("FSN_TC_PAIR");
+    pair_env = e ? atoi(e) : 0;  // opt-in: currently ring-latency bound
+  }
+  const int Ksb = (2 * d->sb_num_neighbors + 1) + (2 * d->fb_num_neighbors + 1);
+  return pair_env != 0 && d->sb_hidden == tc2::H && Ksb <= tc2::KS;
+}
+
+size_t sb_tc2_packed_bytes() { return tc2::PACKED_BYTES; }
+
+int sb_tc2_pack(const fsn_model_desc* d, const fsn_seq_weights* sb, void* packed, cudaStream_t st) {
+  const int Ksb = (2 * d->sb_num_neighbors + 1) + (2 * d->fb_num_neighbors + 1);
+  tc2::pack2_kernel<<<148 * 4, 256, 0, st>>>(sb->w_ih[0], sb->w_hh[0], sb->w_ih[1], sb->w_hh[1], sb->b_ih[0],
+                                             sb->b_hh[0], sb->b_ih[1], sb->b_hh[1], sb->fc_w, sb->fc_b, Ksb,
+                                             (uint8_t*)packed);
+  FSN_CHECK_LAUNCH("sb pack2_kernel");
+  return FSN_OK;
+}
+
+int sb_tc2_forward(const SbTcArgs& s, cudaStream_t st) {
+  tc2::KArgs a;
+  a.packed = (const uint8_t*)s.packed;
+  a.magT = s.magT; a.fbT = s.fbT; a.inv2 = s.inv2; a.crm = s.crm;
+  a.R = s.map.B * s.map.Fsub; a.F = s.F; a.Tp = s.Tp; a.la = s.la; a.T = s.Tp - s.la;
+  a.Ns = s.Ns; a.Nf = s.Nf; a.Ksb = (2 * s.Ns + 1) + (2 * s.Nf + 1); a.act = s.act;
+  a.Fsub = s.map.Fsub; a.map = s.map;
+  a.dbg = nullptr;
+  static long long* dbg_buf = nullptr;
+  if (getenv("FSN_TC_TRACE")) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 8 * sizeof(long long));
+    a.dbg = dbg_buf;
+  }
+  const size_t smem = tc2::SM_TOTAL + 1024;
+  int rc = check_cuda(cudaFuncSetAttribute(tc2::sb_lstm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem), "sb_lstm_tc2 smem attr");
+  if (rc) return rc;
+  const int pairs = cdiv(a.R, 2 * tc2::NB);
+  tc2::sb_lstm_tc2_kernel<<<2 * pairs, tc2::NTHREADS, smem, st>>>(a);
+  FSN_CHECK_LAUNCH("sb_lstm_tc2_kernel");
+  if (a.dbg) {
+    long long h[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tc2 leader cycles] total %lld | wait own stage %lld | wait peer stage %lld | wait acc drained %lld | "
+                    "wait state ready %lld | issue+commit %lld  (Tp=%d)\n", h[0], h[1], h[2], h[3], h[4], h[5], a.Tp);
+  }
+  return FSN_OK;
+}
+
+}  // namespace fsn
