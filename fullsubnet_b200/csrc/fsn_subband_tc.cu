@@ -275,7 +275,7 @@ __host__ __device__ inline Smem smem_plan(int H, int stages) {
   s.w = o; o += stages * W_TILE;
   s.x = o; o += 2 * S_KBLK;
   s.h0 = o; o += 2 * nkh * S_KBLK;
-  s.h1 = o; o += 2 * nkh * S_KBLK;
+  s.h1 = o; o += nkh * S_KBLK;  // single buffer: h1_t overwrites h1_{t-1} once every layer-1 MMA of step t is done
   s.fcw = o; o += 4 * MAX_MT * 2 * NB * 4;  // Linear partial sums [epilogue warp][o][row]
   s.outst = o; o += NB * 2 * OUT_T * 4;
   s.rows = o; o += NB * 16;
@@ -289,6 +289,7 @@ struct Bars {
   uint64_t x_full[2], x_empty[2];
   uint64_t acc_full[MAX_MT], acc_empty[MAX_MT];
   uint64_t h0_ready, h1_ready, fc_done;
+  uint64_t l1_done;   // all layer-1 MMAs of a step have completed (h1 may be overwritten)
   uint32_t tmem_base;
 };
 static_assert(sizeof(Bars) <= 256, "barrier block too large");
@@ -353,6 +354,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
     mbar_init(&bars.h0_ready, 4 * MT);
     mbar_init(&bars.h1_ready, 4 * MT);
     mbar_init(&bars.fc_done, 1);
+    mbar_init(&bars.l1_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {  // TMEM: 512 columns (3 accumulator buffers of 4*NB columns are used)
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
           const uint32_t x_addr = smem_u32(smem + sp.x + (t & 1) * S_KBLK);
           const uint32_t h0_cur = smem_u32(smem + sp.h0 + (t & 1) * nkh * S_KBLK);        // h0_t
           const uint32_t h0_prev = smem_u32(smem + sp.h0 + ((t + 1) & 1) * nkh * S_KBLK);  // h0_{t-1}
-          const uint32_t h1_prev = smem_u32(smem + sp.h1 + ((t + 1) & 1) * nkh * S_KBLK);  // h1_{t-1}
+          const uint32_t h1_prev = smem_u32(smem + sp.h1);                                    // h1_{t-1}
           // B operand (state, K-major 128B-swizzled blocks of 64 k): layer 0: [x_t (32 k)] [h0_{t-1} (H)];
           // layer 1: [h0_t (H)] [h1_{t-1} (H)].  One weight stage covers 32 k = half a block.
           const uint64_t bd_a = make_desc(layer ? h0_cur : x_addr);
@@ -487,10 +489,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
             if (lane == 0) trace_ev(a.trace, it, (layer * 3 + m) * 2 + 1);
             jobs[m]++;
           }
-          if (layer == 0) {
-            if (elect_one()) tc_commit(&bars.x_empty[t & 1]);
-            __syncwarp();
+          if (elect_one()) {
+            if (layer == 0) tc_commit(&bars.x_empty[t & 1]);
+            else tc_commit(&bars.l1_done);  // every layer-1 MMA of step t has read h1_{t-1}
           }
+          __syncwarp();
         }
       }
     }
@@ -585,7 +588,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
           tc_fence_after();
           if (q == 0 && lane == 0) trace_ev(a.trace, it, 12 + (layer * 3 + m) * 2);
           if (layer == 1 && t >= 1) mbar_wait_relaxed(&bars.fc_done, (t - 1) & 1);  // FC(t-1) has read h1[(t+1)&1]
-          uint8_t* hb = smem + (layer ? sp.h1 : sp.h0) + (t & 1) * nkh * S_KBLK + kbu * S_KBLK + el * 2;
+          uint8_t* hb = smem + (layer ? sp.h1 : sp.h0 + (t & 1) * nkh * S_KBLK) + kbu * S_KBLK + el * 2;
+          __half2 hst[NB / 2];  // layer 1: h1_t is held back until every layer-1 MMA of this step is done
 #pragma unroll
           for (int j0 = 0; j0 < NB; j0 += 8) {
             float gi[8], gf[8], gg[8], go[8];
@@ -603,8 +607,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
               if (layer == 0) c0[j0 + j] = cn; else c1[j0 + j] = cn;
               const float h = fast_sigmoid(go[j] + bo) * fast_tanh(cn);
               // row n = j0 + j: (n>>3)*1024 + (n&7)*128 + ((chunk ^ (n&7)) << 4)
-              *reinterpret_cast<__half*>(hb + (j0 >> 3) * 1024 + j * 128 + ((chunk ^ j) << 4)) = __float2half_rn(h);
+              if (layer == 0)
+                *reinterpret_cast<__half*>(hb + (j0 >> 3) * 1024 + j * 128 + ((chunk ^ j) << 4)) = __float2half_rn(h);
               go[j] = h;  // keep the fp32 h for the Linear layer
+            }
+            if (layer == 1) {
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) hst[(j0 + j) >> 1] = __floats2half2_rn(go[j], go[j + 1]);
             }
             if (layer == 1) {
               // Linear(H->2) in fp32: 16 products (2 outputs x 8 rows) summed over the warp's 32 hidden
@@ -628,10 +637,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
             }
           }
           tc_fence_before();
+          if (layer == 1) {
+            // TMEM is drained: release the accumulators first, then wait until the last layer-1 MMA of this
+            // step has consumed h1_{t-1} and overwrite it with h1_t
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.acc_empty[m]);
+            mbar_wait_relaxed(&bars.l1_done, t & 1);
+#pragma unroll
+            for (int n = 0; n < NB; n += 2) {
+              *reinterpret_cast<__half*>(hb + (n >> 3) * 1024 + (n & 7) * 128 + ((chunk ^ (n & 7)) << 4)) = __low2half(hst[n >> 1]);
+              *reinterpret_cast<__half*>(hb + ((n + 1) >> 3) * 1024 + ((n + 1) & 7) * 128 + ((chunk ^ ((n + 1) & 7)) << 4)) =
+                  __high2half(hst[n >> 1]);
+            }
+          }
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
-            mbar_arrive(&bars.acc_empty[m]);
+            if (layer == 0) mbar_arrive(&bars.acc_empty[m]);
             mbar_arrive(layer ? &bars.h1_ready : &bars.h0_ready);
             if (q == 0) trace_ev(a.trace, it, 12 + (layer * 3 + m) * 2 + 1);
           }
@@ -687,7 +709,7 @@ int sb_tc_forward(const SbTcArgs& s, cudaStream_t st) {
   static int stages_env = -1;
   if (stages_env < 0) {
     const char* e = getenv("FSN_TC_STAGES");
-    stages_env = e ? atoi(e) : 3;
+    stages_env = e ? atoi(e) : 4;
     if (stages_env < 2) stages_env = 2;
     if (stages_env > tc::MAX_STAGES) stages_env = tc::MAX_STAGES;
   }

@@ -38,7 +38,8 @@ constexpr int W_SUB2 = 64 * KS * 2;    // J2 gate sub-tile (64 units x 32 k)
 constexpr int W_ST2 = 4 * W_SUB2;      // 16 KB
 constexpr int NK0 = 1 + H / KS;        // 13 k-ranges: x, h0_{t-1}
 constexpr int NK1 = 2 * H / KS;        // 24 k-ranges: h0_t, h1_{t-1}
-constexpr int STAGES = 3;
+constexpr int GRAN = 16384;            // ring granule; a J1 k-range takes 2 granules ((i,f),(g,o)), a J2 k-range 1
+constexpr int NG = 8;                  // 128 KB of weights in flight per CTA
 constexpr int OUT_T = 8;
 constexpr int NTHREADS = 512;
 constexpr int FC_SLOTS = 12;
@@ -116,25 +117,26 @@ __global__ void pack2_kernel(const float* __restrict__ wih0, const float* __rest
 
 // ---------------------------------------------------------------- shared-memory plan (identical in both CTAs)
 constexpr uint32_t SM_W = 0;
-constexpr uint32_t SM_X = SM_W + STAGES * W_ST1;
+constexpr uint32_t SM_X = SM_W + NG * GRAN;
 constexpr uint32_t SM_H0 = SM_X + 2 * S_KBLK;
 constexpr uint32_t SM_H1 = SM_H0 + 2 * NKH * S_KBLK;
-constexpr uint32_t SM_FC = SM_H1 + 2 * NKH * S_KBLK;           // [FC_SLOTS][2][NB] float
+constexpr uint32_t SM_FC = SM_H1 + NKH * S_KBLK;               // h1 single-buffered; then [FC_SLOTS][2][NB] float
 constexpr uint32_t SM_OUT = SM_FC + FC_SLOTS * 2 * NB * 4;     // [NB][2][OUT_T] float
 constexpr uint32_t SM_ROWS = SM_OUT + NB * 2 * OUT_T * 4;
 constexpr uint32_t SM_BARS = SM_ROWS + NB * 16;
-constexpr uint32_t SM_TOTAL = SM_BARS + 256;
+constexpr uint32_t SM_TOTAL = SM_BARS + 384;
 
 struct Bars {
-  uint64_t w_full[STAGES], w_peer[STAGES], w_empty[STAGES];
+  uint64_t w_full[NG], w_empty[NG];  // indexed by granule; a stage uses the full barrier of its first granule
   uint64_t x_full[2], x_empty[2];
   uint64_t accf_j1, accf_j2[2];     // MMA -> epilogue (multicast commit)
   uint64_t acce_j1, acce_j2[2];     // epilogue (both CTAs) -> leader MMA
   uint64_t h0_ready, h1_ready;      // epilogue (both CTAs) -> leader MMA
   uint64_t fc_ready, fc_done;       // Linear partials ready (12 writer warps) / consumed (both FC warps)
+  uint64_t l1_done;                 // every layer-1 MMA of the step has completed: h1 may be overwritten
   uint32_t tmem_base;
 };
-static_assert(sizeof(Bars) <= 256, "barrier block too large");
+static_assert(sizeof(Bars) <= 384, "barrier block too large");
 
 struct RowInfo {
   int src_b, src_f;
@@ -183,7 +185,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
 
   // ---------------- one-time setup
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.w_full[s], 1); mbar_init(&bars.w_peer[s], 1); mbar_init(&bars.w_empty[s], 1); }
+    // leader: a stage is full when its own half has landed (arrive.expect_tx + bytes) AND the peer's relay arrived
+    for (int s = 0; s < NG; ++s) { mbar_init(&bars.w_full[s], leader ? 2 : 1); mbar_init(&bars.w_empty[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars.x_full[i], 2); mbar_init(&bars.x_empty[i], 1); }
     mbar_init(&bars.accf_j1, 1);
     mbar_init(&bars.acce_j1, 16);
@@ -192,6 +195,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
     mbar_init(&bars.h1_ready, 24);
     mbar_init(&bars.fc_ready, FC_SLOTS);
     mbar_init(&bars.fc_done, 2);
+    mbar_init(&bars.l1_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -225,8 +229,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
-      // ================= weight producer: this CTA's half of the stream, same sequence every step
-      uint32_t stage = 0, phase = 0;
+      // ================= weight producer: this CTA's half of the stream, same sequence every step.
+      // Ring of NG granules; phases are tracked per barrier (bit g of the masks) because a granule's full
+      // barrier is only used when the granule is the first one of a stage.
+      uint32_t g = 0, empty_ph = 0;
+      long long pw = 0, pi = 0; const long long p0 = clock64();
       for (int it = 0; it <= Tp; ++it) {
         for (int layer = 0; layer < 2; ++layer) {
           const int t = it - layer;
@@ -234,48 +241,66 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
           const int nk = layer ? NK1 : NK0;
           for (int j2 = 0; j2 < 2; ++j2) {
             const uint8_t* src = my_stream + (layer ? (j2 ? OFF_L1J2 : OFF_L1J1) : (j2 ? OFF_L0J2 : OFF_L0J1));
-            const uint32_t bytes = j2 ? W_ST2 : W_ST1;
-            for (int k = 0; k < nk; ++k, src += bytes) {
-              mbar_wait<true>(&bars.w_empty[stage], phase ^ 1);
+            const int ng = j2 ? 1 : 2;
+            for (int k = 0; k < nk; ++k, src += ng * GRAN) {
+              const uint32_t g0 = g;
+              const long long q0 = clock64();
+              for (int i = 0; i < ng; ++i) {
+                const uint32_t gi = (g0 + i) & (NG - 1);
+                mbar_wait<false>(&bars.w_empty[gi], ((empty_ph >> gi) & 1) ^ 1);
+                empty_ph ^= 1u << gi;
+              }
+              const long long q1 = clock64();
               if (elect_one()) {
-                mbar_expect_tx(&bars.w_full[stage], bytes);
-                bulk_g2s(smem + SM_W + stage * W_ST1, src, bytes, &bars.w_full[stage]);
+                mbar_expect_tx(&bars.w_full[g0], ng * GRAN);
+                for (int i = 0; i < ng; ++i)
+                  bulk_g2s(smem + SM_W + ((g0 + i) & (NG - 1)) * GRAN, src + i * GRAN, GRAN, &bars.w_full[g0]);
               }
               __syncwarp();
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              pw += q1 - q0; pi += clock64() - q1;
+              g = (g0 + ng) & (NG - 1);
             }
           }
         }
       }
+      if (a.dbg && (blockIdx.x >> 1) == 0 && lane == 0) { a.dbg[8 + rank * 4] = clock64() - p0; a.dbg[9 + rank * 4] = pw; a.dbg[10 + rank * 4] = pi; }
     } else if (warp == 1 && !leader) {
-      // ================= peer: relay "my half of stage s has landed" to the leader
-      uint32_t stage = 0, phase = 0;
+      // ================= peer: relay "my half of this stage has landed" to the leader's stage barrier
+      uint32_t g = 0, full_ph = 0;
+      long long rw = 0; const long long r0 = clock64();
       for (int it = 0; it <= Tp; ++it) {
         for (int layer = 0; layer < 2; ++layer) {
           const int t = it - layer;
           if (t < 0 || t >= Tp) continue;
-          const int n = 2 * (layer ? NK1 : NK0);
-          for (int k = 0; k < n; ++k) {
-            mbar_wait<false>(&bars.w_full[stage], phase);
-            if (elect_one()) mbar_arrive_cluster(&bars.w_peer[stage], 0);
-            __syncwarp();
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          const int nk = layer ? NK1 : NK0;
+          for (int j2 = 0; j2 < 2; ++j2) {
+            const int ng = j2 ? 1 : 2;
+            for (int k = 0; k < nk; ++k) {
+              const long long q0 = clock64();
+              mbar_wait<false>(&bars.w_full[g], (full_ph >> g) & 1);
+              rw += clock64() - q0;
+              full_ph ^= 1u << g;
+              // relaxed: the relay publishes no data of its own (the weights were written by the TMA engine into
+              // this CTA's shared memory, where this CTA's tensor core reads them)
+              if (elect_one()) mbar_arrive_cluster_relaxed(&bars.w_full[g], 0);
+              __syncwarp();
+              g = (g + ng) & (NG - 1);
+            }
           }
         }
       }
+      if (a.dbg && (blockIdx.x >> 1) == 0 && lane == 0) { a.dbg[16] = clock64() - r0; a.dbg[17] = rw; }
     } else if (warp == 1) {
       // ================= leader: MMA issuer for the pair (converged warp, one elected lane issues)
-      uint32_t stage = 0, phase = 0;
+      uint32_t g = 0, full_ph = 0;
       const uint64_t adesc0 = desc_sw64(smem_u32(smem + SM_W));
       int h0_seen = 0, h1_seen = 0;
       uint32_t j1_uses = 0, j2_uses[2] = {0, 0};
-      long long c_full = 0, c_peer = 0, c_acce = 0, c_h = 0, c_issue = 0;
-      const long long c_start = clock64();
+      bool w_ready = false;
       for (int it = 0; it <= Tp; ++it) {
         for (int layer = 0; layer < 2; ++layer) {
           const int t = it - layer;
           if (t < 0 || t >= Tp) continue;
-          long long c0 = clock64();
           if (layer == 0) {
             mbar_wait<false>(&bars.x_full[t & 1], (t >> 1) & 1);
             for (; h0_seen < t; ++h0_seen) mbar_wait<false>(&bars.h0_ready, h0_seen & 1);
@@ -283,78 +308,83 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
             for (; h0_seen < t + 1; ++h0_seen) mbar_wait<false>(&bars.h0_ready, h0_seen & 1);
             for (; h1_seen < t; ++h1_seen) mbar_wait<false>(&bars.h1_ready, h1_seen & 1);
           }
-          c_h += clock64() - c0;
           tc_fence_after();
           const uint32_t x_addr = smem_u32(smem + SM_X + (t & 1) * S_KBLK);
           const uint32_t h0_cur = smem_u32(smem + SM_H0 + (t & 1) * NKH * S_KBLK);
           const uint32_t h0_prev = smem_u32(smem + SM_H0 + ((t + 1) & 1) * NKH * S_KBLK);
-          const uint32_t h1_prev = smem_u32(smem + SM_H1 + ((t + 1) & 1) * NKH * S_KBLK);
+          const uint32_t h1_prev = smem_u32(smem + SM_H1);
           const uint64_t bd_a = desc_sw128(layer ? h0_cur : x_addr);
           const uint64_t bd_b = desc_sw128(layer ? h1_prev : h0_prev);
           const int n_a = layer ? H / KS : 1;
           const int n_b = H / KS;
-          // one stage: 2 k16 slices x 4 gates (8 MMAs on 4 different accumulators)
-          auto issue_stage = [&](uint32_t d0, uint32_t dstep, uint32_t sub16, uint32_t idesc, uint64_t bd, bool first) {
-            long long c1 = clock64();
-            mbar_wait<false>(&bars.w_full[stage], phase);
-            long long c2 = clock64();
-            mbar_wait<false>(&bars.w_peer[stage], phase);
-            long long c3 = clock64();
-            c_full += c2 - c1; c_peer += c3 - c2;
+          // one k range of 32 = 2 k16 slices x 4 gates (8 MMAs on 4 different accumulators); ONE barrier wait per
+          // stage (own half + the peer's relay arrive on the same barrier), probed early for the next stage
+          auto issue_stage = [&](uint32_t d0, uint64_t bd, bool first, bool j2) {
+            const uint32_t g0 = g, g1 = (g + 1) & (NG - 1);
+            if (!w_ready) mbar_wait<false>(&bars.w_full[g0], (full_ph >> g0) & 1);
+            full_ph ^= 1u << g0;
             tc_fence_after();
-            const uint64_t ad = adesc0 + (uint64_t)(stage * (W_ST1 >> 4));
+            const uint64_t ad0 = adesc0 + (uint64_t)(g0 * (GRAN >> 4));
+            const uint64_t ad1 = adesc0 + (uint64_t)(g1 * (GRAN >> 4));
             if (elect_one()) {
+              if (!j2) {
 #pragma unroll
-              for (int k = 0; k < 2; ++k)
+                for (int k = 0; k < 2; ++k) {
+                  const uint32_t acc = (first && k == 0) ? 0u : 1u;
+                  tc_mma2_f16(d0 + 0 * 64, ad0 + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kIdesc256, acc);
+                  tc_mma2_f16(d0 + 1 * 64, ad0 + (uint64_t)((W_SUB1 >> 4) + 2 * k), bd + (uint64_t)(2 * k), kIdesc256, acc);
+                  tc_mma2_f16(d0 + 2 * 64, ad1 + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kIdesc256, acc);
+                  tc_mma2_f16(d0 + 3 * 64, ad1 + (uint64_t)((W_SUB1 >> 4) + 2 * k), bd + (uint64_t)(2 * k), kIdesc256, acc);
+                }
+                tc_commit2_mc(&bars.w_empty[g0], 3);  // frees the granules in both CTAs
+                tc_commit2_mc(&bars.w_empty[g1], 3);
+              } else {
 #pragma unroll
-                for (int g = 0; g < 4; ++g)
-                  tc_mma2_f16(d0 + (uint32_t)g * dstep, ad + (uint64_t)(g * sub16 + 2 * k), bd + (uint64_t)(2 * k), idesc,
-                              (first && k == 0) ? 0u : 1u);
-              tc_commit2_mc(&bars.w_empty[stage], 3);  // frees the stage in both CTAs
+                for (int k = 0; k < 2; ++k)
+#pragma unroll
+                  for (int gt = 0; gt < 4; ++gt)
+                    tc_mma2_f16(d0 + (uint32_t)gt * 32, ad0 + (uint64_t)(gt * (W_SUB2 >> 4) + 2 * k), bd + (uint64_t)(2 * k),
+                                kIdesc128, (first && k == 0) ? 0u : 1u);
+                tc_commit2_mc(&bars.w_empty[g0], 3);
+              }
             }
             __syncwarp();
-            c_issue += clock64() - c3;
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            g = (g0 + (j2 ? 1 : 2)) & (NG - 1);
+            w_ready = mbar_test_wait(&bars.w_full[g], (full_ph >> g) & 1);  // probe the next stage early
           };
-          auto run_job = [&](uint32_t d0, uint32_t dstep, uint32_t sub16, uint32_t idesc) {
+          auto run_job = [&](uint32_t d0, bool j2) {
             uint64_t bd = bd_a;
 #pragma unroll 1
             for (int j = 0; j < n_a; ++j) {
-              issue_stage(d0, dstep, sub16, idesc, bd, j == 0);
+              issue_stage(d0, bd, j == 0, j2);
               bd += (j & 1) ? (uint64_t)((S_KBLK >> 4) - 4) : 4ull;
             }
             bd = bd_b;
 #pragma unroll 1
             for (int j = 0; j < n_b; ++j) {
-              issue_stage(d0, dstep, sub16, idesc, bd, false);
+              issue_stage(d0, bd, false, j2);
               bd += (j & 1) ? (uint64_t)((S_KBLK >> 4) - 4) : 4ull;
             }
           };
           // ---- J1: M=256, accumulators at columns [0,256): gate g at g*64
-          c0 = clock64();
           mbar_wait<false>(&bars.acce_j1, (j1_uses & 1) ^ 1);
-          c_acce += clock64() - c0;
           tc_fence_after();
-          run_job(tmem_base, 64, W_SUB1 >> 4, kIdesc256);
+          run_job(tmem_base, false);
           if (elect_one()) tc_commit2_mc(&bars.accf_j1, 3);
           __syncwarp();
           ++j1_uses;
           // ---- J2: M=128 over the pair, accumulators at columns 256 + layer*128: gate g at g*32
-          c0 = clock64();
           mbar_wait<false>(&bars.acce_j2[layer], (j2_uses[layer] & 1) ^ 1);
-          c_acce += clock64() - c0;
           tc_fence_after();
-          run_job(tmem_base + 256 + layer * 128, 32, W_SUB2 >> 4, kIdesc128);
+          run_job(tmem_base + 256 + layer * 128, true);
           if (elect_one()) {
             tc_commit2_mc(&bars.accf_j2[layer], 3);
             if (layer == 0) tc_commit2_mc(&bars.x_empty[t & 1], 3);
+            else tc_commit2_mc(&bars.l1_done, 3);  // every layer-1 MMA of step t has read h1_{t-1}
           }
           __syncwarp();
           ++j2_uses[layer];
         }
-      }
-      if (a.dbg && blockIdx.x == 0 && lane == 0) {
-        a.dbg[0] = clock64() - c_start; a.dbg[1] = c_full; a.dbg[2] = c_peer; a.dbg[3] = c_acce; a.dbg[4] = c_h; a.dbg[5] = c_issue;
       }
     } else if (warp == 2) {
       // ================= x_t gather for this CTA's 32 rows (base_model.py:35-44, model.py:98-111)
@@ -455,7 +485,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
         tc_fence_after();
         if (layer == 1 && t >= 1) mbar_wait<true>(&bars.fc_done, (t - 1) & 1);  // both Linear warps read step t-1
         const uint32_t gstep = is_j2 ? 32u : 64u;
-        const uint32_t hb = dst_base + (layer ? SM_H1 : SM_H0) + (uint32_t)((t & 1) * NKH * S_KBLK + kbu * S_KBLK + el * 2);
+        const uint32_t hb = dst_base + (layer ? SM_H1 : SM_H0 + (uint32_t)((t & 1) * NKH * S_KBLK)) + (uint32_t)(kbu * S_KBLK + el * 2);
+        __half2 hst[NB / 2];  // layer 1: h1_t is held back until every layer-1 MMA of this step is done
 #pragma unroll
         for (int j0 = 0; j0 < NB; j0 += 8) {
           float gi[8], gf[8], gg[8], go[8];
@@ -473,8 +504,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
             if (layer == 0) c0[j0 + j] = cn; else c1[j0 + j] = cn;
             const float h = fast_sigmoid(go[j] + bo) * fast_tanh(cn);
             // row n = j0 + j of the destination CTA: (n>>3)*1024 + (n&7)*128 + ((chunk ^ (n&7)) << 4)
-            st_cluster_b16(hb + (uint32_t)((j0 >> 3) * 1024 + j * 128 + ((chunk ^ j) << 4)), __float2half_rn(h));
+            if (layer == 0)
+              st_cluster_b16(hb + (uint32_t)((j0 >> 3) * 1024 + j * 128 + ((chunk ^ j) << 4)), __float2half_rn(h));
             go[j] = h;
+          }
+          if (layer == 1) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) hst[(j0 + j) >> 1] = __floats2half2_rn(go[j], go[j + 1]);
           }
           if (layer == 1) {
             // Linear(H->2) in fp32: 2 outputs x 8 rows, summed over the warp's 32 hidden units
@@ -497,12 +533,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
           }
         }
         tc_fence_before();
+        if (layer == 1) {
+          // accumulators drained and Linear partials written: release them, then wait until the last layer-1
+          // MMA of this step has consumed h1_{t-1} before overwriting it with h1_t
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_cluster(is_j2 ? &bars.acce_j2[layer] : &bars.acce_j1, 0);
+            mbar_arrive_cluster(&bars.fc_ready, dest);
+          }
+          mbar_wait<true>(&bars.l1_done, t & 1);
+#pragma unroll
+          for (int n = 0; n < NB; n += 2) {
+            st_cluster_b16(hb + (uint32_t)((n >> 3) * 1024 + (n & 7) * 128 + ((chunk ^ (n & 7)) << 4)), __low2half(hst[n >> 1]));
+            st_cluster_b16(hb + (uint32_t)(((n + 1) >> 3) * 1024 + ((n + 1) & 7) * 128 + ((chunk ^ ((n + 1) & 7)) << 4)),
+                           __high2half(hst[n >> 1]));
+          }
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive_cluster(is_j2 ? &bars.acce_j2[layer] : &bars.acce_j1, 0);
+          if (layer == 0) mbar_arrive_cluster(is_j2 ? &bars.acce_j2[layer] : &bars.acce_j1, 0);
           mbar_arrive_cluster(layer ? &bars.h1_ready : &bars.h0_ready, 0);
-          if (layer == 1) mbar_arrive_cluster(&bars.fc_ready, dest);
         }
       }
     }
@@ -524,7 +575,7 @@ bool sb_tc2_supported(const fsn_model_desc* d) {
   static int pair_env = -1;
   if (pair_env < 0) {
     const char* e = getenv("FSN_TC_PAIR");
-    pair_env = e ? atoi(e) : 0;  // opt-in: currently ring-latency bound
+    pair_env = e ? atoi(e) : 1;  // default: CTA-pair kernel (FSN_TC_PAIR=0 selects the single-CTA kernel)
   }
   const int Ksb = (2 * d->sb_num_neighbors + 1) + (2 * d->fb_num_neighbors + 1);
   return pair_env != 0 && d->sb_hidden == tc2::H && Ksb <= tc2::KS;
@@ -551,7 +602,7 @@ int sb_tc2_forward(const SbTcArgs& s, cudaStream_t st) {
   a.dbg = nullptr;
   static long long* dbg_buf = nullptr;
   if (getenv("FSN_TC_TRACE")) {
-    if (!dbg_buf) cudaMalloc(&dbg_buf, 8 * sizeof(long long));
+    if (!dbg_buf) { cudaMalloc(&dbg_buf, 32 * sizeof(long long)); cudaMemset(dbg_buf, 0, 32 * sizeof(long long)); }
     a.dbg = dbg_buf;
   }
   const size_t smem = tc2::SM_TOTAL + 1024;
@@ -562,9 +613,11 @@ int sb_tc2_forward(const SbTcArgs& s, cudaStream_t st) {
   tc2::sb_lstm_tc2_kernel<<<2 * pairs, tc2::NTHREADS, smem, st>>>(a);
   FSN_CHECK_LAUNCH("sb_lstm_tc2_kernel");
   if (a.dbg) {
-    long long h[8];
+    long long h[32];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tc2 producers] leader: total %lld wait-empty %lld issue %lld | peer: total %lld wait-empty %lld issue %lld | "
+                    "relay: total %lld wait-full %lld\n", h[8], h[9], h[10], h[12], h[13], h[14], h[16], h[17]);
     fprintf(stderr, "[tc2 leader cycles] total %lld | wait own stage %lld | wait peer stage %lld | wait acc drained %lld | "
                     "wait state ready %lld | issue+commit %lld  (Tp=%d)\n", h[0], h[1], h[2], h[3], h[4], h[5], a.Tp);
   }

@@ -58,8 +58,9 @@ __device__ __forceinline__ void commit_mc(uint64_t* bar, uint16_t mask) {
 
 struct Sm {
   uint8_t a[128 * 128];   // A half: 128 rows x 64 k fp16, SW128
-  uint8_t b[32 * 128];    // B half: 32 rows x 64 k
-  uint64_t ready, done1, done2;
+  uint8_t b[128 * 128];   // B half: up to 128 rows x 64 k (rows >= 32 are only used by the timing runs)
+  uint64_t ready, done1, done2, done3;
+  long long cyc[16];
   uint32_t tmem;
 };
 
@@ -76,10 +77,11 @@ probe(const __half* A, const __half* B, float* out1, float* out2) {
     mbar_init(&s.ready, 2 * 128);
     mbar_init(&s.done1, 1);
     mbar_init(&s.done2, 1);
+    mbar_init(&s.done3, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&s.tmem)));
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s.tmem)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
   // own A half -> own smem
@@ -115,6 +117,21 @@ probe(const __half* A, const __half* B, float* out1, float* out2) {
       const uint32_t idesc128 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
       for (int k = 0; k < 4; ++k) mma2(tmem + 64, ad + 2 * k, bd + 2 * k, idesc128, k ? 1u : 0u);
       commit_mc(&s.done2, 3);
+      // (3) timing: 128 MMAs round-robin over 4 accumulators (as the LSTM kernel issues them), then one commit
+      uint32_t ph3 = 0;
+      int cfg = 0;
+      for (int Mm = 256; Mm >= 128; Mm -= 128)
+        for (int Nn = 64; Nn <= 256; Nn *= 2) {
+          const uint32_t idesc = (1u << 4) | (((uint32_t)Nn >> 3) << 17) | (((uint32_t)Mm >> 4) << 24);
+          const uint32_t dstep = (Mm == 256) ? Nn : Nn / 2;
+          const int nacc = (4 * dstep <= 512) ? 4 : (512 / dstep);
+          long long t0 = clock64();
+          for (int i = 0; i < 128; ++i) mma2(tmem + (i % nacc) * dstep, ad + 2 * (i & 3), bd + 2 * (i & 3), idesc, 1u);
+          asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s.done3)) : "memory");
+          mbar_wait(&s.done3, ph3); ph3 ^= 1;
+          s.cyc[cfg++] = clock64() - t0;
+        }
+      for (int i = 0; i < cfg; ++i) printf("timing cfg %d: %lld cycles for 128 MMAs = %lld per MMA\n", i, s.cyc[i], s.cyc[i] / 128);
     }
   }
   mbar_wait(&s.done1, 0);
@@ -139,7 +156,7 @@ probe(const __half* A, const __half* B, float* out1, float* out2) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 128;" ::"r"(tmem));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
 int main() {
