@@ -249,7 +249,9 @@ def main():
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if precision == "f16_tc" and B == 256 and os.path.exists(tpath):  # ncu capture of this exact workload
-        traffic = json.load(open(tpath))["sb_lstm_tc_kernel"]["dram_bytes_per_launch"]
+        tj = json.load(open(tpath))
+        key = "sb_lstm_tc_kernel" if os.environ.get("FSN_TC_PAIR", "1") == "0" else "sb_lstm_tc2_kernel"
+        traffic = tj.get(key, {}).get("dram_bytes_per_launch")
     line = {
         "metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

@@ -15,6 +15,7 @@
 // Thread mapping (512 threads): row = tid/2 (clip), half = tid%2 -> gate columns [8*half, 8*half+8)
 // of the CTA's 16 (= 2 complete hidden units), for both layers: 32 accumulators per thread.
 #include <cooperative_groups.h>
+#include <type_traits>
 
 #include "fsn_internal.cuh"
 
@@ -119,7 +120,8 @@ __global__ void __launch_bounds__(THREADS, 1) fb_lstm_kernel(const Args a) {
   // 4-byte cp.async for the x segment whose rows (F floats) are not 16-byte aligned
   const int l_row0 = (tid >> 5) * 32 + ((tid & 31) >> 4), l_k = tid & 15;
   const int v_row0 = tid >> 2, v_k = (tid & 3) * 4;
-  const bool vec_ok = (H % 4) == 0;
+  const bool vec_ok = (H % KC) == 0;
+  const uint32_t At_s = (uint32_t)__cvta_generic_to_shared(At);
   __syncthreads();
 
   for (int p = 0; p <= Tp; ++p) {
@@ -144,35 +146,32 @@ __global__ void __launch_bounds__(THREADS, 1) fb_lstm_kernel(const Args a) {
         int seg = 0, k0 = ci * KC;
         if (ci >= nch_f) { seg = 1; k0 = (ci - nch_f) * KC; }
         if (ci >= nch_f + nch_h) { seg = 2; k0 = (ci - nch_f - nch_h) * KC; }
-        const int klen = seg ? H : F;
-        float* Ab = At + (size_t)((ci - c_begin) % NSTAGE) * ROWS * RS;
+        const uint32_t Ab = At_s + (uint32_t)((ci - c_begin) % NSTAGE) * (ROWS * RS * 4);
         if (seg != 0 && vec_ok) {
+          const float* base = (seg == 1) ? h0_prev + k0 : h1_prev + k0;
+          const unsigned rstride = (seg == 1) ? (unsigned)H : (unsigned)(Tp * H);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int r = v_row0 + 64 * j, k = k0 + v_k;
-            const bool ok = r < B && k < klen;  // H % 4 == 0: a 4-wide group is entirely in or out
-            const float* src = a.x;
-            if (ok) src = (seg == 1) ? h0_prev + (size_t)r * H + k : h1_prev + (size_t)r * Tp * H + k;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
-                             (uint32_t)__cvta_generic_to_shared(Ab + r * RS + v_k)),
-                         "l"(src), "r"(ok ? 16 : 0)
+            const int r = v_row0 + 64 * j;
+            const bool ok = r < B;  // H % KC == 0: h chunks are always full
+            const float* src = ok ? base + (size_t)r * rstride + v_k : a.x;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(Ab + (uint32_t)((r * RS + v_k) * 4)), "l"(src),
+                         "r"(ok ? 16 : 0)
                          : "memory");
           }
         } else {
+          const int klen = seg ? H : F;
           const int k = k0 + l_k;
+          const bool kok = k < klen;
+          const float* base = (seg == 0) ? a.x + (size_t)p * F + k : ((seg == 1) ? h0_prev + k : h1_prev + k);
+          const size_t rstride = (seg == 0) ? (size_t)Tp * F : ((seg == 1) ? (size_t)H : (size_t)Tp * H);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int r = l_row0 + 2 * j;
-            const bool ok = r < B && k < klen;
-            const float* src = a.x;  // any valid address when the element is zero-filled
-            if (ok) {
-              if (seg == 0) src = a.x + ((size_t)r * Tp + p) * F + k;
-              else if (seg == 1) src = h0_prev + (size_t)r * H + k;
-              else src = h1_prev + (size_t)r * Tp * H + k;
-            }
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(
-                             (uint32_t)__cvta_generic_to_shared(Ab + r * RS + l_k)),
-                         "l"(src), "r"(ok ? 4 : 0)
+            const bool ok = kok && r < B;
+            const float* src = ok ? base + (size_t)r * rstride : a.x;  // any valid address when zero-filled
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(Ab + (uint32_t)((r * RS + l_k) * 4)), "l"(src),
+                         "r"(ok ? 4 : 0)
                          : "memory");
           }
         }
@@ -194,26 +193,35 @@ __global__ void __launch_bounds__(THREADS, 1) fb_lstm_kernel(const Args a) {
       const float* w1 = ((seg == 1) ? W1 : W1 + (size_t)H * 16) + (size_t)k0 * 16 + cq * 4;   // layer-1 rows
       const bool use0 = (seg <= 1) && do0, use1 = (seg >= 1) && do1;
       const float* ar = Ab + row_base * RS;
-      // rows beyond klen inside the chunk are zero-filled, so the full KC is always safe to consume
+      // rows beyond klen inside the chunk are zero-filled, so the full KC is always safe to consume; the three
+      // segment kinds get their own straight-line code (branch once per chunk, not per FMA group)
+      auto consume = [&](auto use0_c, auto use1_c, auto scale_c) {
+        constexpr bool U0 = decltype(use0_c)::value, U1 = decltype(use1_c)::value, SC = decltype(scale_c)::value;
 #pragma unroll
-      for (int k4 = 0; k4 < KC; k4 += 4) {
-        float4 a4[4];
+        for (int k4 = 0; k4 < KC; k4 += 4) {
+          float4 a4[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) a4[r] = *reinterpret_cast<const float4*>(ar + (8 * r) * RS + k4);
-        if (seg == 0) {
+          for (int r = 0; r < 4; ++r) a4[r] = *reinterpret_cast<const float4*>(ar + (8 * r) * RS + k4);
+          if (SC) {
 #pragma unroll
-          for (int r = 0; r < 4; ++r) { a4[r].x *= rs[r]; a4[r].y *= rs[r]; a4[r].z *= rs[r]; a4[r].w *= rs[r]; }
+            for (int r = 0; r < 4; ++r) { a4[r].x *= rs[r]; a4[r].y *= rs[r]; a4[r].z *= rs[r]; a4[r].w *= rs[r]; }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float av[4] = {q == 0 ? a4[0].x : q == 1 ? a4[0].y : q == 2 ? a4[0].z : a4[0].w,
+                                 q == 0 ? a4[1].x : q == 1 ? a4[1].y : q == 2 ? a4[1].z : a4[1].w,
+                                 q == 0 ? a4[2].x : q == 1 ? a4[2].y : q == 2 ? a4[2].z : a4[2].w,
+                                 q == 0 ? a4[3].x : q == 1 ? a4[3].y : q == 2 ? a4[3].z : a4[3].w};
+            if (U0) fma_4x4(acc0, av, *reinterpret_cast<const float4*>(w0 + (k4 + q) * 16));
+            if (U1) fma_4x4(acc1, av, *reinterpret_cast<const float4*>(w1 + (k4 + q) * 16));
+          }
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float av[4] = {q == 0 ? a4[0].x : q == 1 ? a4[0].y : q == 2 ? a4[0].z : a4[0].w,
-                               q == 0 ? a4[1].x : q == 1 ? a4[1].y : q == 2 ? a4[1].z : a4[1].w,
-                               q == 0 ? a4[2].x : q == 1 ? a4[2].y : q == 2 ? a4[2].z : a4[2].w,
-                               q == 0 ? a4[3].x : q == 1 ? a4[3].y : q == 2 ? a4[3].z : a4[3].w};
-          if (use0) fma_4x4(acc0, av, *reinterpret_cast<const float4*>(w0 + (k4 + q) * 16));
-          if (use1) fma_4x4(acc1, av, *reinterpret_cast<const float4*>(w1 + (k4 + q) * 16));
-        }
-      }
+      };
+      using T_ = std::true_type; using F_ = std::false_type;
+      if (seg == 0) { if (use0) consume(T_{}, F_{}, T_{}); }
+      else if (use0 && use1) consume(T_{}, T_{}, F_{});
+      else if (use0) consume(T_{}, F_{}, F_{});
+      else if (use1) consume(F_{}, T_{}, F_{});
     }
     // ---- cell updates of the thread's unit for its 4 rows (gate order i,f,g,o), write h
     if (unit_ok) {

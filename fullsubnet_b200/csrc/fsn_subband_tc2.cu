@@ -538,8 +538,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
           // MMA of this step has consumed h1_{t-1} before overwriting it with h1_t
           __syncwarp();
           if (lane == 0) {
-            mbar_arrive_cluster(is_j2 ? &bars.acce_j2[layer] : &bars.acce_j1, 0);
-            mbar_arrive_cluster(&bars.fc_ready, dest);
+            fence_release_cluster();  // Linear partials (st.shared::cluster) before the arrives below
+            mbar_arrive_cluster_relaxed(is_j2 ? &bars.acce_j2[layer] : &bars.acce_j1, 0);
+            mbar_arrive_cluster_relaxed(&bars.fc_ready, dest);
           }
           mbar_wait<true>(&bars.l1_done, t & 1);
 #pragma unroll
@@ -552,8 +553,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (layer == 0) mbar_arrive_cluster(is_j2 ? &bars.acce_j2[layer] : &bars.acce_j1, 0);
-          mbar_arrive_cluster(layer ? &bars.h1_ready : &bars.h0_ready, 0);
+          fence_release_cluster();  // h (st.shared::cluster) of the whole warp before the arrives below
+          if (layer == 0) mbar_arrive_cluster_relaxed(is_j2 ? &bars.acce_j2[layer] : &bars.acce_j1, 0);
+          mbar_arrive_cluster_relaxed(layer ? &bars.h1_ready : &bars.h0_ready, 0);
         }
       }
     }

@@ -51,6 +51,9 @@ __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint3
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa(smem_u32(bar), rank))
                : "memory");
 }
+// one cluster-scope release fence, to be followed by any number of relaxed arrives (release pattern with a
+// single fence instead of one per arrive)
+__device__ __forceinline__ void fence_release_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
