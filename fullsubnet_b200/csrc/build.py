@@ -26,7 +26,7 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    flags = [f for f in FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("FSN_EXTRA_NVCC_FLAGS", "").split()
     objs = []
     procs = []
     for s in SOURCES:

@@ -23,6 +23,15 @@
 #include "fsn_internal.cuh"
 #include "fsn_tc_ptx.cuh"
 
+#ifndef FSN_TC2_ACCOUNT
+#define FSN_TC2_ACCOUNT 0   // 1: cycle accounting of the leader's MMA warp (diagnostic builds, FSN_TC_TRACE=1)
+#endif
+#if FSN_TC2_ACCOUNT
+#define ACCT(...) __VA_ARGS__
+#else
+#define ACCT(...)
+#endif
+
 namespace fsn {
 namespace tc2 {
 using namespace ptx;
@@ -297,10 +306,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
       int h0_seen = 0, h1_seen = 0;
       uint32_t j1_uses = 0, j2_uses[2] = {0, 0};
       bool w_ready = false;
+      ACCT(long long c_full = 0, c_acce = 0, c_h = 0, c_issue = 0; const long long c_start = clock64();)
       for (int it = 0; it <= Tp; ++it) {
         for (int layer = 0; layer < 2; ++layer) {
           const int t = it - layer;
           if (t < 0 || t >= Tp) continue;
+          ACCT(long long c0 = clock64();)
           if (layer == 0) {
             mbar_wait<false>(&bars.x_full[t & 1], (t >> 1) & 1);
             for (; h0_seen < t; ++h0_seen) mbar_wait<false>(&bars.h0_ready, h0_seen & 1);
@@ -308,6 +319,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
             for (; h0_seen < t + 1; ++h0_seen) mbar_wait<false>(&bars.h0_ready, h0_seen & 1);
             for (; h1_seen < t; ++h1_seen) mbar_wait<false>(&bars.h1_ready, h1_seen & 1);
           }
+          ACCT(c_h += clock64() - c0;)
           tc_fence_after();
           const uint32_t x_addr = smem_u32(smem + SM_X + (t & 1) * S_KBLK);
           const uint32_t h0_cur = smem_u32(smem + SM_H0 + (t & 1) * NKH * S_KBLK);
@@ -321,7 +333,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
           // stage (own half + the peer's relay arrive on the same barrier), probed early for the next stage
           auto issue_stage = [&](uint32_t d0, uint64_t bd, bool first, bool j2) {
             const uint32_t g0 = g, g1 = (g + 1) & (NG - 1);
+            ACCT(const long long c1 = clock64();)
             if (!w_ready) mbar_wait<false>(&bars.w_full[g0], (full_ph >> g0) & 1);
+            ACCT(const long long c2 = clock64(); c_full += c2 - c1;)
             full_ph ^= 1u << g0;
             tc_fence_after();
             const uint64_t ad0 = adesc0 + (uint64_t)(g0 * (GRAN >> 4));
@@ -351,6 +365,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
             __syncwarp();
             g = (g0 + (j2 ? 1 : 2)) & (NG - 1);
             w_ready = mbar_test_wait(&bars.w_full[g], (full_ph >> g) & 1);  // probe the next stage early
+            ACCT(c_issue += clock64() - c2;)
           };
           auto run_job = [&](uint32_t d0, bool j2) {
             uint64_t bd = bd_a;
@@ -367,14 +382,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
             }
           };
           // ---- J1: M=256, accumulators at columns [0,256): gate g at g*64
+          ACCT(c0 = clock64();)
           mbar_wait<false>(&bars.acce_j1, (j1_uses & 1) ^ 1);
+          ACCT(c_acce += clock64() - c0;)
           tc_fence_after();
           run_job(tmem_base, false);
           if (elect_one()) tc_commit2_mc(&bars.accf_j1, 3);
           __syncwarp();
           ++j1_uses;
           // ---- J2: M=128 over the pair, accumulators at columns 256 + layer*128: gate g at g*32
+          ACCT(c0 = clock64();)
           mbar_wait<false>(&bars.acce_j2[layer], (j2_uses[layer] & 1) ^ 1);
+          ACCT(c_acce += clock64() - c0;)
           tc_fence_after();
           run_job(tmem_base + 256 + layer * 128, true);
           if (elect_one()) {
@@ -386,6 +405,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
           ++j2_uses[layer];
         }
       }
+      ACCT(if (a.dbg && blockIdx.x == 0 && lane == 0) {
+        a.dbg[0] = clock64() - c_start; a.dbg[1] = c_full; a.dbg[2] = 0; a.dbg[3] = c_acce; a.dbg[4] = c_h; a.dbg[5] = c_issue;
+      })
     } else if (warp == 2) {
       // ================= x_t gather for this CTA's 32 rows (base_model.py:35-44, model.py:98-111)
       const int nmag = 2 * a.Ns + 1;
