@@ -35,6 +35,7 @@ struct StepParams {
   float* c;
   // SEG0_DENSE: x = x0[row * x0_row_stride + k] * (row_scale ? row_scale[row] : 1)
   const float* x0; size_t x0_row_stride; const float* row_scale;
+  int row_scale_div;  // scale index = row / row_scale_div (0 or 1: per row)
   // SEG0_GATHER: sub-band unit of row r at frame t (base_model.py:13-46 + model.py:98-111)
   const float* magT; const float* fbT; const float* inv2;
   int F, Tp, t, Ns, Nf;
@@ -43,11 +44,15 @@ struct StepParams {
 
 int lstm_step_launch(const StepParams& p, int mode, cudaStream_t st);
 int fc_gemm_launch(const float* A, const float* W, const float* bias, float* out, int M, int K, int O, int act,
-                   cudaStream_t st);
+                   cudaStream_t st, bool w_kmajor = false);
+// out[row*row_stride + o*o_stride] = act(h[row,:] . W[o,:] + b[o]), one warp per row (small O)
+int rows_fc_launch(const float* h, int R, int H, const float* W, const float* bias, int O, int act, float* out,
+                   size_t row_stride, size_t o_stride, cudaStream_t st);
 int sb_fc_step_launch(const float* h, int R, int H, const float* W, const float* bias, int O, int act, float* crm,
                       int Fsub, int T_out, int t_out, cudaStream_t st);
 int transpose_mag_launch(const float* in, float* out, int B, int F, int T, int T_pad, cudaStream_t st);
 int clip_stats_launch(const float* x, int B, int T_pad, int F, int N, float2* fs, float2* sums, cudaStream_t st);
+int clip_reduce_only_launch(const float2* fs, int B, int T_pad, float2* sums, cudaStream_t st);
 int norm_scales_launch(const float2* mag_sums, const float2* fb_sums, int B, float cnt1, float cnt2, float* inv1,
                        float* inv2, cudaStream_t st);
 

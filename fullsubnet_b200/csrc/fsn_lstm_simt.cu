@@ -100,7 +100,7 @@ template <int MODE>
 __device__ __forceinline__ float load_seg0(const StepParams& p, int row, int k, int src_b, int src_f) {
   if (MODE == SEG0_DENSE) {
     const float v = p.x0[(size_t)row * p.x0_row_stride + k];
-    return p.row_scale ? v * p.row_scale[row] : v;
+    return p.row_scale ? v * p.row_scale[p.row_scale_div > 1 ? row / p.row_scale_div : row] : v;
   } else {
     const int nmag = 2 * p.Ns + 1;
     const size_t base = ((size_t)src_b * p.Tp + p.t) * p.F;
@@ -220,7 +220,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // out[M,O] = act(A[M,K] W[O,K]^T + b)   (full-band Linear + ReLU over all (b,t) rows at once)
 __global__ void __launch_bounds__(256)
 fc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
-               float* __restrict__ out, int M, int K, int O, int act) {
+               float* __restrict__ out, int M, int K, int O, int act, int w_kmajor) {
   __shared__ __align__(16) float As[16][64];
   __shared__ float Ws[16][64 + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -236,7 +236,7 @@ fc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ W, const f
     for (int j = 0; j < 4; ++j) {
       const int k = k0 + l_k + j;
       As[l_k + j][l_row] = (row0 + l_row < M && k < K) ? A[(size_t)(row0 + l_row) * K + k] : 0.f;
-      Ws[l_k + j][l_row] = (o0 + l_row < O && k < K) ? W[(size_t)(o0 + l_row) * K + k] : 0.f;
+      Ws[l_k + j][l_row] = (o0 + l_row < O && k < K) ? (w_kmajor ? W[(size_t)k * O + o0 + l_row] : W[(size_t)(o0 + l_row) * K + k]) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -259,15 +259,15 @@ fc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ W, const f
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int o = o0 + tx + 16 * j;
-      if (o < O) out[(size_t)row * O + o] = apply_act(acc[i][j] + bias[o], act);
+      if (o < O) out[(size_t)row * O + o] = apply_act(acc[i][j] + (bias ? bias[o] : 0.f), act);
     }
   }
 }
 
 int fc_gemm_launch(const float* A, const float* W, const float* bias, float* out, int M, int K, int O, int act,
-                   cudaStream_t st) {
+                   cudaStream_t st, bool w_kmajor) {
   dim3 grid(cdiv(M, 64), cdiv(O, 64));
-  fc_gemm_kernel<<<grid, 256, 0, st>>>(A, W, bias, out, M, K, O, act);
+  fc_gemm_kernel<<<grid, 256, 0, st>>>(A, W, bias, out, M, K, O, act, w_kmajor ? 1 : 0);
   FSN_CHECK_LAUNCH("fc_gemm_kernel");
   return FSN_OK;
 }
@@ -290,6 +290,28 @@ __global__ void sb_fc_step_kernel(const float* __restrict__ h, int R, int H, con
   }
 }
 
+__global__ void rows_fc_kernel(const float* __restrict__ h, int R, int H, const float* __restrict__ W,
+                               const float* __restrict__ bias, int O, int act, float* __restrict__ out, size_t row_stride,
+                               size_t o_stride) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* hp = h + (size_t)row * H;
+  for (int o = 0; o < O; ++o) {
+    float s = 0.f;
+    for (int k = lane; k < H; k += 32) s = fmaf(hp[k], W[(size_t)o * H + k], s);
+    s = warp_sum(s);
+    if (lane == 0) out[(size_t)row * row_stride + (size_t)o * o_stride] = apply_act(s + bias[o], act);
+  }
+}
+
+int rows_fc_launch(const float* h, int R, int H, const float* W, const float* bias, int O, int act, float* out,
+                   size_t row_stride, size_t o_stride, cudaStream_t st) {
+  rows_fc_kernel<<<cdiv(R, 8), 256, 0, st>>>(h, R, H, W, bias, O, act, out, row_stride, o_stride);
+  FSN_CHECK_LAUNCH("rows_fc_kernel");
+  return FSN_OK;
+}
+
 int sb_fc_step_launch(const float* h, int R, int H, const float* W, const float* bias, int O, int act, float* crm,
                       int Fsub, int T_out, int t_out, cudaStream_t st) {
   sb_fc_step_kernel<<<cdiv(R, 8), 256, 0, st>>>(h, R, H, W, bias, O, act, crm, Fsub, T_out, t_out);
@@ -308,6 +330,12 @@ int clip_stats_launch(const float* x, int B, int T_pad, int F, int N, float2* fs
   const int rows = B * T_pad;
   frame_stats_kernel<<<cdiv(rows, 8), 256, 0, st>>>(x, rows, F, N, fs);
   FSN_CHECK_LAUNCH("frame_stats_kernel");
+  clip_reduce_kernel<<<B, 256, 0, st>>>(fs, T_pad, sums);
+  FSN_CHECK_LAUNCH("clip_reduce_kernel");
+  return FSN_OK;
+}
+
+int clip_reduce_only_launch(const float2* fs, int B, int T_pad, float2* sums, cudaStream_t st) {
   clip_reduce_kernel<<<B, 256, 0, st>>>(fs, T_pad, sums);
   FSN_CHECK_LAUNCH("clip_reduce_kernel");
   return FSN_OK;

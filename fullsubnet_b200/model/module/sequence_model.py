@@ -24,11 +24,11 @@ class SequenceModel(nn.Module):
         else:
             # sequence_model.py:59-79: GRU exists upstream; this build covers the LSTM configs only
             raise NotImplementedError(f"Not implemented {sequence_model}")
-        if bidirectional or num_layers != 2:
-            raise NotImplementedError("libfsn_b200 builds the uni-directional 2-layer LSTM stack of FullSubNet")
-        if not int(output_size):
-            raise NotImplementedError("libfsn_b200 expects the Linear output layer (output_size > 0)")
-        self.fc_output_layer = nn.Linear(hidden_size, output_size)
+        if bidirectional or num_layers not in (1, 2):
+            raise NotImplementedError("libfsn_b200 builds uni-directional 1- or 2-layer LSTM stacks")
+        if int(output_size):  # sequence_model.py:82-84 (no Linear layer when output_size == 0)
+            self.fc_output_layer = nn.Linear(hidden_size, output_size)
+        self.num_layers = num_layers
         if output_activate_function:
             if output_activate_function not in ("Tanh", "ReLU", "ReLU6"):
                 raise NotImplementedError(f"Not implemented activation function {output_activate_function}")
@@ -36,8 +36,26 @@ class SequenceModel(nn.Module):
         self.output_size = output_size
         self.input_size, self.hidden_size = input_size, hidden_size
 
+    @staticmethod
+    def _check(p, name):
+        if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+            raise RuntimeError(f"fullsubnet_b200: parameter {name} must be a contiguous fp32 CUDA tensor "
+                               f"(got {p.device}, {p.dtype}); call model.cuda() first - there is no CPU path.")
+        return p.data_ptr()
+
+    def layer_struct(self, l: int = 0) -> "_lib.LstmLayer":
+        """Raw device pointers of LSTM layer ``l`` (fsn_lstm_layer)."""
+        lstm = self.sequence_model
+        return _lib.LstmLayer(*(self._check(getattr(lstm, f"{n}_l{l}"), f"{n}_l{l}")
+                                for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")))
+
+    def fc_ptrs(self):
+        return (self._check(self.fc_output_layer.weight, "fc_output_layer.weight"),
+                self._check(self.fc_output_layer.bias, "fc_output_layer.bias"))
+
     def weight_struct(self) -> "_lib.SeqWeights":
         """Raw device pointers into the parameter storage (fsn_seq_weights)."""
+        assert self.num_layers == 2 and hasattr(self, "fc_output_layer")
         w = _lib.SeqWeights()
         lstm = self.sequence_model
         for l in range(2):

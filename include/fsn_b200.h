@@ -140,6 +140,49 @@ int fsn_enhance(const fsn_model_desc* d, const fsn_seq_weights* fb, const fsn_se
                 float* enhanced, float* crm_out, void* workspace, size_t workspace_bytes,
                 fsn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * recipes/dns_interspeech_2020/fast_fullsubnet/model.py:11-202  Model (BASELINE config 4)
+ *   MelScale(F->M) -> norm -> encoder LSTM(M->He1), LSTM(He1->He2)+Linear(M)+ReLU -> unfold(noisy mel, Nn) ||
+ *   unfold(encoder out, Ne) -> real-time down-sampling x`shrink` -> norm -> bottleneck 2xLSTM(Hb)+Linear(1)+ReLU on
+ *   B*M rows -> up-sampling -> decoder LSTM(2M->Hd), LSTM(Hd->Hd)+Linear(2F) -> [B,2,F,T].  fp32 kernels.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct fsn_lstm_layer {
+  const float* w_ih; /* [4H, K] */
+  const float* w_hh; /* [4H, H] */
+  const float* b_ih;
+  const float* b_hh;
+} fsn_lstm_layer;
+
+typedef struct fsn_fast_desc {
+  int32_t num_freqs;   /* encoder_input_size (257) */
+  int32_t look_ahead;
+  int32_t shrink_size;
+  int32_t num_mels;    /* 64 */
+  int32_t enc1_hidden; /* 384 */
+  int32_t enc2_hidden; /* 257 */
+  int32_t bn_hidden;   /* bottleneck_hidden_size */
+  int32_t bn_layers;   /* bottleneck_num_layers (2) */
+  int32_t dec_hidden;  /* 512 */
+  int32_t noisy_num_neighbors; /* noisy_input_num_neighbors */
+  int32_t enc_num_neighbors;   /* encoder_output_num_neighbors */
+  int32_t reserved;
+} fsn_fast_desc;
+
+typedef struct fsn_fast_weights {
+  const float* mel_fb;  /* mel_scale.fb [F, M] */
+  fsn_lstm_layer enc1, enc2;
+  const float* enc_fc_w; const float* enc_fc_b;   /* [M, He2], [M] */
+  fsn_lstm_layer bn[2];
+  const float* bn_fc_w; const float* bn_fc_b;     /* [1, Hb], [1] */
+  fsn_lstm_layer dec1, dec2;
+  const float* dec_fc_w; const float* dec_fc_b;   /* [2F, Hd], [2F] */
+} fsn_fast_weights;
+
+size_t fsn_fast_workspace_bytes(const fsn_fast_desc* d, int B, int T);
+/* Model.forward (fast_fullsubnet/model.py:143-202): mix_mag [B,1,F,T] -> [B,2,F,T] */
+int fsn_fast_model_forward(const fsn_fast_desc* d, const fsn_fast_weights* w, const float* mix_mag, int B, int T,
+                           float* out, void* workspace, size_t workspace_bytes, fsn_stream_t stream);
+
 /* Opt-in stage timing for bench.py: when enabled, fsn_model_forward / fsn_enhance bracket their
  * stages with CUDA events on `stream` (thread-local, created lazily).  After the caller has
  * synchronised the stream, fsn_last_stage_ms(stage) returns the device time of the last call:

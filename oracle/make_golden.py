@@ -118,6 +118,24 @@ def main():
         res["y"] = yf.numpy()
         print(tag, "crm range", float(crm.min()), float(crm.max()), "wav max", float(np.abs(wav).max()))
     np.savez_compressed(os.path.join(out_dir, "model_full.npz"), **res)
+    # ------------------------------------------------------- fast_fullsubnet (A13)
+    from oracle import fast_fullsubnet_oracle as FO
+    ti = types.ModuleType("torchinfo"); ti.summary = lambda *a, **k: None
+    sys.modules.setdefault("torchinfo", ti)
+    from fast_fullsubnet.model import Model as FastModel
+    fargs = dict(FO.DEFAULT_FAST_ARGS)
+    fsd = FO.make_fast_state_dict(seed=3, args=fargs)
+    fm = FastModel(**fargs).eval()
+    ref_fb = fm.state_dict()["mel_scale.fb"].clone()
+    fm.load_state_dict(fsd, strict=True)
+    yq = O.make_noisy(3, 6000, seed=9, speechlike=True)
+    magq = feature.stft(yq, 512, 256, 512)[0]
+    with torch.no_grad():
+        fo_b1 = fm(magq[:1].unsqueeze(1))
+        fo_b3 = fm(magq.unsqueeze(1))
+    np.savez_compressed(os.path.join(out_dir, "fast_full.npz"), y=yq.numpy(), mag=magq.numpy(),
+                        out_b1=fo_b1.numpy(), out_b3=fo_b3.numpy(), mel_fb=ref_fb.numpy())
+    print("fast crm range", float(fo_b3.min()), float(fo_b3.max()))
     for f in sorted(os.listdir(out_dir)):
         print(f, os.path.getsize(os.path.join(out_dir, f)))
 

@@ -94,3 +94,17 @@ def test_initialize_module_plugin_mechanism():
     assert type(m).__name__ == "Model"
     cls = initialize_module("fullsubnet_b200.inferencer.Inferencer", initialize=False)
     assert cls.__name__ == "Inferencer"
+
+
+def test_fast_fullsubnet_state_dict_contract():
+    from fullsubnet_b200.fast_fullsubnet.model import Model
+    from oracle import fast_fullsubnet_oracle as FO
+    m = Model(**FO.DEFAULT_FAST_ARGS)
+    sd = m.state_dict()
+    want = FO.fast_state_dict_shapes()  # validated against the reference by oracle/make_golden.py (strict load)
+    assert list(sd.keys()) == [k for k, _ in want] and [tuple(v.shape) for v in sd.values()] == [s for _, s in want]
+    assert sum(p.numel() for p in m.parameters()) == 6842895
+    assert torch.allclose(sd["mel_scale.fb"], FO.melscale_fbanks(257, 64))
+    m.load_state_dict(FO.make_fast_state_dict(3), strict=True)
+    with pytest.raises(RuntimeError):
+        m.eval()(torch.zeros(1, 1, 257, 4))  # no CPU path

@@ -217,3 +217,27 @@ def test_full_size_batch_properties(dev):
     ref_wav, ref_crm = O.enhance(y[255:256], sd, return_crm=True)
     assert rel_max(crm[255:256].cpu(), ref_crm) < CRM_TOL and rel_l2(crm[255:256].cpu(), ref_crm) < CRM_TOL
     assert np.abs(out[255:256].cpu().numpy() - ref_wav.numpy()).max() < WAV_TOL
+
+
+# ------------------------------------------------------------------ fast_fullsubnet (config 4, A13)
+def test_fast_fullsubnet_matches_reference(golden, dev):
+    from fullsubnet_b200.fast_fullsubnet.model import Model
+    from oracle import fast_fullsubnet_oracle as FO
+    g = golden("fast_full")
+    m = Model(**FO.DEFAULT_FAST_ARGS)
+    m.load_state_dict(FO.make_fast_state_dict(seed=3), strict=True)
+    m = m.to(dev).eval()
+    mag = T(g["mag"], dev).unsqueeze(1)
+    with torch.no_grad():
+        o1 = m(mag[:1])
+        o3 = m(mag)
+    assert o3.shape == g["out_b3"].shape
+    assert rel_max(o1.cpu(), g["out_b1"]) < 5e-5 and rel_max(o3.cpu(), g["out_b3"]) < 5e-5
+    assert rel_l2(o3.cpu(), g["out_b3"]) < 5e-5
+    # odd / even frame counts exercise the last (short) down-sampling block
+    for Tn in (7, 8):
+        x = torch.rand(2, 1, 257, Tn)
+        ref = FO.fast_model_forward(x, FO.make_fast_state_dict(seed=3))
+        with torch.no_grad():
+            got = m(x.to(dev))
+        assert rel_max(got.cpu(), ref) < 5e-5, Tn

@@ -108,3 +108,20 @@ def test_reflect_count_closed_form():
     mu = cat.mean(dim=(1, 2, 3))
     closed = ((mag[:, 0].sum(-1) * torch.from_numpy(c).float()).sum(-1) + fb.sum(dim=(1, 2, 3))) / (257 * 32 * 9)
     assert rel_max(closed, mu) < 1e-5
+
+
+def test_fast_fullsubnet_oracle_matches_reference(golden):
+    from oracle import fast_fullsubnet_oracle as FO
+    g = golden("fast_full")
+    assert rel_max(FO.melscale_fbanks(257, 64), g["mel_fb"]) < 1e-6  # torchaudio MelScale buffer
+    sd = FO.make_fast_state_dict(seed=3)
+    mag = T(g["mag"]).unsqueeze(1)
+    assert rel_max(FO.fast_model_forward(mag[:1], sd), g["out_b1"]) < 2e-5
+    out, mid = FO.fast_model_forward(mag, sd, return_intermediates=True)
+    assert out.shape == g["out_b3"].shape and rel_max(out, g["out_b3"]) < 2e-5
+    # down/up-sampling restatement on odd and even lengths
+    for Tn in (2, 3, 8, 9):
+        x = torch.arange(Tn, dtype=torch.float32).reshape(1, 1, 1, Tn)
+        d = FO.real_time_downsampling(x, 2)
+        assert d.shape[-1] == 1 + (Tn - 1 + 1) // 2
+        assert FO.real_time_upsampling(d, 2, Tn).shape[-1] == Tn
