@@ -152,6 +152,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=256, help="clips per GPU (configs[1]: 256)")
     ap.add_argument("--precision", default="auto")
+    ap.add_argument("--model", default="fullsubnet", choices=["fullsubnet", "fast_fullsubnet"],
+                    help="fullsubnet = BASELINE configs[1] (the headline); fast_fullsubnet = configs[3] (use --batch 512)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -179,10 +181,19 @@ def main():
     lib = _lib.load()
     B, L = args.batch, SR * CLIP_SECONDS
     T = 1 + L // HOP
-    model = Model(**O.DEFAULT_MODEL_ARGS, precision=args.precision)
-    model.load_state_dict(O.make_state_dict(seed=0), strict=True)
-    model = model.to(dev).eval()
-    precision = model._resolve_precision()
+    if args.model == "fast_fullsubnet":
+        from fullsubnet_b200.fast_fullsubnet.model import Model as FastModel
+        from oracle import fast_fullsubnet_oracle as FO
+        model = FastModel(**FO.DEFAULT_FAST_ARGS, **({"precision": args.precision} if "precision" in
+                                                     FastModel.__init__.__code__.co_varnames else {}))
+        model.load_state_dict(FO.make_fast_state_dict(seed=0), strict=True)
+        model = model.to(dev).eval()
+        precision = getattr(model, "_resolve_precision", lambda: "fp32")()
+    else:
+        model = Model(**O.DEFAULT_MODEL_ARGS, precision=args.precision)
+        model.load_state_dict(O.make_state_dict(seed=0), strict=True)
+        model = model.to(dev).eval()
+        precision = model._resolve_precision()
     inf = Inferencer(model=model, device=dev)
     host_in = O.make_noisy(B, L, seed=rank).pin_memory()  # every rank enhances its own clips
     host_out = torch.empty(B, L, dtype=torch.float32).pin_memory()
@@ -220,7 +231,10 @@ def main():
         return ms / steps, [s / steps for s in stage]
 
     def step_resident():
-        model.enhance(x_dev, N_FFT, HOP, WIN)
+        if args.model == "fullsubnet":
+            model.enhance(x_dev, N_FFT, HOP, WIN)
+        else:
+            inf.enhance_batch(x_dev)
 
     def step_e2e():
         out = inf.enhance_batch(host_in)  # H2D inside
@@ -257,8 +271,11 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f16xf32acc" if precision == "f16_tc" else "f32", "data": "synthetic",
         "rtf_x": value / (SR / HOP),
-        "config": {"workload": f"fullsubnet inference, batch={B} x 4 s 16 kHz synthetic clips per GPU, "
-                               "n_fft=512 hop=256 N=15, 2xLSTM-512 fb + 2xLSTM-384 sb (BASELINE configs[1])",
+        "config": {"workload": (f"fullsubnet inference, batch={B} x 4 s 16 kHz synthetic clips per GPU, "
+                                "n_fft=512 hop=256 N=15, 2xLSTM-512 fb + 2xLSTM-384 sb (BASELINE configs[1])"
+                                if args.model == "fullsubnet" else
+                                f"fast_fullsubnet inference, batch={B} x 4 s 16 kHz synthetic clips per GPU "
+                                "(BASELINE configs[3])"),
                    "clips_per_gpu": B, "frames_per_clip": T, "precision": precision,
                    "l2": "256 MiB flush write between timed iterations", "parallelism": f"clips sharded x{world}"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e,

@@ -64,7 +64,25 @@ class Inferencer:
         """The same path for B independent clips in ONE library call (fsn_enhance): pinned/host or device
         ``noisy`` [B,L] -> device tensor [B,L].  Equivalent to looping full_band_crm_mask over the clips."""
         x = noisy.to(self.device, non_blocking=True)
-        return self.model.enhance(x, self.n_fft, self.hop_length, self.win_length)
+        if hasattr(self.model, "enhance"):  # fullsubnet: one fused library call
+            return self.model.enhance(x, self.n_fft, self.hop_length, self.win_length)
+        # other models (fast_fullsubnet): same flow, three library calls (stft -> model -> mask + istft)
+        import ctypes as C  # noqa: F401
+        from . import _lib
+        B, L = x.shape
+        F, T = self.n_fft // 2 + 1, 1 + L // self.hop_length
+        buf = torch.empty(3, B, F, T, dtype=torch.float32, device=x.device)
+        out = torch.empty(B, L, dtype=torch.float32, device=x.device)
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            st = _lib.stream_ptr(x.device)
+            x = _lib.require_cuda(x, "noisy")
+            _lib.check(lib.fsn_stft(x.data_ptr(), B, L, self.n_fft, self.hop_length, self.win_length, buf[0].data_ptr(),
+                                    None, buf[1].data_ptr(), buf[2].data_ptr(), None, 0, st))
+            crm = self.model(buf[0].unsqueeze(1)).contiguous()
+            _lib.check(lib.fsn_istft(buf[1].data_ptr(), buf[2].data_ptr(), 1, crm.data_ptr(), B, T, self.n_fft,
+                                     self.hop_length, self.win_length, L, out.data_ptr(), st))
+        return out
 
     @torch.no_grad()
     def __call__(self, clips):
