@@ -34,13 +34,14 @@ class LstmLayer(C.Structure):
 class FastDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "num_freqs", "look_ahead", "shrink_size", "num_mels", "enc1_hidden", "enc2_hidden", "bn_hidden", "bn_layers",
-        "dec_hidden", "noisy_num_neighbors", "enc_num_neighbors", "reserved")]
+        "dec_hidden", "noisy_num_neighbors", "enc_num_neighbors", "precision")]
 
 
 class FastWeights(C.Structure):
     _fields_ = [("mel_fb", C.c_void_p), ("enc1", LstmLayer), ("enc2", LstmLayer), ("enc_fc_w", C.c_void_p),
                 ("enc_fc_b", C.c_void_p), ("bn", LstmLayer * 2), ("bn_fc_w", C.c_void_p), ("bn_fc_b", C.c_void_p),
-                ("dec1", LstmLayer), ("dec2", LstmLayer), ("dec_fc_w", C.c_void_p), ("dec_fc_b", C.c_void_p)]
+                ("dec1", LstmLayer), ("dec2", LstmLayer), ("dec_fc_w", C.c_void_p), ("dec_fc_b", C.c_void_p),
+                ("bn_packed", C.c_void_p)]
 
 
 _P, _I, _L, _F, _S = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
@@ -63,6 +64,8 @@ _SIGNATURES = {
     "fsn_enhance": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(SeqWeights), C.POINTER(SeqWeights), _P, _P, _I, _I,
                               _I, _I, _I, _P, _P, _P, _S, _P]),
     "fsn_fast_workspace_bytes": (_S, [C.POINTER(FastDesc), _I, _I]),
+    "fsn_fast_packed_bytes": (_S, [C.POINTER(FastDesc)]),
+    "fsn_fast_pack_bn_weights": (C.c_int, [C.POINTER(FastDesc), C.POINTER(FastWeights), _P, _P]),
     "fsn_fast_model_forward": (C.c_int, [C.POINTER(FastDesc), C.POINTER(FastWeights), _P, _I, _I, _P, _P, _S, _P]),
     "fsn_last_launch_count": (C.c_int64, []),
     "fsn_set_profiling": (C.c_int, [_I]),

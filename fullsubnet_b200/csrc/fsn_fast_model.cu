@@ -44,8 +44,10 @@ __global__ void fast_bn_input_kernel(const float* __restrict__ melT, const float
 
 // decoder input (model.py:194): [enc_out (M) | up-sampled bottleneck output (M)] per (b,t); frame t of the
 // up-sampled signal is shrunk frame t / S (model.py:131-140)
-__global__ void fast_dec_input_kernel(const float* __restrict__ encT, const float* __restrict__ bn_out, int B, int Tp,
-                                      int M, int S, int Ts, float* __restrict__ dec_in) {
+// bn_out element (b, m, ts) lives at bn_out[(b*bn_bstride + m) * Ts + ts]: bn_bstride = M for the fp32 path
+// ([B*M, Ts]) and 2*M for the tensor-core path, which writes a [B,2,M,Ts] tensor whose channel 0 is the output
+__global__ void fast_dec_input_kernel(const float* __restrict__ encT, const float* __restrict__ bn_out, int bn_bstride,
+                                      int B, int Tp, int M, int S, int Ts, float* __restrict__ dec_in) {
   const size_t total = (size_t)B * Tp * 2 * M;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % (2 * M));
@@ -53,7 +55,7 @@ __global__ void fast_dec_input_kernel(const float* __restrict__ encT, const floa
     const int t = (int)(bt % Tp), b = (int)(bt / Tp);
     float v;
     if (c < M) v = encT[bt * M + c];
-    else       v = bn_out[((size_t)b * M + (c - M)) * Ts + min(t / S, Ts - 1)];
+    else       v = bn_out[((size_t)b * bn_bstride + (c - M)) * Ts + min(t / S, Ts - 1)];
     dec_in[i] = v;
   }
 }
@@ -78,6 +80,11 @@ __global__ void fast_output_kernel(const float* __restrict__ dec, int B, int Tp,
 }
 
 struct FastDims { int B, T, Tp, F, M, K, Ts, S; };
+
+static bool fast_tc_ok(const fsn_fast_desc* d) {
+  const int K = (2 * d->noisy_num_neighbors + 1) + (2 * d->enc_num_neighbors + 1);
+  return sb_tc2_enabled() && d->bn_hidden == 384 && d->bn_layers == 2 && K <= 32;
+}
 
 struct FastWs {
   float *magT, *melT, *encT, *bn, *bn_out, *dec_in, *dec_out, *inv1, *inv2;
@@ -119,7 +126,7 @@ static void fast_carve(const fsn_fast_desc* d, const FastDims& m, void* base, Fa
   w.melT = c.take<float>(BT * m.M);
   w.encT = c.take<float>(BT * m.M);
   w.bn = c.take<float>((size_t)m.Ts * R * m.K);
-  w.bn_out = c.take<float>(R * m.Ts);
+  w.bn_out = c.take<float>(2 * R * m.Ts);  // [B,2,M,Ts] when written by the tensor-core kernel
   w.dec_in = c.take<float>(BT * 2 * m.M);
   w.dec_out = c.take<float>(BT * 2 * m.F);
   w.inv1 = c.take<float>(m.B);
@@ -130,9 +137,11 @@ static void fast_carve(const fsn_fast_desc* d, const FastDims& m, void* base, Fa
   w.e1_c = c.take<float>((size_t)m.B * d->enc1_hidden);
   w.e2_hall = c.take<float>(BT * d->enc2_hidden);
   w.e2_c = c.take<float>((size_t)m.B * d->enc2_hidden);
-  for (int i = 0; i < 2; ++i) { w.bn_h0[i] = c.take<float>(R * d->bn_hidden); w.bn_h1[i] = c.take<float>(R * d->bn_hidden); }
-  w.bn_c0 = c.take<float>(R * d->bn_hidden);
-  w.bn_c1 = c.take<float>(R * d->bn_hidden);
+  if (d->precision == FSN_PREC_FP32) {
+    for (int i = 0; i < 2; ++i) { w.bn_h0[i] = c.take<float>(R * d->bn_hidden); w.bn_h1[i] = c.take<float>(R * d->bn_hidden); }
+    w.bn_c0 = c.take<float>(R * d->bn_hidden);
+    w.bn_c1 = c.take<float>(R * d->bn_hidden);
+  }
   for (int i = 0; i < 2; ++i) w.d1_h[i] = c.take<float>((size_t)m.B * d->dec_hidden);
   w.d1_c = c.take<float>((size_t)m.B * d->dec_hidden);
   w.d2_hall = c.take<float>(BT * d->dec_hidden);
@@ -180,6 +189,18 @@ extern "C" size_t fsn_fast_workspace_bytes(const fsn_fast_desc* d, int B, int T)
   return w.bytes;
 }
 
+extern "C" size_t fsn_fast_packed_bytes(const fsn_fast_desc* d) { return fast_tc_ok(d) ? sb_tc2_packed_bytes() : 0; }
+
+extern "C" int fsn_fast_pack_bn_weights(const fsn_fast_desc* d, const fsn_fast_weights* wt, void* packed,
+                                        fsn_stream_t stream) {
+  FSN_REQUIRE(fast_tc_ok(d), FSN_ERR_UNSUPPORTED, "fast model: the tensor-core bottleneck needs bn_hidden = 384, 2 layers");
+  fsn_seq_weights s;
+  for (int l = 0; l < 2; ++l) { s.w_ih[l] = wt->bn[l].w_ih; s.w_hh[l] = wt->bn[l].w_hh; s.b_ih[l] = wt->bn[l].b_ih; s.b_hh[l] = wt->bn[l].b_hh; }
+  s.fc_w = wt->bn_fc_w; s.fc_b = wt->bn_fc_b;
+  const int K = (2 * d->noisy_num_neighbors + 1) + (2 * d->enc_num_neighbors + 1);
+  return sb_tc2_pack_raw(&s, K, /*fc_out=*/1, packed, (cudaStream_t)stream);
+}
+
 extern "C" int fsn_fast_model_forward(const fsn_fast_desc* d, const fsn_fast_weights* wt, const float* mix_mag, int B,
                                       int T, float* out, void* workspace, size_t workspace_bytes, fsn_stream_t stream) {
   launch_counter() = 0;
@@ -214,6 +235,21 @@ extern "C" int fsn_fast_model_forward(const fsn_fast_desc* d, const fsn_fast_wei
   if ((rc = norm_scales_launch(w.sums, w.sums, B, (float)M * m.K * m.Ts, 1.f, w.inv2, nullptr, st))) return rc;
   // S: 2xLSTM(K->Hb->Hb) + Linear(1) + ReLU on B*M rows over Ts steps (model.py:188-189)
   const int Hb = d->bn_hidden;
+  int bn_bstride = M;
+  if (d->precision == FSN_PREC_F16_TC) {
+    // tcgen05 CTA-pair kernel of the fullsubnet sub-band stack: same stack shape (K<=32 -> 384 -> 384), the gather
+    // does the unfold AND the time down-sampling on the fly from melT / encT, Linear output 1 of 2 is zero-padded
+    FSN_REQUIRE(wt->bn_packed && fast_tc_ok(d), FSN_ERR_UNSUPPORTED,
+                "fast model: FSN_PREC_F16_TC needs packed bottleneck weights, bn_hidden = 384 and input width <= 32");
+    SbTcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.packed = wt->bn_packed; a.magT = w.melT; a.fbT = w.encT; a.inv2 = w.inv2; a.crm = w.bn_out;
+    a.B = B; a.F = M; a.Tp = Tp; a.la = 0; a.Ns = d->noisy_num_neighbors; a.Nf = d->enc_num_neighbors;
+    a.H = Hb; a.act = FSN_ACT_RELU; a.steps = m.Ts; a.shrink = m.S; a.pair = true;
+    a.map = RowMap{B, M, M, 1};
+    if ((rc = sb_tc2_forward(a, st))) return rc;
+    bn_bstride = 2 * M;
+  } else {
   for (int t = 0; t < m.Ts; ++t) {
     StepParams p;
     memset(&p, 0, sizeof(p));
@@ -236,12 +272,13 @@ extern "C" int fsn_fast_model_forward(const fsn_fast_desc* d, const fsn_fast_wei
                              (size_t)m.Ts, 0, st)))
       return rc;
   }
+  }
   // up-sampling + concat with the encoder output (model.py:191-194)
   {
     const size_t n = (size_t)B * Tp * 2 * M;
     int g = (int)((n + 255) / 256);
     if (g > 148 * 16) g = 148 * 16;
-    fast_dec_input_kernel<<<g, 256, 0, st>>>(w.encT, w.bn_out, B, Tp, M, m.S, m.Ts, w.dec_in);
+    fast_dec_input_kernel<<<g, 256, 0, st>>>(w.encT, w.bn_out, bn_bstride, B, Tp, M, m.S, m.Ts, w.dec_in);
     FSN_CHECK_LAUNCH("fast_dec_input_kernel");
   }
   // F_m2l: LSTM(2M->Hd), LSTM(Hd->Hd) + Linear(2F) (model.py:77-96,196)

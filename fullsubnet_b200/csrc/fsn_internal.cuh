@@ -72,6 +72,7 @@ struct SbTcArgs {
   const float* magT; const float* fbT; const float* inv2;
   float* crm;
   int B, F, Tp, la, Ns, Nf, H, act;
+  int steps, shrink;      // pair kernel only: LSTM steps (0 = Tp) and time down-sampling of the gathered input (0/1 = none)
   bool pair;              // packed for / run by the CTA-pair kernel
   RowMap map;
 };
@@ -85,5 +86,7 @@ bool sb_tc2_supported(const fsn_model_desc* d);
 size_t sb_tc2_packed_bytes();
 int sb_tc2_pack(const fsn_model_desc* d, const fsn_seq_weights* sb, void* packed, cudaStream_t st);
 int sb_tc2_forward(const SbTcArgs& a, cudaStream_t st);
+int sb_tc2_pack_raw(const fsn_seq_weights* sb, int Ksb, int fc_out, void* packed, cudaStream_t st);
+bool sb_tc2_enabled();  // H = 384 stacks may use the pair kernel (FSN_TC_PAIR != 0)
 
 }  // namespace fsn

@@ -72,7 +72,7 @@ __global__ void pack2_kernel(const float* __restrict__ wih0, const float* __rest
                              const float* __restrict__ wih1, const float* __restrict__ whh1,
                              const float* __restrict__ bih0, const float* __restrict__ bhh0,
                              const float* __restrict__ bih1, const float* __restrict__ bhh1,
-                             const float* __restrict__ fcw, const float* __restrict__ fcb, int Ksb,
+                             const float* __restrict__ fcw, const float* __restrict__ fcb, int Ksb, int fc_out,
                              uint8_t* __restrict__ out) {
   // one thread per 16-byte chunk (8 halves): chunks per rank = STREAM_BYTES / 16
   const size_t chunks_per_rank = STREAM_BYTES / 16;
@@ -120,8 +120,10 @@ __global__ void pack2_kernel(const float* __restrict__ wih0, const float* __rest
     bias[i] = bih0[i] + bhh0[i];
     bias[4 * H + i] = bih1[i] + bhh1[i];
   }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * H; i += gridDim.x * blockDim.x) pfcw[i] = fcw[i];
-  if (blockIdx.x == 0 && threadIdx.x < 2) pfcb[threadIdx.x] = fcb[threadIdx.x];
+  // the kernel always evaluates 2 Linear outputs; a model with fewer (fast_fullsubnet bottleneck: 1) gets zero rows
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * H; i += gridDim.x * blockDim.x)
+    pfcw[i] = (i < fc_out * H) ? fcw[i] : 0.f;
+  if (blockIdx.x == 0 && threadIdx.x < 2) pfcb[threadIdx.x] = ((int)threadIdx.x < fc_out) ? fcb[threadIdx.x] : 0.f;
 }
 
 // ---------------------------------------------------------------- shared-memory plan (identical in both CTAs)
@@ -158,6 +160,7 @@ struct KArgs {
   const float* magT; const float* fbT; const float* inv2;
   float* crm;
   int R, F, Tp, la, T, Ns, Nf, Ksb, act, Fsub;
+  int src_T, shrink;  // frames in magT/fbT; x_t = mean of `shrink` source frames (fast_fullsubnet down-sampling), 1 = none
   long long* dbg;  // FSN_TC_TRACE: cycle accounting of the leader's MMA warp (block 0)
   RowMap map;
 };
@@ -414,15 +417,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
       for (int t = 0; t < Tp; ++t) {
         mbar_wait<true>(&bars.x_empty[t & 1], ((t >> 1) & 1) ^ 1);
         uint8_t* xb = smem + SM_X + (t & 1) * S_KBLK;
+        // source frames of step t: itself, or (fast_fullsubnet/model.py:108-129) frame 0 alone, then blocks of
+        // `shrink` frames, the last one over its own length
+        int f0 = t, f1 = t + 1;
+        if (a.shrink > 1 && t > 0) { f0 = 1 + (t - 1) * a.shrink; f1 = min(f0 + a.shrink, a.src_T); }
+        const float wmean = 1.0f / (float)(f1 - f0);
 #pragma unroll 4
         for (int n = 0; n < NB; ++n) {
           const RowInfo ri = rows[n];
           float v = 0.f;
           if (ri.src_b >= 0 && lane < a.Ksb) {
-            const size_t base = ((size_t)ri.src_b * Tp + t) * a.F;
-            if (lane < nmag) v = a.magT[base + reflect_idx(ri.src_f + lane - a.Ns, a.F)];
-            else             v = a.fbT[base + reflect_idx(ri.src_f + (lane - nmag) - a.Nf, a.F)];
-            v *= ri.scale;
+            const int col = (lane < nmag) ? reflect_idx(ri.src_f + lane - a.Ns, a.F)
+                                          : reflect_idx(ri.src_f + (lane - nmag) - a.Nf, a.F);
+            const float* src = (lane < nmag) ? a.magT : a.fbT;
+            for (int fr = f0; fr < f1; ++fr) v += src[((size_t)ri.src_b * a.src_T + fr) * a.F + col];
+            v *= wmean * ri.scale;
           }
           *reinterpret_cast<__half*>(xb + swz128_off(n, lane)) = __float2half_rn(v);
         }
@@ -607,10 +616,25 @@ bool sb_tc2_supported(const fsn_model_desc* d) {
 
 size_t sb_tc2_packed_bytes() { return tc2::PACKED_BYTES; }
 
+int sb_tc2_pack_raw(const fsn_seq_weights* sb, int Ksb, int fc_out, void* packed, cudaStream_t st) {
+  tc2::pack2_kernel<<<148 * 4, 256, 0, st>>>(sb->w_ih[0], sb->w_hh[0], sb->w_ih[1], sb->w_hh[1], sb->b_ih[0],
+                                             sb->b_hh[0], sb->b_ih[1], sb->b_hh[1], sb->fc_w, sb->fc_b, Ksb, fc_out,
+                                             (uint8_t*)packed);
+  FSN_CHECK_LAUNCH("sb pack2_kernel");
+  return FSN_OK;
+}
+
+bool sb_tc2_enabled() {
+  fsn_model_desc d;
+  memset(&d, 0, sizeof(d));
+  d.sb_hidden = tc2::H; d.sb_num_neighbors = 0; d.fb_num_neighbors = 0;
+  return sb_tc2_supported(&d);
+}
+
 int sb_tc2_pack(const fsn_model_desc* d, const fsn_seq_weights* sb, void* packed, cudaStream_t st) {
   const int Ksb = (2 * d->sb_num_neighbors + 1) + (2 * d->fb_num_neighbors + 1);
   tc2::pack2_kernel<<<148 * 4, 256, 0, st>>>(sb->w_ih[0], sb->w_hh[0], sb->w_ih[1], sb->w_hh[1], sb->b_ih[0],
-                                             sb->b_hh[0], sb->b_ih[1], sb->b_hh[1], sb->fc_w, sb->fc_b, Ksb,
+                                             sb->b_hh[0], sb->b_ih[1], sb->b_hh[1], sb->fc_w, sb->fc_b, Ksb, 2,
                                              (uint8_t*)packed);
   FSN_CHECK_LAUNCH("sb pack2_kernel");
   return FSN_OK;
@@ -620,7 +644,8 @@ int sb_tc2_forward(const SbTcArgs& s, cudaStream_t st) {
   tc2::KArgs a;
   a.packed = (const uint8_t*)s.packed;
   a.magT = s.magT; a.fbT = s.fbT; a.inv2 = s.inv2; a.crm = s.crm;
-  a.R = s.map.B * s.map.Fsub; a.F = s.F; a.Tp = s.Tp; a.la = s.la; a.T = s.Tp - s.la;
+  a.R = s.map.B * s.map.Fsub; a.F = s.F; a.Tp = s.steps > 0 ? s.steps : s.Tp; a.la = s.la; a.T = a.Tp - s.la;
+  a.src_T = s.Tp; a.shrink = s.shrink > 1 ? s.shrink : 1;
   a.Ns = s.Ns; a.Nf = s.Nf; a.Ksb = (2 * s.Ns + 1) + (2 * s.Nf + 1); a.act = s.act;
   a.Fsub = s.map.Fsub; a.map = s.map;
   a.dbg = nullptr;

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -39,7 +40,7 @@ class _MelScale(nn.Module):
 class Model(BaseModel):
     def __init__(self, look_ahead, shrink_size, sequence_model, num_mels, encoder_input_size, bottleneck_hidden_size,
                  bottleneck_num_layers, noisy_input_num_neighbors, encoder_output_num_neighbors,
-                 norm_type="offline_laplace_norm", weight_init=False):
+                 norm_type="offline_laplace_norm", weight_init=False, precision=None):
         super().__init__()
         assert sequence_model in ("GRU", "LSTM"), f"{self.__class__.__name__} only support GRU and LSTM."
         self.encoder = nn.Sequential(
@@ -64,17 +65,36 @@ class Model(BaseModel):
         self.noisy_input_num_neighbors = noisy_input_num_neighbors
         self.enc_output_num_neighbors = encoder_output_num_neighbors
         self.norm = self.norm_wrapper(norm_type)
+        # arithmetic of the bottleneck stack (92 % of the FLOPs): 'fp32' | 'f16_tc' (tcgen05 pair kernel) | 'auto'
+        self.precision = precision or os.environ.get("FSN_PRECISION", "auto")
+        self._packed = None
+        self._packed_key = None
         if num_mels != 64 or encoder_input_size != 257:
             raise NotImplementedError("the reference hard-codes 64 mel bins / 257 frequencies in its layer sizes")
         if weight_init:
             self.apply(self.weight_init)
 
-    def _structs(self):
-        d = _lib.FastDesc(num_freqs=self.encoder_input_size, look_ahead=self.look_ahead, shrink_size=self.shrink_size,
+    def _resolve_precision(self) -> str:
+        d = self._desc(_lib.PREC["f16_tc"])
+        ok = _lib.load().fsn_fast_packed_bytes(C.byref(d)) > 0
+        if self.precision == "auto":
+            return "f16_tc" if ok else "fp32"
+        if self.precision not in _lib.PREC:
+            raise ValueError(f"precision must be one of {list(_lib.PREC)} or 'auto'")
+        if self.precision == "f16_tc" and not ok:
+            raise NotImplementedError("f16_tc needs bottleneck_hidden_size = 384, 2 layers and input width <= 32")
+        return self.precision
+
+    def _desc(self, prec: int):
+        return _lib.FastDesc(num_freqs=self.encoder_input_size, look_ahead=self.look_ahead, shrink_size=self.shrink_size,
                           num_mels=self.num_mels, enc1_hidden=384, enc2_hidden=257,
                           bn_hidden=self.bottleneck.hidden_size, bn_layers=self.bottleneck.num_layers, dec_hidden=512,
                           noisy_num_neighbors=self.noisy_input_num_neighbors,
-                          enc_num_neighbors=self.enc_output_num_neighbors, reserved=0)
+                          enc_num_neighbors=self.enc_output_num_neighbors, precision=prec)
+
+    def _structs(self, device):
+        prec = self._resolve_precision()
+        d = self._desc(_lib.PREC[prec])
         w = _lib.FastWeights()
         fb = self.mel_scale.fb
         if not fb.is_cuda:
@@ -87,6 +107,15 @@ class Model(BaseModel):
         w.bn_fc_w, w.bn_fc_b = self.bottleneck.fc_ptrs()
         w.dec1, w.dec2 = self.decoder_lstm[0].layer_struct(0), self.decoder_lstm[1].layer_struct(0)
         w.dec_fc_w, w.dec_fc_b = self.decoder_lstm[1].fc_ptrs()
+        w.bn_packed = None
+        if prec == "f16_tc":  # tile-ordered fp16 image of the bottleneck weights, rebuilt when a parameter changes
+            key = (self.bottleneck.version_key(), str(device))
+            if self._packed is None or self._packed_key != key:
+                lib = _lib.load()
+                buf = torch.empty(lib.fsn_fast_packed_bytes(C.byref(d)), dtype=torch.uint8, device=device)
+                _lib.check(lib.fsn_fast_pack_bn_weights(C.byref(d), C.byref(w), buf.data_ptr(), _lib.stream_ptr(device)))
+                self._packed, self._packed_key = buf, key
+            w.bn_packed = self._packed.data_ptr()
         return d, w
 
     def forward(self, mix_mag):
@@ -100,7 +129,7 @@ class Model(BaseModel):
         x = _lib.require_cuda(mix_mag, "mix_mag")
         lib = _lib.load()
         with torch.cuda.device(x.device):
-            d, w = self._structs()
+            d, w = self._structs(x.device)
             n = lib.fsn_fast_workspace_bytes(C.byref(d), batch_size, num_frames)
             if n == 0:
                 _lib.check(_lib.FSN_ERR_SHAPE)

@@ -165,7 +165,7 @@ typedef struct fsn_fast_desc {
   int32_t dec_hidden;  /* 512 */
   int32_t noisy_num_neighbors; /* noisy_input_num_neighbors */
   int32_t enc_num_neighbors;   /* encoder_output_num_neighbors */
-  int32_t reserved;
+  int32_t precision;           /* FSN_PREC_* for the bottleneck stack (the tensor-core path needs bn_hidden = 384) */
 } fsn_fast_desc;
 
 typedef struct fsn_fast_weights {
@@ -176,9 +176,13 @@ typedef struct fsn_fast_weights {
   const float* bn_fc_w; const float* bn_fc_b;     /* [1, Hb], [1] */
   fsn_lstm_layer dec1, dec2;
   const float* dec_fc_w; const float* dec_fc_b;   /* [2F, Hd], [2F] */
+  const void* bn_packed;  /* FSN_PREC_F16_TC: fsn_fast_pack_bn_weights() image of the bottleneck stack, else NULL */
 } fsn_fast_weights;
 
 size_t fsn_fast_workspace_bytes(const fsn_fast_desc* d, int B, int T);
+/* FSN_PREC_F16_TC: 0 when the tensor-core path cannot run this descriptor */
+size_t fsn_fast_packed_bytes(const fsn_fast_desc* d);
+int fsn_fast_pack_bn_weights(const fsn_fast_desc* d, const fsn_fast_weights* w, void* packed, fsn_stream_t stream);
 /* Model.forward (fast_fullsubnet/model.py:143-202): mix_mag [B,1,F,T] -> [B,2,F,T] */
 int fsn_fast_model_forward(const fsn_fast_desc* d, const fsn_fast_weights* w, const float* mix_mag, int B, int T,
                            float* out, void* workspace, size_t workspace_bytes, fsn_stream_t stream);

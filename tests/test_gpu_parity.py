@@ -220,11 +220,12 @@ def test_full_size_batch_properties(dev):
 
 
 # ------------------------------------------------------------------ fast_fullsubnet (config 4, A13)
-def test_fast_fullsubnet_matches_reference(golden, dev):
+@pytest.mark.parametrize("precision,tol", [("fp32", 5e-5), ("f16_tc", CRM_TOL)])
+def test_fast_fullsubnet_matches_reference(golden, dev, precision, tol):
     from fullsubnet_b200.fast_fullsubnet.model import Model
     from oracle import fast_fullsubnet_oracle as FO
     g = golden("fast_full")
-    m = Model(**FO.DEFAULT_FAST_ARGS)
+    m = Model(**FO.DEFAULT_FAST_ARGS, precision=precision)
     m.load_state_dict(FO.make_fast_state_dict(seed=3), strict=True)
     m = m.to(dev).eval()
     mag = T(g["mag"], dev).unsqueeze(1)
@@ -232,12 +233,14 @@ def test_fast_fullsubnet_matches_reference(golden, dev):
         o1 = m(mag[:1])
         o3 = m(mag)
     assert o3.shape == g["out_b3"].shape
-    assert rel_max(o1.cpu(), g["out_b1"]) < 5e-5 and rel_max(o3.cpu(), g["out_b3"]) < 5e-5
-    assert rel_l2(o3.cpu(), g["out_b3"]) < 5e-5
+    e1, e3 = rel_max(o1.cpu(), g["out_b1"]), rel_max(o3.cpu(), g["out_b3"])
+    print(f"fast_fullsubnet {precision}: max-rel {e1:.2e} / {e3:.2e}, rel-l2 {rel_l2(o3.cpu(), g['out_b3']):.2e}")
+    assert e1 < tol and e3 < tol
+    assert rel_l2(o3.cpu(), g["out_b3"]) < tol
     # odd / even frame counts exercise the last (short) down-sampling block
     for Tn in (7, 8):
         x = torch.rand(2, 1, 257, Tn)
         ref = FO.fast_model_forward(x, FO.make_fast_state_dict(seed=3))
         with torch.no_grad():
             got = m(x.to(dev))
-        assert rel_max(got.cpu(), ref) < 5e-5, Tn
+        assert rel_max(got.cpu(), ref) < tol, Tn
