@@ -1,6 +1,7 @@
 // fast_fullsubnet (recipes/dns_interspeech_2020/fast_fullsubnet/model.py:11-202, BASELINE config 4): host
 // orchestration and the few extra kernels on top of the shared fp32 building blocks (mel filtering, real-time
 // down/up-sampling, bottleneck input, decoder re-layout).
+#include <stdlib.h>
 #include <string.h>
 
 #include "fsn_internal.cuh"
@@ -92,6 +93,8 @@ struct FastWs {
   float *e1_h[2], *e1_c, *e2_hall, *e2_c;
   float *bn_h0[2], *bn_h1[2], *bn_c0, *bn_c1;
   float *d1_h[2], *d1_c, *d2_hall, *d2_c;
+  float* pp;               // h0 ping-pong of the persistent LSTM kernel [2][256][max H0]
+  unsigned int* barrier;
   size_t bytes;
 };
 
@@ -146,6 +149,8 @@ static void fast_carve(const fsn_fast_desc* d, const FastDims& m, void* base, Fa
   w.d1_c = c.take<float>((size_t)m.B * d->dec_hidden);
   w.d2_hall = c.take<float>(BT * d->dec_hidden);
   w.d2_c = c.take<float>((size_t)m.B * d->dec_hidden);
+  w.pp = c.take<float>((size_t)2 * 256 * (d->dec_hidden > d->enc1_hidden ? d->dec_hidden : d->enc1_hidden));
+  w.barrier = c.take<unsigned int>(64);
   w.bytes = c.off;
 }
 
@@ -153,8 +158,24 @@ static void fast_carve(const fsn_fast_desc* d, const FastDims& m, void* base, Fa
 // (Ha -> Hb, output kept for every step for the Linear layer that follows)
 static int run_lstm_pair(const fsn_lstm_layer& la, int Ka, int Ha, const fsn_lstm_layer& lb, int Hb, int R, int steps,
                          const float* x, size_t x_row_stride, size_t x_step_stride, const float* row_scale,
-                         float* ha[2], float* ca, float* hb_all, float* cb, cudaStream_t st) {
+                         float* ha[2], float* ca, float* hb_all, float* cb, float* pp, unsigned int* barrier,
+                         cudaStream_t st) {
   int rc;
+  static const bool stepwise = getenv("FSN_FB_STEPWISE") != nullptr;
+  if (!stepwise && x_step_stride == (size_t)Ka && x_row_stride == (size_t)steps * Ka && fb_persistent_supported(Ka, Ha, Hb)) {
+    // persistent cooperative wavefront kernel (fsn_fullband.cu), chunks of <= 256 rows
+    fsn_seq_weights w2;
+    memset(&w2, 0, sizeof(w2));
+    w2.w_ih[0] = la.w_ih; w2.w_hh[0] = la.w_hh; w2.b_ih[0] = la.b_ih; w2.b_hh[0] = la.b_hh;
+    w2.w_ih[1] = lb.w_ih; w2.w_hh[1] = lb.w_hh; w2.b_ih[1] = lb.b_ih; w2.b_hh[1] = lb.b_hh;
+    for (int r0 = 0; r0 < R; r0 += 256) {
+      const int nb = (R - r0 < 256) ? R - r0 : 256;
+      if ((rc = fb_persistent_launch(&w2, x + (size_t)r0 * x_row_stride, row_scale ? row_scale + r0 : nullptr, pp,
+                                     hb_all + (size_t)r0 * steps * Hb, barrier, nb, Ka, Ha, Hb, steps, st)))
+        return rc;
+    }
+    return FSN_OK;
+  }
   for (int t = 0; t < steps; ++t) {
     StepParams p;
     memset(&p, 0, sizeof(p));
@@ -222,7 +243,7 @@ extern "C" int fsn_fast_model_forward(const fsn_fast_desc* d, const fsn_fast_wei
   if ((rc = norm_scales_launch(w.sums, w.sums, B, (float)M * Tp, 1.f, w.inv1, nullptr, st))) return rc;
   // F_l2m: LSTM(M->He1), LSTM(He1->He2) + Linear(M) + ReLU (model.py:35-54,171)
   if ((rc = run_lstm_pair(wt->enc1, M, d->enc1_hidden, wt->enc2, d->enc2_hidden, B, Tp, w.melT, (size_t)Tp * M, M,
-                          w.inv1, w.e1_h, w.e1_c, w.e2_hall, w.e2_c, st)))
+                          w.inv1, w.e1_h, w.e1_c, w.e2_hall, w.e2_c, w.pp, w.barrier, st)))
     return rc;
   if ((rc = fc_gemm_launch(w.e2_hall, wt->enc_fc_w, wt->enc_fc_b, w.encT, B * Tp, d->enc2_hidden, M, FSN_ACT_RELU, st)))
     return rc;
@@ -283,7 +304,7 @@ extern "C" int fsn_fast_model_forward(const fsn_fast_desc* d, const fsn_fast_wei
   }
   // F_m2l: LSTM(2M->Hd), LSTM(Hd->Hd) + Linear(2F) (model.py:77-96,196)
   if ((rc = run_lstm_pair(wt->dec1, 2 * M, d->dec_hidden, wt->dec2, d->dec_hidden, B, Tp, w.dec_in, (size_t)Tp * 2 * M,
-                          2 * M, nullptr, w.d1_h, w.d1_c, w.d2_hall, w.d2_c, st)))
+                          2 * M, nullptr, w.d1_h, w.d1_c, w.d2_hall, w.d2_c, w.pp, w.barrier, st)))
     return rc;
   if ((rc = fc_gemm_launch(w.d2_hall, wt->dec_fc_w, wt->dec_fc_b, w.dec_out, B * Tp, d->dec_hidden, 2 * F, FSN_ACT_NONE,
                            st)))

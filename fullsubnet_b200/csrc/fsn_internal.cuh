@@ -62,9 +62,10 @@ int istft_launch(const float* real, const float* imag, int cstride, const float*
                  int hop, int win_length, int length, float* wav, cudaStream_t st);
 
 // persistent cooperative full-band LSTM (fsn_fullband.cu)
-bool fb_persistent_supported(int F, int H);
-int fb_persistent_launch(const fsn_seq_weights* w, const float* magT_chunk, const float* inv1_chunk, float* h0buf,
-                         float* h1all_chunk, unsigned int* barrier, int nb, int F, int H, int Tp, cudaStream_t st);
+bool fb_persistent_supported(int F, int H0, int H1);
+int fb_persistent_launch(const fsn_seq_weights* w, const float* x_chunk, const float* inv1_chunk, float* h0buf,
+                         float* h1all_chunk, unsigned int* barrier, int nb, int F, int H0, int H1, int Tp,
+                         cudaStream_t st);
 
 // tcgen05 sub-band stack (fsn_subband_tc.cu)
 struct SbTcArgs {

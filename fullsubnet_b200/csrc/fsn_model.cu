@@ -115,13 +115,13 @@ static int model_core(const fsn_model_desc* d, const fsn_seq_weights* fb, const 
 
   // ---- full-band stack (model.py:92-95): 2-layer LSTM(F -> Hf -> Hf), rows = clips
   static const bool fb_stepwise = getenv("FSN_FB_STEPWISE") != nullptr;  // debug: force the per-step kernels
-  if (!fb_stepwise && fb_persistent_supported(F, Hf)) {
+  if (!fb_stepwise && fb_persistent_supported(F, Hf, Hf)) {
     // one persistent cooperative kernel per chunk of <= 256 clips: weights resident in shared memory,
     // layer wavefront, one grid barrier per time step
     for (int b0 = 0; b0 < B; b0 += 256) {
       const int nb = (B - b0 < 256) ? B - b0 : 256;
       if ((rc = fb_persistent_launch(fb, w.magT + (size_t)b0 * Tp * F, w.inv1 + b0, w.fb_pp,
-                                     w.fb_h1all + (size_t)b0 * Tp * Hf, w.fb_barrier, nb, F, Hf, Tp, st)))
+                                     w.fb_h1all + (size_t)b0 * Tp * Hf, w.fb_barrier, nb, F, Hf, Hf, Tp, st)))
         return rc;
     }
   } else {
