@@ -422,18 +422,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
         int f0 = t, f1 = t + 1;
         if (a.shrink > 1 && t > 0) { f0 = 1 + (t - 1) * a.shrink; f1 = min(f0 + a.shrink, a.src_T); }
         const float wmean = 1.0f / (float)(f1 - f0);
+        if (a.shrink <= 1) {  // fullsubnet: one source frame per step, 4 rows of loads in flight
 #pragma unroll 4
-        for (int n = 0; n < NB; ++n) {
-          const RowInfo ri = rows[n];
-          float v = 0.f;
-          if (ri.src_b >= 0 && lane < a.Ksb) {
-            const int col = (lane < nmag) ? reflect_idx(ri.src_f + lane - a.Ns, a.F)
-                                          : reflect_idx(ri.src_f + (lane - nmag) - a.Nf, a.F);
-            const float* src = (lane < nmag) ? a.magT : a.fbT;
-            for (int fr = f0; fr < f1; ++fr) v += src[((size_t)ri.src_b * a.src_T + fr) * a.F + col];
-            v *= wmean * ri.scale;
+          for (int n = 0; n < NB; ++n) {
+            const RowInfo ri = rows[n];
+            float v = 0.f;
+            if (ri.src_b >= 0 && lane < a.Ksb) {
+              const size_t base = ((size_t)ri.src_b * a.src_T + t) * a.F;
+              if (lane < nmag) v = a.magT[base + reflect_idx(ri.src_f + lane - a.Ns, a.F)];
+              else             v = a.fbT[base + reflect_idx(ri.src_f + (lane - nmag) - a.Nf, a.F)];
+              v *= ri.scale;
+            }
+            *reinterpret_cast<__half*>(xb + swz128_off(n, lane)) = __float2half_rn(v);
           }
-          *reinterpret_cast<__half*>(xb + swz128_off(n, lane)) = __float2half_rn(v);
+        } else {
+#pragma unroll 2
+          for (int n = 0; n < NB; ++n) {
+            const RowInfo ri = rows[n];
+            float v = 0.f;
+            if (ri.src_b >= 0 && lane < a.Ksb) {
+              const int col = (lane < nmag) ? reflect_idx(ri.src_f + lane - a.Ns, a.F)
+                                            : reflect_idx(ri.src_f + (lane - nmag) - a.Nf, a.F);
+              const float* src = (lane < nmag) ? a.magT : a.fbT;
+              for (int fr = f0; fr < f1; ++fr) v += src[((size_t)ri.src_b * a.src_T + fr) * a.F + col];
+              v *= wmean * ri.scale;
+            }
+            *reinterpret_cast<__half*>(xb + swz128_off(n, lane)) = __float2half_rn(v);
+          }
         }
         fence_proxy_async();
         __syncwarp();
