@@ -44,6 +44,22 @@ class FastWeights(C.Structure):
                 ("bn_packed", C.c_void_p)]
 
 
+IMP_MAX_SECTIONS = 8
+
+
+class ImprovedDesc(C.Structure):
+    _fields_ = [("n_fft", C.c_int32), ("hop_length", C.c_int32), ("win_length", C.c_int32), ("num_freqs", C.c_int32),
+                ("fdrc", C.c_float), ("num_sections", C.c_int32), ("freq_cutoffs", C.c_int32 * IMP_MAX_SECTIONS),
+                ("sb_num_center", C.c_int32 * IMP_MAX_SECTIONS), ("sb_num_neighbor", C.c_int32 * IMP_MAX_SECTIONS),
+                ("fb_num_center", C.c_int32 * IMP_MAX_SECTIONS), ("fb_num_neighbor", C.c_int32 * IMP_MAX_SECTIONS),
+                ("fb_hidden", C.c_int32), ("sb_hidden", C.c_int32), ("fb_activation", C.c_int32),
+                ("sb_activation", C.c_int32)]
+
+
+class ImprovedWeights(C.Structure):
+    _fields_ = [("fb", SeqWeights), ("sb", SeqWeights * IMP_MAX_SECTIONS)]
+
+
 _P, _I, _L, _F, _S = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 _SIGNATURES = {
     "fsn_version": (C.c_int, []),
@@ -67,6 +83,9 @@ _SIGNATURES = {
     "fsn_fast_packed_bytes": (_S, [C.POINTER(FastDesc)]),
     "fsn_fast_pack_bn_weights": (C.c_int, [C.POINTER(FastDesc), C.POINTER(FastWeights), _P, _P]),
     "fsn_fast_model_forward": (C.c_int, [C.POINTER(FastDesc), C.POINTER(FastWeights), _P, _I, _I, _P, _P, _S, _P]),
+    "fsn_improved_workspace_bytes": (_S, [C.POINTER(ImprovedDesc), _I, _I]),
+    "fsn_improved_forward": (C.c_int, [C.POINTER(ImprovedDesc), C.POINTER(ImprovedWeights), _P, _I, _I, _P, _P, _P, _S,
+                                       _P]),
     "fsn_last_launch_count": (C.c_int64, []),
     "fsn_set_profiling": (C.c_int, [_I]),
     "fsn_last_stage_ms": (C.c_float, [_I]),

@@ -129,7 +129,7 @@ stft_kernel(const float* __restrict__ wav, int L, int n, int hop, int win_length
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kDspThreads)
 istft_kernel(const float* __restrict__ real, const float* __restrict__ imag, int cstride,
-             const float* __restrict__ crm, int T, int n, int hop, int win_length, int out_len,
+             const float* __restrict__ crm, int mask_mode, int T, int n, int hop, int win_length, int out_len,
              int seg, int np_max, float* __restrict__ wav) {
   extern __shared__ float2 smem2[];
   const int log2n = ilog2(n);
@@ -163,7 +163,10 @@ istft_kernel(const float* __restrict__ real, const float* __restrict__ imag, int
         const size_t o = (size_t)k * T + t;
         r = xr[o * cstride];
         i = xi[o * cstride];
-        if (crm) {  // mask.py:58-63 then inferencer.py:139-140
+        if (crm && mask_mode == 2) {  // improved_fullsubnet/model.py:575-576: element-wise, no decompression
+          r *= cr[o];
+          i *= ci[o];
+        } else if (crm) {  // mask.py:58-63 then inferencer.py:139-140
           const float mr = decompress_cirm_f(cr[o], 10.0f, 9.9f);
           const float mi = decompress_cirm_f(ci[o], 10.0f, 9.9f);
           const float er = mr * r - mi * i;
@@ -291,7 +294,7 @@ int stft_launch(const float* wav, int B, int L, int n_fft, int hop, int win_leng
 }
 
 int istft_launch(const float* real, const float* imag, int cstride, const float* crm, int B, int T, int n_fft,
-                 int hop, int win_length, int length, float* wav, cudaStream_t st) {
+                 int hop, int win_length, int length, float* wav, cudaStream_t st, int mask_mode) {
   FSN_REQUIRE(B > 0 && T > 0, FSN_ERR_SHAPE, "istft: empty input");
   FSN_REQUIRE(is_pow2(n_fft) && n_fft >= 16 && n_fft <= 2048, FSN_ERR_UNSUPPORTED,
               "istft: n_fft=%d unsupported (power of two in [16,2048])", n_fft);
@@ -309,8 +312,8 @@ int istft_launch(const float* real, const float* imag, int cstride, const float*
     if (rc) return rc;
   }
   dim3 grid(cdiv(out_len, seg), B);
-  istft_kernel<<<grid, kDspThreads, smem, st>>>(real, imag, cstride, crm, T, n_fft, hop, win_length, out_len, seg,
-                                                np_max, wav);
+  istft_kernel<<<grid, kDspThreads, smem, st>>>(real, imag, cstride, crm, mask_mode, T, n_fft, hop, win_length, out_len,
+                                                seg, np_max, wav);
   FSN_CHECK_LAUNCH("istft_kernel");
   return FSN_OK;
 }
@@ -326,7 +329,7 @@ extern "C" int fsn_stft(const float* wav, int B, int L, int n_fft, int hop, int 
 
 extern "C" int fsn_istft(const float* real, const float* imag, int cstride, const float* crm, int B, int T,
                          int n_fft, int hop, int win_length, int length, float* wav, fsn_stream_t stream) {
-  return istft_launch(real, imag, cstride, crm, B, T, n_fft, hop, win_length, length, wav, (cudaStream_t)stream);
+  return istft_launch(real, imag, cstride, crm, B, T, n_fft, hop, win_length, length, wav, (cudaStream_t)stream, 1);
 }
 
 extern "C" int fsn_decompress_cirm(const float* in, float* out, int64_t n, float K, float limit,

@@ -54,12 +54,13 @@ int transpose_mag_launch(const float* in, float* out, int B, int F, int T, int T
 int clip_stats_launch(const float* x, int B, int T_pad, int F, int N, float2* fs, float2* sums, cudaStream_t st);
 int clip_reduce_only_launch(const float2* fs, int B, int T_pad, float2* sums, cudaStream_t st);
 int norm_scales_launch(const float2* mag_sums, const float2* fb_sums, int B, float cnt1, float cnt2, float* inv1,
-                       float* inv2, cudaStream_t st);
+                       float* inv2, cudaStream_t st, float eps = 1e-5f);
 
 int stft_launch(const float* wav, int B, int L, int n_fft, int hop, int win_length, float* mag, float* phase,
                 float* real, float* imag, float* magT, int T_pad, cudaStream_t st);
+// mask_mode: 1 = decompress_cIRM + complex product (fullsubnet), 2 = element-wise re*crm0, im*crm1 (improved_fullsubnet)
 int istft_launch(const float* real, const float* imag, int cstride, const float* crm, int B, int T, int n_fft,
-                 int hop, int win_length, int length, float* wav, cudaStream_t st);
+                 int hop, int win_length, int length, float* wav, cudaStream_t st, int mask_mode = 1);
 
 // persistent cooperative full-band LSTM (fsn_fullband.cu)
 bool fb_persistent_supported(int F, int H0, int H1);

@@ -84,11 +84,11 @@ __global__ void clip_reduce_kernel(const float2* __restrict__ fs, int T_pad, flo
 // inv1[b] = 1/(mean(mag_pad)+1e-5)              (model.py:92)
 // inv2[b] = 1/(mean(cat(unfold(mag), unfold(fb)))+1e-5) via the closed form   (model.py:110-111)
 __global__ void norm_scales_kernel(const float2* __restrict__ mag_sums, const float2* __restrict__ fb_sums, int B,
-                                   float cnt1, float cnt2, float* __restrict__ inv1, float* __restrict__ inv2) {
+                                   float cnt1, float cnt2, float* __restrict__ inv1, float* __restrict__ inv2, float eps) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  if (inv1) inv1[b] = 1.0f / (mag_sums[b].x / cnt1 + 1e-5f);
-  if (inv2) inv2[b] = 1.0f / ((mag_sums[b].y + fb_sums[b].y) / cnt2 + 1e-5f);
+  if (inv1) inv1[b] = 1.0f / (mag_sums[b].x / cnt1 + eps);
+  if (inv2) inv2[b] = 1.0f / ((mag_sums[b].y + fb_sums[b].y) / cnt2 + eps);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -342,8 +342,8 @@ int clip_reduce_only_launch(const float2* fs, int B, int T_pad, float2* sums, cu
 }
 
 int norm_scales_launch(const float2* mag_sums, const float2* fb_sums, int B, float cnt1, float cnt2, float* inv1,
-                       float* inv2, cudaStream_t st) {
-  norm_scales_kernel<<<cdiv(B, 128), 128, 0, st>>>(mag_sums, fb_sums, B, cnt1, cnt2, inv1, inv2);
+                       float* inv2, cudaStream_t st, float eps) {
+  norm_scales_kernel<<<cdiv(B, 128), 128, 0, st>>>(mag_sums, fb_sums, B, cnt1, cnt2, inv1, inv2, eps);
   FSN_CHECK_LAUNCH("norm_scales_kernel");
   return FSN_OK;
 }

@@ -187,6 +187,36 @@ int fsn_fast_pack_bn_weights(const fsn_fast_desc* d, const fsn_fast_weights* w, 
 int fsn_fast_model_forward(const fsn_fast_desc* d, const fsn_fast_weights* w, const float* mix_mag, int B, int T,
                            float* out, void* workspace, size_t workspace_bytes, fsn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * recipes/dns_interspeech_2020/improved_fullsubnet/model.py:452-591  Model (BASELINE config 5)
+ *   wav -> STFT -> |X|^fdrc, Nyquist bin dropped -> norm -> full-band 2xLSTM + Linear -> per sub-band section:
+ *   strided unfold (centre/neighbour widths) of noisy and full-band output, concat, per-section norm, 2xLSTM +
+ *   Linear(2*centre) -> cRM (Nyquist row 0) -> element-wise mask on (re, im) -> iSTFT -> wav.  fp32 kernels;
+ *   n_fft must be a power of two (the reference's n_fft=960 example needs a mixed-radix FFT: not built).
+ * ---------------------------------------------------------------------------------------- */
+#define FSN_IMP_MAX_SECTIONS 8
+typedef struct fsn_improved_desc {
+  int32_t n_fft, hop_length, win_length, num_freqs;
+  float fdrc;
+  int32_t num_sections;                       /* len(sb_num_center_freqs) = len(freq_cutoffs) + 1 */
+  int32_t freq_cutoffs[FSN_IMP_MAX_SECTIONS];
+  int32_t sb_num_center[FSN_IMP_MAX_SECTIONS], sb_num_neighbor[FSN_IMP_MAX_SECTIONS];
+  int32_t fb_num_center[FSN_IMP_MAX_SECTIONS], fb_num_neighbor[FSN_IMP_MAX_SECTIONS];
+  int32_t fb_hidden, sb_hidden, fb_activation, sb_activation;
+} fsn_improved_desc;
+
+typedef struct fsn_improved_weights {
+  fsn_seq_weights fb;                          /* fb_model */
+  fsn_seq_weights sb[FSN_IMP_MAX_SECTIONS];    /* sb_model.sb_models[s] */
+} fsn_improved_weights;
+
+size_t fsn_improved_workspace_bytes(const fsn_improved_desc* d, int B, int L);
+/* Model.forward (improved_fullsubnet/model.py:541-591): wav [B,L] -> enhanced [B,L] (the reference returns
+ * [B,1,L]); crm_out optional [B,2,F,T] */
+int fsn_improved_forward(const fsn_improved_desc* d, const fsn_improved_weights* w, const float* wav, int B, int L,
+                         float* enhanced, float* crm_out, void* workspace, size_t workspace_bytes,
+                         fsn_stream_t stream);
+
 /* Opt-in stage timing for bench.py: when enabled, fsn_model_forward / fsn_enhance bracket their
  * stages with CUDA events on `stream` (thread-local, created lazily).  After the caller has
  * synchronised the stream, fsn_last_stage_ms(stage) returns the device time of the last call:

@@ -136,6 +136,21 @@ def main():
     np.savez_compressed(os.path.join(out_dir, "fast_full.npz"), y=yq.numpy(), mag=magq.numpy(),
                         out_b1=fo_b1.numpy(), out_b3=fo_b3.numpy(), mel_fb=ref_fb.numpy())
     print("fast crm range", float(fo_b3.min()), float(fo_b3.max()))
+    # ------------------------------------------------------- improved_fullsubnet (A14)
+    from oracle import improved_fullsubnet_oracle as IO
+    from improved_fullsubnet.model import Model as ImpModel
+    res = {}
+    for tag, iargs, L in (("k16", dict(IO.DEFAULT_IMPROVED_ARGS), 4000), ("k48", dict(IO.ARGS_48K_1024), 12000)):
+        isd = IO.make_improved_state_dict(seed=5, args=iargs)
+        im = ImpModel(**iargs).eval()
+        assert [k for k, _ in IO.improved_state_dict_shapes(iargs)] == list(im.state_dict().keys())
+        im.load_state_dict(isd, strict=True)
+        yi = O.make_noisy(2, L, seed=13, speechlike=True)
+        with torch.no_grad():
+            wi = im(yi)
+        res[tag + "_y"] = yi.numpy(); res[tag + "_wav"] = wi.numpy()
+        print("improved", tag, tuple(wi.shape), float(wi.abs().max()), sum(v.numel() for v in isd.values()))
+    np.savez_compressed(os.path.join(out_dir, "improved.npz"), **res)
     for f in sorted(os.listdir(out_dir)):
         print(f, os.path.getsize(os.path.join(out_dir, f)))
 

@@ -108,3 +108,19 @@ def test_fast_fullsubnet_state_dict_contract():
     m.load_state_dict(FO.make_fast_state_dict(3), strict=True)
     with pytest.raises(RuntimeError):
         m.eval()(torch.zeros(1, 1, 257, 4))  # no CPU path
+
+
+def test_improved_fullsubnet_state_dict_contract():
+    from fullsubnet_b200.improved_fullsubnet.model import Model
+    from oracle import improved_fullsubnet_oracle as IO
+    for args in (IO.DEFAULT_IMPROVED_ARGS, IO.ARGS_48K_1024):
+        m = Model(**args)
+        sd = m.state_dict()
+        want = IO.improved_state_dict_shapes(args)  # validated against the reference by oracle/make_golden.py
+        assert list(sd.keys()) == [k for k, _ in want]
+        assert [tuple(v.shape) for v in sd.values()] == [s for _, s in want]
+        m.load_state_dict(IO.make_improved_state_dict(5, args), strict=True)
+        with pytest.raises(RuntimeError):
+            m.eval()(torch.zeros(1, 2000))  # no CPU path
+    with pytest.raises(NotImplementedError):
+        Model(norm_type="cumulative_laplace_norm")

@@ -244,3 +244,28 @@ def test_fast_fullsubnet_matches_reference(golden, dev, precision, tol):
         with torch.no_grad():
             got = m(x.to(dev))
         assert rel_max(got.cpu(), ref) < tol, Tn
+
+
+# ------------------------------------------------------------------ improved_fullsubnet (config 5, A14)
+@pytest.mark.parametrize("tag", ["k16", "k48"])
+def test_improved_fullsubnet_matches_reference(golden, dev, tag):
+    from fullsubnet_b200.improved_fullsubnet.model import Model
+    from oracle import improved_fullsubnet_oracle as IO
+    g = golden("improved")
+    args = IO.DEFAULT_IMPROVED_ARGS if tag == "k16" else IO.ARGS_48K_1024
+    m = Model(**args)
+    m.load_state_dict(IO.make_improved_state_dict(seed=5, args=args), strict=True)
+    m = m.to(dev).eval()
+    y = T(g[tag + "_y"], dev)
+    with torch.no_grad():
+        wav = m(y)
+        wav3 = m(y.unsqueeze(1)[:1])
+    assert wav.shape == g[tag + "_wav"].shape
+    err = np.abs(wav.cpu().numpy() - g[tag + "_wav"]).max()
+    print(f"improved_fullsubnet {tag}: waveform max-abs {err:.2e} (scale {np.abs(g[tag + '_wav']).max():.2e})")
+    assert err < WAV_TOL
+    assert np.abs(wav3.cpu().numpy() - g[tag + "_wav"][:1]).max() < WAV_TOL
+    # bad section geometry: ValueError like the reference (model.py:341-345)
+    bad = Model(**dict(args, freq_cutoffs=[21] + list(args["freq_cutoffs"][1:]))).to(dev).eval()
+    with pytest.raises(ValueError), torch.no_grad():
+        bad(y)

@@ -125,3 +125,15 @@ def test_fast_fullsubnet_oracle_matches_reference(golden):
         d = FO.real_time_downsampling(x, 2)
         assert d.shape[-1] == 1 + (Tn - 1 + 1) // 2
         assert FO.real_time_upsampling(d, 2, Tn).shape[-1] == Tn
+
+
+def test_improved_fullsubnet_oracle_matches_reference(golden):
+    from oracle import improved_fullsubnet_oracle as IO
+    g = golden("improved")
+    for tag, args in (("k16", IO.DEFAULT_IMPROVED_ARGS), ("k48", IO.ARGS_48K_1024)):
+        sd = IO.make_improved_state_dict(seed=5, args=args)
+        wav = IO.improved_forward(T(g[tag + "_y"]), sd, args)
+        assert wav.shape == g[tag + "_wav"].shape
+        assert np.abs(wav.numpy() - g[tag + "_wav"]).max() < 2e-6 * max(1.0, np.abs(g[tag + "_wav"]).max()), tag
+    with pytest.raises(ValueError):
+        IO.freq_unfold(torch.zeros(1, 1, 40, 3), 0, 21, 4, 15)
