@@ -91,6 +91,7 @@ struct ImpWs {
   float *fb_pp, *fb_h1all;
   unsigned int* barrier;
   float *h0[2], *h1[2], *c0, *c1;
+  float *fbs_h0[2], *fbs_c0, *fbs_c1;  // per-step full-band fallback
   size_t bytes;
 };
 
@@ -147,6 +148,9 @@ static void imp_carve(const fsn_improved_desc* d, const ImpDims& m, void* base, 
   const size_t RH = (size_t)m.B * m.maxR * d->sb_hidden;
   for (int i = 0; i < 2; ++i) { w.h0[i] = c.take<float>(RH); w.h1[i] = c.take<float>(RH); }
   w.c0 = c.take<float>(RH); w.c1 = c.take<float>(RH);
+  const size_t BH = (size_t)m.B * d->fb_hidden;
+  w.fbs_h0[0] = c.take<float>(BH); w.fbs_h0[1] = c.take<float>(BH);
+  w.fbs_c0 = c.take<float>(BH); w.fbs_c1 = c.take<float>(BH);
   w.bytes = c.off;
 }
 
@@ -173,8 +177,6 @@ extern "C" int fsn_improved_forward(const fsn_improved_desc* d, const fsn_improv
   imp_carve(d, m, workspace, w);
   FSN_REQUIRE(workspace && workspace_bytes >= w.bytes, FSN_ERR_WORKSPACE, "workspace too small: %zu < %zu",
               workspace_bytes, w.bytes);
-  FSN_REQUIRE(fb_persistent_supported(m.Fu, d->fb_hidden, d->fb_hidden), FSN_ERR_UNSUPPORTED,
-              "improved model: full-band stack does not fit the persistent kernel");
   cudaStream_t st = (cudaStream_t)stream;
   const int T = m.T, F = m.F, Fu = m.Fu, Hf = d->fb_hidden, Hs = d->sb_hidden;
   const float eps = 1.1920928955078125e-07f;  // np.finfo(np.float32).eps (model.py:23,148)
@@ -190,11 +192,34 @@ extern "C" int fsn_improved_forward(const fsn_improved_desc* d, const fsn_improv
   // full band: norm (566) -> 2xLSTM + Linear (567)
   if ((rc = clip_stats_launch(w.magc, B, T, Fu, 0, w.fs, w.sums, st))) return rc;
   if ((rc = norm_scales_launch(w.sums, w.sums, B, (float)Fu * T, 1.f, w.inv1, nullptr, st, eps))) return rc;
-  for (int b0 = 0; b0 < B; b0 += 256) {
-    const int nb = (B - b0 < 256) ? B - b0 : 256;
-    if ((rc = fb_persistent_launch(&wt->fb, w.magc + (size_t)b0 * T * Fu, w.inv1 + b0, w.fb_pp,
-                                   w.fb_h1all + (size_t)b0 * T * Hf, w.barrier, nb, Fu, Hf, Hf, T, st)))
-      return rc;
+  if (fb_persistent_supported(Fu, Hf, Hf)) {
+    for (int b0 = 0; b0 < B; b0 += 256) {
+      const int nb = (B - b0 < 256) ? B - b0 : 256;
+      if ((rc = fb_persistent_launch(&wt->fb, w.magc + (size_t)b0 * T * Fu, w.inv1 + b0, w.fb_pp,
+                                     w.fb_h1all + (size_t)b0 * T * Hf, w.barrier, nb, Fu, Hf, Hf, T, st)))
+        return rc;
+    }
+  } else {
+    // weights of a (Fu + 3 Hf) x 16 slice exceed one SM's shared memory (n_fft = 1024): per-step kernels
+    for (int t = 0; t < T; ++t) {
+      StepParams p;
+      memset(&p, 0, sizeof(p));
+      p.R = B; p.H = Hf; p.first = (t == 0);
+      p.K0 = Fu;
+      p.w_ih = wt->fb.w_ih[0]; p.w_hh = wt->fb.w_hh[0]; p.b_ih = wt->fb.b_ih[0]; p.b_hh = wt->fb.b_hh[0];
+      p.h_prev = w.fbs_h0[(t + 1) & 1]; p.h_prev_stride = Hf;
+      p.h_out = w.fbs_h0[t & 1]; p.h_out_stride = Hf;
+      p.c = w.fbs_c0;
+      p.x0 = w.magc + (size_t)t * Fu; p.x0_row_stride = (size_t)T * Fu; p.row_scale = w.inv1;
+      if ((rc = lstm_step_launch(p, SEG0_DENSE, st))) return rc;
+      p.K0 = Hf;
+      p.w_ih = wt->fb.w_ih[1]; p.w_hh = wt->fb.w_hh[1]; p.b_ih = wt->fb.b_ih[1]; p.b_hh = wt->fb.b_hh[1];
+      p.x0 = w.fbs_h0[t & 1]; p.x0_row_stride = Hf; p.row_scale = nullptr;
+      p.h_prev = w.fb_h1all + (size_t)(t > 0 ? t - 1 : 0) * Hf; p.h_prev_stride = (size_t)T * Hf;
+      p.h_out = w.fb_h1all + (size_t)t * Hf; p.h_out_stride = (size_t)T * Hf;
+      p.c = w.fbs_c1;
+      if ((rc = lstm_step_launch(p, SEG0_DENSE, st))) return rc;
+    }
   }
   if ((rc = fc_gemm_launch(w.fb_h1all, wt->fb.fc_w, wt->fb.fc_b, w.fbT, B * T, Hf, Fu, d->fb_activation, st))) return rc;
   // cRM, Nyquist row = 0 (572)
