@@ -44,6 +44,20 @@ class FastWeights(C.Structure):
                 ("bn_packed", C.c_void_p)]
 
 
+class SeqGrads(C.Structure):
+    _fields_ = [("w_ih", C.c_void_p * 2), ("w_hh", C.c_void_p * 2), ("b_ih", C.c_void_p * 2),
+                ("b_hh", C.c_void_p * 2), ("fc_w", C.c_void_p), ("fc_b", C.c_void_p)]
+
+
+MAX_PARAM_TENSORS = 64
+
+
+class ParamList(C.Structure):
+    _fields_ = [("n", C.c_int), ("param", C.c_void_p * MAX_PARAM_TENSORS), ("grad", C.c_void_p * MAX_PARAM_TENSORS),
+                ("exp_avg", C.c_void_p * MAX_PARAM_TENSORS), ("exp_avg_sq", C.c_void_p * MAX_PARAM_TENSORS),
+                ("numel", C.c_int64 * MAX_PARAM_TENSORS)]
+
+
 IMP_MAX_SECTIONS = 8
 
 
@@ -86,6 +100,15 @@ _SIGNATURES = {
     "fsn_improved_workspace_bytes": (_S, [C.POINTER(ImprovedDesc), _I, _I]),
     "fsn_improved_forward": (C.c_int, [C.POINTER(ImprovedDesc), C.POINTER(ImprovedWeights), _P, _I, _I, _P, _P, _P, _S,
                                        _P]),
+    "fsn_train_workspace_bytes": (_S, [C.POINTER(ModelDesc), _I, _I]),
+    "fsn_train_forward": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(SeqWeights), C.POINTER(SeqWeights), _P, _I, _I, _P,
+                                    _P, _S, _P]),
+    "fsn_train_backward": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(SeqWeights), C.POINTER(SeqWeights), _P, _I, _I,
+                                     C.POINTER(SeqGrads), C.POINTER(SeqGrads), _P, _S, _P]),
+    "fsn_mse_loss_scratch_bytes": (_S, []),
+    "fsn_mse_loss": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _P, _S, _P]),
+    "fsn_clip_adam_scratch_bytes": (_S, []),
+    "fsn_clip_adam": (C.c_int, [C.POINTER(ParamList), _F, _F, _F, _F, _F, _F, _I, _P, _P, _S, _P]),
     "fsn_last_launch_count": (C.c_int64, []),
     "fsn_set_profiling": (C.c_int, [_I]),
     "fsn_last_stage_ms": (C.c_float, [_I]),

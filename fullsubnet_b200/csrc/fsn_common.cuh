@@ -44,6 +44,24 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
   return i >= n ? 2 * (n - 1) - i : i;
 }
 
+// c[r] = #{(f,k): reflect(f+k) = r, |k| <= N}: multiplicity of row r in the unfolded tensor
+__device__ __forceinline__ int reflect_count(int r, int F, int N) {
+  int c = 0;
+  for (int k = -N; k <= N; ++k) {
+    int f = r - k;                       // f + k = r
+    c += (f >= 0 && f < F);
+    if (r > 0) {                         // f + k = -r (left reflection)
+      f = -r - k;
+      c += (f >= 0 && f < F);
+    }
+    if (r < F - 1) {                     // f + k = 2(F-1) - r (right reflection)
+      f = 2 * (F - 1) - r - k;
+      c += (f >= 0 && f < F);
+    }
+  }
+  return c;
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

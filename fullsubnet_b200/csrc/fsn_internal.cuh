@@ -33,6 +33,9 @@ struct StepParams {
   const float* h_prev; size_t h_prev_stride;
   float* h_out; size_t h_out_stride;
   float* c;
+  // training only (both nullable): previous cell state read from c_in instead of c; post-activation gates
+  // (i,f,g,o) of this step stored at save_gates[row*4H + g*H + u]
+  const float* c_in; float* save_gates;
   // SEG0_DENSE: x = x0[row * x0_row_stride + k] * (row_scale ? row_scale[row] : 1)
   const float* x0; size_t x0_row_stride; const float* row_scale;
   int row_scale_div;  // scale index = row / row_scale_div (0 or 1: per row)
@@ -43,6 +46,22 @@ struct StepParams {
 };
 
 int lstm_step_launch(const StepParams& p, int mode, cudaStream_t st);
+
+// shapes of one Model.forward call (fsn_model.cu)
+struct Dims {
+  int B, T, Tp, F, Fsub, G, R, Ksb;
+};
+int make_dims(const fsn_model_desc* d, int B, int T, Dims& m);
+
+// (clip, frequency) -> sub-band row, or -1 when drop_band removed the unit (inverse of row_to_unit)
+__host__ __device__ inline int unit_to_row(const RowMap& m, int b, int f) {
+  if (m.G <= 1) return b * m.Fsub + f;
+  const int g = b % m.G;
+  if (f % m.G != g || f / m.G >= m.Fsub) return -1;
+  int off = 0;
+  for (int gg = 0; gg < g; ++gg) off += (m.B - gg + m.G - 1) / m.G;
+  return (off + b / m.G) * m.Fsub + f / m.G;
+}
 int fc_gemm_launch(const float* A, const float* W, const float* bias, float* out, int M, int K, int O, int act,
                    cudaStream_t st, bool w_kmajor = false);
 // out[row*row_stride + o*o_stride] = act(h[row,:] . W[o,:] + b[o]), one warp per row (small O)

@@ -28,23 +28,6 @@ __global__ void transpose_mag_kernel(const float* __restrict__ in, float* __rest
   }
 }
 
-// c[r] = #{(f,k): reflect(f+k) = r, |k| <= N}: multiplicity of row r in the unfolded tensor
-__device__ __forceinline__ int reflect_count(int r, int F, int N) {
-  int c = 0;
-  for (int k = -N; k <= N; ++k) {
-    int f = r - k;                       // f + k = r
-    c += (f >= 0 && f < F);
-    if (r > 0) {                         // f + k = -r (left reflection)
-      f = -r - k;
-      c += (f >= 0 && f < F);
-    }
-    if (r < F - 1) {                     // f + k = 2(F-1) - r (right reflection)
-      f = 2 * (F - 1) - r - k;
-      c += (f >= 0 && f < F);
-    }
-  }
-  return c;
-}
 
 // one warp per (b,t) row of a time-major [B,T_pad,F] tensor: fs[row] = (sum_f x, sum_f c_N[f] x)
 __global__ void frame_stats_kernel(const float* __restrict__ x, int rows, int F, int N, float2* __restrict__ fs) {
@@ -191,10 +174,15 @@ __global__ void __launch_bounds__(256) lstm_step_kernel(const StepParams p) {
       const float gg = acc[i][2][q] + bias[2];
       const float go = acc[i][3][q] + bias[3];
       const size_t ci = (size_t)row * p.H + u;
-      const float c_prev = p.first ? 0.f : p.c[ci];
-      const float c = sigmoidf_(gf) * c_prev + sigmoidf_(gi) * tanhf(gg);
+      const float c_prev = p.first ? 0.f : (p.c_in ? p.c_in[ci] : p.c[ci]);
+      const float si = sigmoidf_(gi), sf = sigmoidf_(gf), tg = tanhf(gg), so = sigmoidf_(go);
+      const float c = sf * c_prev + si * tg;
       p.c[ci] = c;
-      p.h_out[(size_t)row * p.h_out_stride + u] = sigmoidf_(go) * tanhf(c);
+      p.h_out[(size_t)row * p.h_out_stride + u] = so * tanhf(c);
+      if (p.save_gates) {
+        float* gp = p.save_gates + (size_t)row * 4 * p.H + u;
+        gp[0] = si; gp[p.H] = sf; gp[2 * p.H] = tg; gp[3 * p.H] = so;
+      }
     }
   }
 }

@@ -51,11 +51,7 @@ struct ModelWs {
   size_t bytes;
 };
 
-struct Dims {
-  int B, T, Tp, F, Fsub, G, R, Ksb;
-};
-
-static int make_dims(const fsn_model_desc* d, int B, int T, Dims& m) {
+int make_dims(const fsn_model_desc* d, int B, int T, Dims& m) {
   FSN_REQUIRE(d && d->num_freqs > 1 && d->fb_hidden > 0 && d->sb_hidden > 0 && d->look_ahead >= 0, FSN_ERR_SHAPE,
               "model: bad descriptor");
   FSN_REQUIRE(B > 0 && T > 0, FSN_ERR_SHAPE, "model: empty input (B=%d, T=%d)", B, T);

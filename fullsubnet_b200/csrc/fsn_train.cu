@@ -1,0 +1,731 @@
+// Training step of recipes/dns_interspeech_2020/fullsubnet/trainer.py:56-68, fp32:
+//   fsn_train_forward   Model.forward in train mode, keeping what back-propagation through time needs
+//   fsn_mse_loss        audio_zen/loss.py:4 (MSELoss) + d loss / d cRM
+//   fsn_train_backward  BPTT through sub-band stack -> second norm (closed form) -> drop_band row map ->
+//                       full-band Linear/ReLU -> full-band stack; weight gradients as split-K GEMMs over all steps
+//   fsn_clip_adam       clip_grad_norm_ + Adam in three launches, no host synchronisation
+// All saved activations are time-major ([Tp, rows, ...]) so every per-step operand is one contiguous block and
+// every weight gradient is one GEMM over K = Tp*rows.  oracle/train_oracle.py:manual_backward is the same
+// algorithm on the CPU.
+#include <string.h>
+
+#include "fsn_internal.cuh"
+
+namespace fsn {
+
+// ------------------------------------------------------------------------------------------ GEMM
+// C[M,N] (+)= op(A) B,  B [K,N] row-major (ldb); op(A) = A [M,K] (lda) or, TA, A stored [K,M] (lda).
+// 64x64 tile, 4x4 per thread.  blockIdx.z = split-K slice writing its own [M,N] slab (ldc = N) at C + z*M*N.
+template <bool TA>
+__global__ void __launch_bounds__(256)
+sgemm_kernel(const float* __restrict__ A, size_t lda, const float* __restrict__ Bm, size_t ldb, float* __restrict__ C,
+             size_t ldc, int M, int N, int K, int k_per_split, int accumulate, size_t split_stride) {
+  __shared__ __align__(16) float As[16][64];
+  __shared__ __align__(16) float Bs[16][64];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  const int kb = blockIdx.z * k_per_split;
+  const int ke = (kb + k_per_split < K) ? kb + k_per_split : K;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = kb; k0 < ke; k0 += 16) {
+    if (!TA) {
+      const int row = tid >> 2, kq = (tid & 3) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + kq + j;
+        As[kq + j][row] = (m0 + row < M && k < ke) ? A[(size_t)(m0 + row) * lda + k] : 0.f;
+      }
+    } else {
+      const int kk = tid >> 4, mq = (tid & 15) * 4, k = k0 + kk;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int m = m0 + mq + j;
+        As[kk][mq + j] = (k < ke && m < M) ? A[(size_t)k * lda + m] : 0.f;
+      }
+    }
+    {
+      const int kk = tid >> 4, nq = (tid & 15) * 4, k = k0 + kk;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + nq + j;
+        Bs[kk][nq + j] = (k < ke && n < N) ? Bm[(size_t)k * ldb + n] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float b = Bs[kk][tx + 16 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i][j] = fmaf(a[i], b, acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+  float* Cz = C + (size_t)blockIdx.z * split_stride;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    if (row >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tx + 16 * j;
+      if (col >= N) continue;
+      float* dst = Cz + (size_t)row * ldc + col;
+      *dst = accumulate ? *dst + acc[i][j] : acc[i][j];
+    }
+  }
+}
+
+// C[m,n] (+)= sum_s part[s][m][n]  (fixed order: deterministic)
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int S, int M, int N, float* __restrict__ C,
+                                     size_t ldc, int accumulate) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)M * N) return;
+  float s = 0.f;
+  for (int z = 0; z < S; ++z) s += part[(size_t)z * M * N + i];
+  float* dst = C + (i / N) * ldc + (i % N);
+  *dst = accumulate ? *dst + s : s;
+}
+
+static const size_t SPLITK_SCRATCH_FLOATS = (size_t)16 << 20;  // 64 MB
+
+static int sgemm_launch(bool ta, const float* A, size_t lda, const float* Bm, size_t ldb, float* C, size_t ldc, int M,
+                        int N, int K, bool accumulate, float* scratch, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return FSN_OK;
+  const int tiles = cdiv(M, 64) * cdiv(N, 64);
+  int S = 1;
+  if (scratch && K >= 4096 && tiles < 592) {  // fill 148 SMs x 4 CTAs; slices of >= 1024 k
+    S = cdiv(592, tiles);
+    if (S > cdiv(K, 1024)) S = cdiv(K, 1024);
+    while (S > 1 && (size_t)S * M * N > SPLITK_SCRATCH_FLOATS) --S;
+  }
+  const int kps = cdiv(cdiv(K, S), 16) * 16;
+  S = cdiv(K, kps);
+  dim3 grid(cdiv(M, 64), cdiv(N, 64), S);
+  float* dst = S > 1 ? scratch : C;
+  const size_t ldd = S > 1 ? (size_t)N : ldc;
+  const int acc = (S > 1) ? 0 : (accumulate ? 1 : 0);
+  if (ta) sgemm_kernel<true><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, dst, ldd, M, N, K, kps, acc, (size_t)M * N);
+  else    sgemm_kernel<false><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, dst, ldd, M, N, K, kps, acc, (size_t)M * N);
+  FSN_CHECK_LAUNCH("sgemm_kernel");
+  if (S > 1) {
+    const size_t n = (size_t)M * N;
+    splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scratch, S, M, N, C, ldc, accumulate ? 1 : 0);
+    FSN_CHECK_LAUNCH("splitk_reduce_kernel");
+  }
+  return FSN_OK;
+}
+
+// out[c] = sum_r X[r*ldx + c]: slabs of rows -> part[S][cols] -> fixed-order sum
+__global__ void colsum_part_kernel(const float* __restrict__ X, size_t rows, int cols, size_t ldx, size_t rows_per,
+                                   float* __restrict__ part) {
+  __shared__ float sh[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const size_t r0 = (size_t)blockIdx.y * rows_per;
+  const size_t r1 = (r0 + rows_per < rows) ? r0 + rows_per : rows;
+  float s = 0.f;
+  if (c < cols)
+    for (size_t r = r0 + threadIdx.y; r < r1; r += 8) s += X[r * ldx + c];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+    part[(size_t)blockIdx.y * cols + c] = t;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, int S, int cols, float* __restrict__ out,
+                                    float* __restrict__ out2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int z = 0; z < S; ++z) s += part[(size_t)z * cols + c];
+  out[c] = s;
+  if (out2) out2[c] = s;
+}
+static const int COLSUM_MAX_S = 512;
+static int colsum_launch(const float* X, size_t rows, int cols, size_t ldx, float* out, float* out2, float* scratch,
+                         cudaStream_t st) {
+  int S = (int)((rows + 2047) / 2048);
+  if (S > COLSUM_MAX_S) S = COLSUM_MAX_S;
+  if (S < 1) S = 1;
+  const size_t rows_per = (rows + S - 1) / S;
+  colsum_part_kernel<<<dim3(cdiv(cols, 32), S), dim3(32, 8), 0, st>>>(X, rows, cols, ldx, rows_per, scratch);
+  FSN_CHECK_LAUNCH("colsum_part_kernel");
+  colsum_final_kernel<<<cdiv(cols, 128), 128, 0, st>>>(scratch, S, cols, out, out2);
+  FSN_CHECK_LAUNCH("colsum_final_kernel");
+  return FSN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ forward helpers
+// per-clip sums of noisy_mag [B,F,T]: (sum, sum_f c_Ns[f] * row sum), one CTA per clip, fixed-order tree
+__global__ void train_mag_stats_kernel(const float* __restrict__ mag, int F, int T, int Ns, float2* __restrict__ sums) {
+  __shared__ float2 sh[256];
+  const int b = blockIdx.x;
+  const float* p = mag + (size_t)b * F * T;
+  float2 a = make_float2(0.f, 0.f);
+  for (int i = threadIdx.x; i < F * T; i += 256) {
+    const float v = p[i];
+    a.x += v;
+    a.y += v * (float)reflect_count(i / T, F, Ns);
+  }
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { sh[threadIdx.x].x += sh[threadIdx.x + s].x; sh[threadIdx.x].y += sh[threadIdx.x + s].y; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sums[b] = sh[0];
+}
+
+// same for a time-major tensor x [Tp,B,F]
+__global__ void train_tm_stats_kernel(const float* __restrict__ x, int B, int F, int Tp, int N, float2* __restrict__ sums) {
+  __shared__ float2 sh[256];
+  const int b = blockIdx.x;
+  float2 a = make_float2(0.f, 0.f);
+  for (int i = threadIdx.x; i < F * Tp; i += 256) {
+    const int t = i / F, f = i - t * F;
+    const float v = x[((size_t)t * B + b) * F + f];
+    a.x += v;
+    a.y += v * (float)reflect_count(f, F, N);
+  }
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { sh[threadIdx.x].x += sh[threadIdx.x + s].x; sh[threadIdx.x].y += sh[threadIdx.x + s].y; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sums[b] = sh[0];
+}
+
+// mag [B,F,T] -> raw [Tp,B,F] (zero look-ahead frames, model.py:85) and scaled = raw * inv1[b] (model.py:92)
+__global__ void train_transpose_kernel(const float* __restrict__ mag, const float* __restrict__ inv1,
+                                       float* __restrict__ raw, float* __restrict__ scaled, int B, int F, int T, int Tp) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, f0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    const int f = f0 + i, t = t0 + tx;
+    tile[i][tx] = (f < F && t < T) ? mag[((size_t)b * F + f) * T + t] : 0.f;
+  }
+  __syncthreads();
+  const float s = inv1[b];
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, f = f0 + tx;
+    if (t < Tp && f < F) {
+      const float v = tile[tx][i];
+      const size_t o = ((size_t)t * B + b) * F + f;
+      raw[o] = v;
+      scaled[o] = v * s;
+    }
+  }
+}
+
+// sub-band input X[t,r,k] (base_model.py:13-46 + model.py:98-119): unit (b,f) of row r, scaled by inv2[b]
+__global__ void train_gather_kernel(const float* __restrict__ raw, const float* __restrict__ fbz,
+                                    const float* __restrict__ inv2, float* __restrict__ X, RowMap map, int Tp, int R,
+                                    int Ns, int Nf) {
+  const int K = 2 * Ns + 1 + 2 * Nf + 1;
+  const size_t n = (size_t)Tp * R * K;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const size_t tr = i / K;
+    const int r = (int)(tr % R), t = (int)(tr / R);
+    int b, f;
+    row_to_unit(map, r, b, f);
+    const size_t base = ((size_t)t * map.B + b) * map.F;
+    float v;
+    if (k < 2 * Ns + 1) v = raw[base + reflect_idx(f + k - Ns, map.F)];
+    else                v = fbz[base + reflect_idx(f + (k - 2 * Ns - 1) - Nf, map.F)];
+    X[i] = v * inv2[b];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ backward kernels
+// dout[t,r,o] = dcrm[b',o,f',t-la] (0 for the look-ahead steps)  (model.py:129-135 backwards)
+__global__ void train_dout_kernel(const float* __restrict__ dcrm, float* __restrict__ dout, int R, int Fsub, int T,
+                                  int Tp, int la) {
+  const size_t n = (size_t)Tp * R * 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i & 1);
+    const size_t tr = i >> 1;
+    const int r = (int)(tr % R), t = (int)(tr / R);
+    float v = 0.f;
+    if (t >= la) {
+      const int bq = r / Fsub, fq = r - bq * Fsub;
+      v = dcrm[(((size_t)bq * 2 + o) * Fsub + fq) * T + (t - la)];
+    }
+    dout[i] = v;
+  }
+}
+
+struct BwdPoint {
+  int R, H;
+  float* G;             // [R,4H] in: gates (post-activation), out: d(pre-activation)
+  const float* C;       // [R,H] cell state of this step
+  const float* C_prev;  // nullable (t == 0)
+  const float* dh_above;  // nullable [R,H]
+  const float* dh_rec;    // nullable [R,H]
+  float* dc;              // [R,H] in (ignored when first_dc): d c_t from step t+1, out: d c_{t-1}
+  int first_dc;
+  const float* dout;  // nullable [R,O]: dh_above += dout W_fc   (Linear backward, small O)
+  const float* fc_w;  // [O,H]
+  int O;
+};
+
+__global__ void lstm_bwd_point_kernel(const BwdPoint p) {
+  const size_t n = (size_t)p.R * p.H;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int u = (int)(idx % p.H);
+    const size_t r = idx / p.H;
+    float dh = 0.f;
+    if (p.dh_above) dh += p.dh_above[idx];
+    if (p.dh_rec) dh += p.dh_rec[idx];
+    if (p.dout)
+      for (int o = 0; o < p.O; ++o) dh = fmaf(p.dout[r * p.O + o], p.fc_w[(size_t)o * p.H + u], dh);
+    float* g = p.G + r * 4 * p.H + u;
+    const float gi = g[0], gf = g[p.H], gg = g[2 * p.H], go = g[3 * p.H];
+    const float tc = tanhf(p.C[idx]);
+    const float dc_tot = (p.first_dc ? 0.f : p.dc[idx]) + dh * go * (1.f - tc * tc);
+    const float c_prev = p.C_prev ? p.C_prev[idx] : 0.f;
+    g[0] = dc_tot * gg * gi * (1.f - gi);
+    g[p.H] = dc_tot * c_prev * gf * (1.f - gf);
+    g[2 * p.H] = dc_tot * gi * (1.f - gg * gg);
+    g[3 * p.H] = dh * tc * go * (1.f - go);
+    p.dc[idx] = dc_tot * gf;
+  }
+}
+
+// dot[b'] = sum over the rows of output clip b' and all t,k of dX * X   (second-norm backward)
+__global__ void train_dot_kernel(const float* __restrict__ dX, const float* __restrict__ X, int Tp, int R, int Fsub,
+                                 int K, float* __restrict__ dot) {
+  __shared__ float sh[256];
+  const int bq = blockIdx.x;
+  const size_t per_t = (size_t)Fsub * K;
+  float a = 0.f;
+  for (int t = 0; t < Tp; ++t) {
+    const size_t base = ((size_t)t * R + (size_t)bq * Fsub) * K;
+    for (size_t i = threadIdx.x; i < per_t; i += 256) a = fmaf(dX[base + i], X[base + i], a);
+  }
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dot[bq] = sh[0];
+}
+
+// dz[t,b,f] = act'(fbz) * ( dX[t, row(b,f), K-1] * inv2[b]  -  inv2[b] * dot[b'(b)] * c_Nf[f] / cnt2 )   (Nf = 0)
+__global__ void train_dfbz_kernel(const float* __restrict__ dX, const float* __restrict__ fbz,
+                                  const float* __restrict__ inv2, const float* __restrict__ dot, RowMap map, int Tp,
+                                  int R, int K, float cnt2, int act, float* __restrict__ dz) {
+  const size_t n = (size_t)Tp * map.B * map.F;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int f = (int)(i % map.F);
+    const size_t tb = i / map.F;
+    const int b = (int)(tb % map.B), t = (int)(tb / map.B);
+    // output clip of b: row of any kept frequency of that clip / Fsub
+    int bq;
+    if (map.G <= 1) bq = b;
+    else bq = unit_to_row(map, b, b % map.G) / map.Fsub;
+    const float s = inv2[b];
+    float v = -s * dot[bq] / cnt2;
+    const int r = unit_to_row(map, b, f);
+    if (r >= 0) v = fmaf(dX[((size_t)t * R + r) * K + (K - 1)], s, v);
+    const float y = fbz[i];
+    if (act == FSN_ACT_RELU) v = y > 0.f ? v : 0.f;
+    else if (act == FSN_ACT_TANH) v *= 1.f - y * y;
+    else if (act == FSN_ACT_RELU6) v = (y > 0.f && y < 6.f) ? v : 0.f;
+    dz[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ workspace
+struct LayerSave { float *G, *C, *H; };
+
+struct TrainWs {
+  float *raw, *xfb, *fbz, *inv1, *inv2;
+  float2 *sums_mag, *sums_fb;
+  LayerSave fb[2], sb[2];
+  float *xsb, *dxsb, *dout, *dz, *dfh1;
+  float *dh_rec[2], *dc[2], *dh_mid, *dot;
+  float *splitk, *colsum;
+  size_t bytes;
+};
+
+struct TCarver {
+  char* base; size_t off;
+  explicit TCarver(void* p) : base((char*)p), off(0) {}
+  float* take(size_t n) {
+    float* r = base ? (float*)(base + off) : nullptr;
+    off = align_up(off + n * sizeof(float), 256);
+    return r;
+  }
+};
+
+static void carve_train(const fsn_model_desc* d, const Dims& m, void* base, TrainWs& w) {
+  TCarver c(base);
+  const size_t Tp = m.Tp, B = m.B, F = m.F, R = m.R, Hf = d->fb_hidden, Hs = d->sb_hidden;
+  w.raw = c.take(Tp * B * F); w.xfb = c.take(Tp * B * F); w.fbz = c.take(Tp * B * F);
+  w.inv1 = c.take(B); w.inv2 = c.take(B);
+  w.sums_mag = (float2*)c.take(2 * B); w.sums_fb = (float2*)c.take(2 * B);
+  for (int l = 0; l < 2; ++l) {
+    w.fb[l].G = c.take(Tp * B * 4 * Hf); w.fb[l].C = c.take(Tp * B * Hf); w.fb[l].H = c.take(Tp * B * Hf);
+    w.sb[l].G = c.take(Tp * R * 4 * Hs); w.sb[l].C = c.take(Tp * R * Hs); w.sb[l].H = c.take(Tp * R * Hs);
+  }
+  w.xsb = c.take(Tp * R * m.Ksb); w.dxsb = c.take(Tp * R * m.Ksb);
+  w.dout = c.take(Tp * R * 2);
+  w.dz = c.take(Tp * B * F); w.dfh1 = c.take(Tp * B * Hf);
+  const size_t RH = (R * Hs > B * Hf) ? R * Hs : B * Hf;
+  for (int i = 0; i < 2; ++i) { w.dh_rec[i] = c.take(RH); w.dc[i] = c.take(RH); }
+  w.dh_mid = c.take(RH);
+  w.dot = c.take(B);
+  w.splitk = c.take(SPLITK_SCRATCH_FLOATS);
+  const size_t maxcols = 4 * (Hf > Hs ? Hf : Hs) > F ? 4 * (Hf > Hs ? Hf : Hs) : F;
+  w.colsum = c.take((size_t)COLSUM_MAX_S * maxcols);
+  w.bytes = c.off;
+}
+
+static int train_check(const fsn_model_desc* d) {
+  FSN_REQUIRE(d->fb_num_neighbors == 0, FSN_ERR_UNSUPPORTED,
+              "training: fb_num_neighbors > 0 is not built (every shipped recipe uses 0)");
+  return FSN_OK;
+}
+
+// one layer forward over all steps, saving gates / cell / hidden:  X [Tp,R,K0] (row_scale == nullptr)
+static int layer_forward_save(const fsn_seq_weights* w, int l, const float* X, int R, int K0, int H, int Tp,
+                              const LayerSave& s, cudaStream_t st) {
+  for (int t = 0; t < Tp; ++t) {
+    StepParams p;
+    memset(&p, 0, sizeof(p));
+    p.R = R; p.K0 = K0; p.H = H; p.first = (t == 0);
+    p.w_ih = w->w_ih[l]; p.w_hh = w->w_hh[l]; p.b_ih = w->b_ih[l]; p.b_hh = w->b_hh[l];
+    p.x0 = X + (size_t)t * R * K0; p.x0_row_stride = K0;
+    p.h_prev = s.H + (size_t)(t > 0 ? t - 1 : 0) * R * H; p.h_prev_stride = H;
+    p.h_out = s.H + (size_t)t * R * H; p.h_out_stride = H;
+    p.c = s.C + (size_t)t * R * H;
+    p.c_in = s.C + (size_t)(t > 0 ? t - 1 : 0) * R * H;
+    p.save_gates = s.G + (size_t)t * R * 4 * H;
+    int rc = lstm_step_launch(p, SEG0_DENSE, st);
+    if (rc) return rc;
+  }
+  return FSN_OK;
+}
+
+struct LayerBwd {
+  const float *w_ih, *w_hh;
+  LayerSave s;
+  int R, K0, H;
+  float *dh_rec, *dc;
+};
+
+// step t of one layer: pointwise gate gradients, then dh_rec = dG W_hh and (optionally) dx = dG W_ih
+static int layer_bwd_step(const LayerBwd& L, int t, int Tp, const float* dh_above, const float* dout, const float* fc_w,
+                          int O, float* dx, cudaStream_t st) {
+  BwdPoint p;
+  memset(&p, 0, sizeof(p));
+  p.R = L.R; p.H = L.H;
+  p.G = L.s.G + (size_t)t * L.R * 4 * L.H;
+  p.C = L.s.C + (size_t)t * L.R * L.H;
+  p.C_prev = t > 0 ? L.s.C + (size_t)(t - 1) * L.R * L.H : nullptr;
+  p.dh_above = dh_above;
+  p.dh_rec = (t == Tp - 1) ? nullptr : L.dh_rec;
+  p.dc = L.dc; p.first_dc = (t == Tp - 1);
+  p.dout = dout; p.fc_w = fc_w; p.O = O;
+  const size_t n = (size_t)L.R * L.H;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  lstm_bwd_point_kernel<<<blocks, 256, 0, st>>>(p);
+  FSN_CHECK_LAUNCH("lstm_bwd_point_kernel");
+  int rc;
+  if (t > 0)
+    if ((rc = sgemm_launch(false, p.G, 4 * L.H, L.w_hh, L.H, L.dh_rec, L.H, L.R, L.H, 4 * L.H, false, nullptr, st)))
+      return rc;
+  if (dx)
+    if ((rc = sgemm_launch(false, p.G, 4 * L.H, L.w_ih, L.K0, dx, L.K0, L.R, L.K0, 4 * L.H, false, nullptr, st)))
+      return rc;
+  return FSN_OK;
+}
+
+// weight / bias gradients of one layer from dG [Tp*R,4H] (in L.s.G), its input X [Tp*R,K0] and hidden states
+static int layer_weight_grads(const LayerBwd& L, int Tp, const float* X, float* g_w_ih, float* g_w_hh, float* g_b_ih,
+                              float* g_b_hh, const TrainWs& w, cudaStream_t st) {
+  const int H4 = 4 * L.H;
+  const int rows = Tp * L.R;
+  int rc;
+  if ((rc = sgemm_launch(true, L.s.G, H4, X, L.K0, g_w_ih, L.K0, H4, L.K0, rows, false, w.splitk, st))) return rc;
+  if (Tp > 1) {
+    if ((rc = sgemm_launch(true, L.s.G + (size_t)L.R * H4, H4, L.s.H, L.H, g_w_hh, L.H, H4, L.H, rows - L.R, false,
+                           w.splitk, st)))
+      return rc;
+  } else if ((rc = check_cuda(cudaMemsetAsync(g_w_hh, 0, (size_t)H4 * L.H * sizeof(float), st), "memset"))) {
+    return rc;
+  }
+  return colsum_launch(L.s.G, (size_t)rows, H4, H4, g_b_ih, g_b_hh, w.colsum, st);
+}
+
+}  // namespace fsn
+
+using namespace fsn;
+
+extern "C" size_t fsn_train_workspace_bytes(const fsn_model_desc* d, int B, int T) {
+  Dims m;
+  if (make_dims(d, B, T, m)) return 0;
+  TrainWs w;
+  carve_train(d, m, nullptr, w);
+  return w.bytes;
+}
+
+extern "C" int fsn_train_forward(const fsn_model_desc* d, const fsn_seq_weights* fb, const fsn_seq_weights* sb,
+                                 const float* noisy_mag, int B, int T, float* crm, void* workspace,
+                                 size_t workspace_bytes, fsn_stream_t stream) {
+  launch_counter() = 0;
+  Dims m;
+  int rc = make_dims(d, B, T, m);
+  if (rc) return rc;
+  if ((rc = train_check(d))) return rc;
+  TrainWs w;
+  carve_train(d, m, workspace, w);
+  FSN_REQUIRE(workspace && workspace_bytes >= w.bytes, FSN_ERR_WORKSPACE, "workspace too small: %zu < %zu",
+              workspace_bytes, w.bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Tp = m.Tp, F = m.F, Hf = d->fb_hidden, Hs = d->sb_hidden;
+  // first norm (model.py:92) and the time-major copies
+  train_mag_stats_kernel<<<B, 256, 0, st>>>(noisy_mag, F, T, d->sb_num_neighbors, w.sums_mag);
+  FSN_CHECK_LAUNCH("train_mag_stats_kernel");
+  if ((rc = norm_scales_launch(w.sums_mag, w.sums_mag, B, (float)F * Tp, 1.f, w.inv1, nullptr, st))) return rc;
+  train_transpose_kernel<<<dim3(cdiv(Tp, 32), cdiv(F, 32), B), dim3(32, 8), 0, st>>>(noisy_mag, w.inv1, w.raw, w.xfb, B,
+                                                                                     F, T, Tp);
+  FSN_CHECK_LAUNCH("train_transpose_kernel");
+  // full-band stack + Linear/activation (model.py:92-95)
+  if ((rc = layer_forward_save(fb, 0, w.xfb, B, F, Hf, Tp, w.fb[0], st))) return rc;
+  if ((rc = layer_forward_save(fb, 1, w.fb[0].H, B, Hf, Hf, Tp, w.fb[1], st))) return rc;
+  if ((rc = fc_gemm_launch(w.fb[1].H, fb->fc_w, fb->fc_b, w.fbz, Tp * B, Hf, F, d->fb_activation, st))) return rc;
+  // second norm in closed form (model.py:110-111)
+  train_tm_stats_kernel<<<B, 256, 0, st>>>(w.fbz, B, F, Tp, d->fb_num_neighbors, w.sums_fb);
+  FSN_CHECK_LAUNCH("train_tm_stats_kernel");
+  if ((rc = norm_scales_launch(w.sums_mag, w.sums_fb, B, 1.f, (float)F * m.Ksb * Tp, nullptr, w.inv2, st))) return rc;
+  // sub-band units (unfold + concat + norm + drop_band as one gather), then the sub-band stack (model.py:98-128)
+  RowMap map{B, F, m.Fsub, m.G};
+  train_gather_kernel<<<148 * 8, 256, 0, st>>>(w.raw, w.fbz, w.inv2, w.xsb, map, Tp, m.R, d->sb_num_neighbors,
+                                               d->fb_num_neighbors);
+  FSN_CHECK_LAUNCH("train_gather_kernel");
+  if ((rc = layer_forward_save(sb, 0, w.xsb, m.R, m.Ksb, Hs, Tp, w.sb[0], st))) return rc;
+  if ((rc = layer_forward_save(sb, 1, w.sb[0].H, m.R, Hs, Hs, Tp, w.sb[1], st))) return rc;
+  for (int t = d->look_ahead; t < Tp; ++t)
+    if ((rc = sb_fc_step_launch(w.sb[1].H + (size_t)t * m.R * Hs, m.R, Hs, sb->fc_w, sb->fc_b, 2, d->sb_activation, crm,
+                                m.Fsub, m.T, t - d->look_ahead, st)))
+      return rc;
+  return FSN_OK;
+}
+
+extern "C" int fsn_train_backward(const fsn_model_desc* d, const fsn_seq_weights* fb, const fsn_seq_weights* sb,
+                                  const float* dcrm, int B, int T, const fsn_seq_grads* gfb, const fsn_seq_grads* gsb,
+                                  void* workspace, size_t workspace_bytes, fsn_stream_t stream) {
+  launch_counter() = 0;
+  Dims m;
+  int rc = make_dims(d, B, T, m);
+  if (rc) return rc;
+  if ((rc = train_check(d))) return rc;
+  FSN_REQUIRE(d->sb_activation == FSN_ACT_NONE, FSN_ERR_UNSUPPORTED,
+              "training: sb_output_activate_function must be off (as in every shipped recipe)");
+  TrainWs w;
+  carve_train(d, m, workspace, w);
+  FSN_REQUIRE(workspace && workspace_bytes >= w.bytes, FSN_ERR_WORKSPACE, "workspace too small: %zu < %zu",
+              workspace_bytes, w.bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Tp = m.Tp, F = m.F, R = m.R, Hf = d->fb_hidden, Hs = d->sb_hidden, K = m.Ksb;
+  RowMap map{B, F, m.Fsub, m.G};
+  // ---- sub-band Linear (model.py:129-135 backwards)
+  train_dout_kernel<<<148 * 8, 256, 0, st>>>(dcrm, w.dout, R, m.Fsub, T, Tp, d->look_ahead);
+  FSN_CHECK_LAUNCH("train_dout_kernel");
+  if ((rc = sgemm_launch(true, w.dout, 2, w.sb[1].H, Hs, gsb->fc_w, Hs, 2, Hs, Tp * R, false, w.splitk, st))) return rc;
+  if ((rc = colsum_launch(w.dout, (size_t)Tp * R, 2, 2, gsb->fc_b, nullptr, w.colsum, st))) return rc;
+  // ---- sub-band stack, both layers one step apart
+  LayerBwd s1{sb->w_ih[1], sb->w_hh[1], w.sb[1], R, Hs, Hs, w.dh_rec[1], w.dc[1]};
+  LayerBwd s0{sb->w_ih[0], sb->w_hh[0], w.sb[0], R, K, Hs, w.dh_rec[0], w.dc[0]};
+  for (int t = Tp - 1; t >= 0; --t) {
+    if ((rc = layer_bwd_step(s1, t, Tp, nullptr, w.dout + (size_t)t * R * 2, sb->fc_w, 2, w.dh_mid, st))) return rc;
+    if ((rc = layer_bwd_step(s0, t, Tp, w.dh_mid, nullptr, nullptr, 0, w.dxsb + (size_t)t * R * K, st))) return rc;
+  }
+  if ((rc = layer_weight_grads(s1, Tp, w.sb[0].H, gsb->w_ih[1], gsb->w_hh[1], gsb->b_ih[1], gsb->b_hh[1], w, st)))
+    return rc;
+  if ((rc = layer_weight_grads(s0, Tp, w.xsb, gsb->w_ih[0], gsb->w_hh[0], gsb->b_ih[0], gsb->b_hh[0], w, st))) return rc;
+  // ---- second norm + drop_band + full-band Linear/activation
+  train_dot_kernel<<<B, 256, 0, st>>>(w.dxsb, w.xsb, Tp, R, m.Fsub, K, w.dot);
+  FSN_CHECK_LAUNCH("train_dot_kernel");
+  train_dfbz_kernel<<<148 * 8, 256, 0, st>>>(w.dxsb, w.fbz, w.inv2, w.dot, map, Tp, R, K, (float)F * K * Tp,
+                                             d->fb_activation, w.dz);
+  FSN_CHECK_LAUNCH("train_dfbz_kernel");
+  if ((rc = sgemm_launch(true, w.dz, F, w.fb[1].H, Hf, gfb->fc_w, Hf, F, Hf, Tp * B, false, w.splitk, st))) return rc;
+  if ((rc = colsum_launch(w.dz, (size_t)Tp * B, F, F, gfb->fc_b, nullptr, w.colsum, st))) return rc;
+  if ((rc = sgemm_launch(false, w.dz, F, fb->fc_w, Hf, w.dfh1, Hf, Tp * B, Hf, F, false, nullptr, st))) return rc;
+  // ---- full-band stack
+  LayerBwd f1{fb->w_ih[1], fb->w_hh[1], w.fb[1], B, Hf, Hf, w.dh_rec[1], w.dc[1]};
+  LayerBwd f0{fb->w_ih[0], fb->w_hh[0], w.fb[0], B, F, Hf, w.dh_rec[0], w.dc[0]};
+  for (int t = Tp - 1; t >= 0; --t) {
+    if ((rc = layer_bwd_step(f1, t, Tp, w.dfh1 + (size_t)t * B * Hf, nullptr, nullptr, 0, w.dh_mid, st))) return rc;
+    if ((rc = layer_bwd_step(f0, t, Tp, w.dh_mid, nullptr, nullptr, 0, nullptr, st))) return rc;
+  }
+  if ((rc = layer_weight_grads(f1, Tp, w.fb[0].H, gfb->w_ih[1], gfb->w_hh[1], gfb->b_ih[1], gfb->b_hh[1], w, st)))
+    return rc;
+  return layer_weight_grads(f0, Tp, w.xfb, gfb->w_ih[0], gfb->w_hh[0], gfb->b_ih[0], gfb->b_hh[0], w, st);
+}
+
+// ------------------------------------------------------------------------------------------ loss
+namespace fsn {
+// loss = mean((cirm - crm)^2) with cirm [B,Fs,T,2] (trainer.py:49-54) and crm [B,2,Fs,T] (Model.forward);
+// dcrm = 2 (crm - cirm) / n.  Stage 1: per-CTA partial sums; stage 2: fixed-order sum.
+__global__ void mse_part_kernel(const float* __restrict__ cirm, const float* __restrict__ crm, int Fs, int T, size_t n,
+                                float* __restrict__ dcrm, float* __restrict__ part) {
+  __shared__ float sh[256];
+  float a = 0.f;
+  const float k = 2.0f / (float)n;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    // i indexes crm [b,o,f,t]
+    const int t = (int)(i % T);
+    size_t q = i / T;
+    const int f = (int)(q % Fs); q /= Fs;
+    const int o = (int)(q & 1);
+    const size_t b = q >> 1;
+    const float dlt = crm[i] - cirm[((b * Fs + f) * T + t) * 2 + o];
+    a = fmaf(dlt, dlt, a);
+    if (dcrm) dcrm[i] = k * dlt;
+  }
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+__global__ void mse_final_kernel(const float* __restrict__ part, int nb, size_t n, float* __restrict__ loss) {
+  __shared__ double sh[256];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < nb; i += 256) a += (double)part[i];
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = (float)(sh[0] / (double)n);
+}
+constexpr int MSE_BLOCKS = 1024;
+}  // namespace fsn
+
+extern "C" size_t fsn_mse_loss_scratch_bytes(void) { return MSE_BLOCKS * sizeof(float); }
+
+extern "C" int fsn_mse_loss(const float* cirm, const float* crm, int B, int Fsub, int T, float* loss, float* dcrm,
+                            void* scratch, size_t scratch_bytes, fsn_stream_t stream) {
+  FSN_REQUIRE(B > 0 && Fsub > 0 && T > 0, FSN_ERR_SHAPE, "mse_loss: empty input");
+  FSN_REQUIRE(scratch && scratch_bytes >= MSE_BLOCKS * sizeof(float), FSN_ERR_WORKSPACE, "mse_loss: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)B * 2 * Fsub * T;
+  int nb = (int)((n + 255) / 256);
+  if (nb > MSE_BLOCKS) nb = MSE_BLOCKS;
+  mse_part_kernel<<<nb, 256, 0, st>>>(cirm, crm, Fsub, T, n, dcrm, (float*)scratch);
+  FSN_CHECK_LAUNCH("mse_part_kernel");
+  mse_final_kernel<<<1, 256, 0, st>>>((const float*)scratch, nb, n, loss);
+  FSN_CHECK_LAUNCH("mse_final_kernel");
+  return FSN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ clip + Adam
+namespace fsn {
+constexpr int ADAM_CHUNKS = 32;
+
+__global__ void gradsq_part_kernel(const fsn_param_list L, float* __restrict__ part) {
+  __shared__ float sh[256];
+  const int ti = blockIdx.y;
+  const float* g = L.grad[ti];
+  const int64_t n = L.numel[ti];
+  float a = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) a = fmaf(g[i], g[i], a);
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[ti * ADAM_CHUNKS + blockIdx.x] = sh[0];
+}
+
+// out[0] = total L2 norm of (grad * grad_scale); out[1] = grad_scale * min(1, max_norm / (norm + 1e-6))
+__global__ void gradnorm_final_kernel(const float* __restrict__ part, int n, float grad_scale, float max_norm,
+                                      float* __restrict__ out) {
+  __shared__ double sh[256];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) a += (double)part[i];
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float norm = (float)sqrt(sh[0]) * grad_scale;
+    float coef = max_norm > 0.f ? max_norm / (norm + 1e-6f) : 1.f;
+    if (coef > 1.f) coef = 1.f;
+    out[0] = norm;
+    out[1] = coef * grad_scale;
+  }
+}
+
+// torch.optim.Adam single-tensor update (no weight decay / amsgrad); the clipped, scaled gradient is written back
+__global__ void adam_kernel(const fsn_param_list L, const float* __restrict__ coef_ptr, float lr, float b1, float b2,
+                            float eps, float bc1, float bc2_sqrt) {
+  const int ti = blockIdx.y;
+  float* p = L.param[ti];
+  float* g = L.grad[ti];
+  float* m = L.exp_avg[ti];
+  float* v = L.exp_avg_sq[ti];
+  const int64_t n = L.numel[ti];
+  const float coef = coef_ptr[1];
+  const float step_size = lr / bc1;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const float gi = g[i] * coef;
+    g[i] = gi;
+    const float mi = m[i] * b1 + (1.f - b1) * gi;   // lerp(m, g, 1 - b1)
+    const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= step_size * (mi / denom);
+  }
+}
+}  // namespace fsn
+
+extern "C" size_t fsn_clip_adam_scratch_bytes(void) { return (FSN_MAX_PARAM_TENSORS * ADAM_CHUNKS + 2) * sizeof(float); }
+
+extern "C" int fsn_clip_adam(const fsn_param_list* L, float max_norm, float grad_scale, float lr, float beta1,
+                             float beta2, float eps, int step, float* norm_out, void* scratch, size_t scratch_bytes,
+                             fsn_stream_t stream) {
+  FSN_REQUIRE(L && L->n > 0 && L->n <= FSN_MAX_PARAM_TENSORS, FSN_ERR_SHAPE, "clip_adam: 1..%d tensors",
+              FSN_MAX_PARAM_TENSORS);
+  FSN_REQUIRE(step >= 1, FSN_ERR_SHAPE, "clip_adam: step starts at 1");
+  FSN_REQUIRE(scratch && scratch_bytes >= fsn_clip_adam_scratch_bytes(), FSN_ERR_WORKSPACE, "clip_adam: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = (float*)scratch;
+  float* res = norm_out ? norm_out : part + FSN_MAX_PARAM_TENSORS * ADAM_CHUNKS;
+  gradsq_part_kernel<<<dim3(ADAM_CHUNKS, L->n), 256, 0, st>>>(*L, part);
+  FSN_CHECK_LAUNCH("gradsq_part_kernel");
+  gradnorm_final_kernel<<<1, 256, 0, st>>>(part, L->n * ADAM_CHUNKS, grad_scale, max_norm, res);
+  FSN_CHECK_LAUNCH("gradnorm_final_kernel");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<dim3(ADAM_CHUNKS * 4, L->n), 256, 0, st>>>(*L, res, lr, beta1, beta2, eps, bc1, sqrtf(bc2));
+  FSN_CHECK_LAUNCH("adam_kernel");
+  return FSN_OK;
+}

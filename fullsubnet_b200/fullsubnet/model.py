@@ -17,6 +17,63 @@ from ..model.base_model import BaseModel
 from ..model.module.sequence_model import SequenceModel
 
 
+def _grad_struct(seq: SequenceModel, grads: dict, prefix: str) -> "_lib.SeqGrads":
+    g = _lib.SeqGrads()
+    for l in range(2):
+        for field, name in (("w_ih", "weight_ih"), ("w_hh", "weight_hh"), ("b_ih", "bias_ih"), ("b_hh", "bias_hh")):
+            getattr(g, field)[l] = grads[f"{prefix}sequence_model.{name}_l{l}"].data_ptr()
+    g.fc_w = grads[f"{prefix}fc_output_layer.weight"].data_ptr()
+    g.fc_b = grads[f"{prefix}fc_output_layer.bias"].data_ptr()
+    return g
+
+
+class _TrainForward(torch.autograd.Function):
+    """Model.forward in train mode with back-propagation through time in libfsn_b200 (fsn_train_forward /
+    fsn_train_backward).  The parameters are passed as inputs so autograd (and DDP's hooks) route the gradients to
+    them exactly as for the reference's nn.LSTM / nn.Linear modules (trainer.py:63)."""
+
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        B, _, F, T = x.shape
+        device = x.device
+        lib = _lib.load()
+        with torch.cuda.device(device):
+            desc = model._desc("fp32", int(model.num_groups_in_drop_band))
+            fb_w, sb_w = model.fb_model.weight_struct(), model.sb_model.weight_struct()
+            n = lib.fsn_train_workspace_bytes(C.byref(desc), B, T)
+            if n == 0:
+                _lib.check(_lib.FSN_ERR_SHAPE)
+            ws = torch.empty(n, dtype=torch.uint8, device=device)
+            G = desc.num_groups_in_drop_band if B > 1 and desc.num_groups_in_drop_band > 1 else 1
+            out = torch.empty(B, 2, F // G if G > 1 else F, T, dtype=torch.float32, device=device)
+            _lib.check(lib.fsn_train_forward(C.byref(desc), C.byref(fb_w), C.byref(sb_w), x.data_ptr(), B, T,
+                                             out.data_ptr(), ws.data_ptr(), n, _lib.stream_ptr(device)))
+        ctx.model, ctx.ws, ctx.dims, ctx.desc = model, ws, (B, T), desc
+        ctx.versions = model.fb_model.version_key() + model.sb_model.version_key()
+        return out
+
+    @staticmethod
+    def backward(ctx, dcrm):
+        model, (B, T) = ctx.model, ctx.dims
+        if ctx.versions != model.fb_model.version_key() + model.sb_model.version_key():
+            raise RuntimeError("fullsubnet_b200: a parameter was modified in place between forward and backward")
+        if ctx.ws is None:
+            raise RuntimeError("fullsubnet_b200: backward through the same forward twice (activations were released)")
+        dcrm = dcrm.contiguous().float()
+        device = dcrm.device
+        lib = _lib.load()
+        names = [k for k, _ in model.named_parameters()]
+        flat, grads = model._new_flat_grads(device)
+        with torch.cuda.device(device):
+            fb_w, sb_w = model.fb_model.weight_struct(), model.sb_model.weight_struct()
+            gfb, gsb = _grad_struct(model.fb_model, grads, "fb_model."), _grad_struct(model.sb_model, grads, "sb_model.")
+            _lib.check(lib.fsn_train_backward(C.byref(ctx.desc), C.byref(fb_w), C.byref(sb_w), dcrm.data_ptr(), B, T,
+                                              C.byref(gfb), C.byref(gsb), ctx.ws.data_ptr(), ctx.ws.numel(),
+                                              _lib.stream_ptr(device)))
+        ctx.ws = None
+        return (None, None) + tuple(grads[k] for k in names)
+
+
 class Model(BaseModel):
     def __init__(self, num_freqs, look_ahead, sequence_model, fb_num_neighbors, sb_num_neighbors,
                  fb_output_activate_function, sb_output_activate_function, fb_model_hidden_size,
@@ -87,11 +144,12 @@ class Model(BaseModel):
         batch_size, num_channels, num_freqs, num_frames = noisy_mag.size()
         assert num_channels == 1, f"{self.__class__.__name__} takes the mag feature as inputs."
         assert num_freqs == self.num_freqs, f"num_freqs {num_freqs} != {self.num_freqs}"
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "fullsubnet_b200: the backward (BPTT) kernels are not built yet; call under torch.no_grad() / "
-                "model.eval().  (SURVEY 8a row A11, next round)")
         x = _lib.require_cuda(noisy_mag, "noisy_mag")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training step (trainer.py:56-63): fp32 kernels that keep the activations for BPTT
+            if not all(p.requires_grad for p in self.parameters()):
+                raise NotImplementedError("fullsubnet_b200: partially frozen models are not built")
+            return _TrainForward.apply(self, x, *self.parameters())
         device = x.device
         lib = _lib.load()
         with torch.cuda.device(device):
@@ -107,6 +165,38 @@ class Model(BaseModel):
                                              x.data_ptr(), batch_size, num_frames, out.data_ptr(), ws.data_ptr(),
                                              ws_bytes, _lib.stream_ptr(device)))
         return out
+
+    def flat_grad(self):
+        """Makes every ``p.grad`` a view into one persistent flat fp32 buffer (keeping current values) and returns
+        the buffer: one ``all_reduce`` then moves all 20 gradients."""
+        params = list(self.parameters())
+        flat = getattr(self, "_flat", None)
+        ok = flat is not None and flat.device == params[0].device and all(
+            p.grad is not None and p.grad.data_ptr() == flat.data_ptr() + 4 * off
+            for p, off in zip(params, self._flat_offsets))
+        if not ok:
+            flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=params[0].device)
+            offs, off = [], 0
+            for p in params:
+                view = flat[off:off + p.numel()].view_as(p)
+                if p.grad is not None:
+                    view.copy_(p.grad)
+                p.grad = view
+                offs.append(off)
+                off += p.numel()
+            self._flat, self._flat_offsets = flat, offs
+        return flat
+
+    def _new_flat_grads(self, device):
+        """One flat fp32 buffer holding every gradient in parameter order (what the single all-reduce of
+        base_trainer.py:32 / SURVEY 8e moves) and the per-parameter views into it."""
+        params = list(self.named_parameters())
+        flat = torch.empty(sum(p.numel() for _, p in params), dtype=torch.float32, device=device)
+        views, off = {}, 0
+        for k, p in params:
+            views[k] = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        return flat, views
 
     @torch.no_grad()
     def enhance(self, noisy, n_fft=512, hop_length=256, win_length=512, return_crm=False):

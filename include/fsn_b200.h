@@ -228,6 +228,54 @@ float fsn_last_stage_ms(int stage);
  * (bench.py reports it as gpu_launches) */
 int64_t fsn_last_launch_count(void);
 
+/* ------------------------------------------------------------------------------------------
+ * Training step: recipes/dns_interspeech_2020/fullsubnet/trainer.py:56-68, fp32.
+ *   fsn_train_forward   = Model.forward in train mode (model.py:72-136, drop_band on) that keeps the activations
+ *                         back-propagation through time needs in `workspace` (same buffer must be passed to
+ *                         fsn_train_backward, untouched in between)
+ *   fsn_mse_loss        = audio_zen/loss.py:4 (torch.nn.MSELoss) between cIRM [B',F',T,2] (trainer.py:49-54) and
+ *                         cRM [B',2,F',T]; also writes d loss / d cRM when dcrm != NULL.  loss: device scalar.
+ *   fsn_train_backward  = loss.backward() (trainer.py:63): gradients of the 20 parameters, OVERWRITTEN into the
+ *                         buffers of gfb / gsb (same shapes as the parameters)
+ *   fsn_clip_adam       = clip_grad_norm_(max_norm) + Adam step (trainer.py:65-68, train.py:55-59) over a list of
+ *                         tensors, no host synchronisation.  grad_scale multiplies every gradient first (1/world
+ *                         after a sum all-reduce).  norm_out (optional, 2 floats on the device) receives the total
+ *                         norm and the applied coefficient; gradients are left clipped like the reference. */
+typedef struct fsn_seq_grads {
+  float* w_ih[2];
+  float* w_hh[2];
+  float* b_ih[2];
+  float* b_hh[2];
+  float* fc_w;
+  float* fc_b;
+} fsn_seq_grads;
+
+size_t fsn_train_workspace_bytes(const fsn_model_desc* d, int B, int T);
+int fsn_train_forward(const fsn_model_desc* d, const fsn_seq_weights* fb, const fsn_seq_weights* sb,
+                      const float* noisy_mag, int B, int T, float* crm, void* workspace, size_t workspace_bytes,
+                      fsn_stream_t stream);
+int fsn_train_backward(const fsn_model_desc* d, const fsn_seq_weights* fb, const fsn_seq_weights* sb,
+                       const float* dcrm, int B, int T, const fsn_seq_grads* gfb, const fsn_seq_grads* gsb,
+                       void* workspace, size_t workspace_bytes, fsn_stream_t stream);
+
+size_t fsn_mse_loss_scratch_bytes(void);
+int fsn_mse_loss(const float* cirm, const float* crm, int B, int Fsub, int T, float* loss, float* dcrm,
+                 void* scratch, size_t scratch_bytes, fsn_stream_t stream);
+
+#define FSN_MAX_PARAM_TENSORS 64
+typedef struct fsn_param_list {
+  int n;
+  float* param[FSN_MAX_PARAM_TENSORS];
+  float* grad[FSN_MAX_PARAM_TENSORS];
+  float* exp_avg[FSN_MAX_PARAM_TENSORS];
+  float* exp_avg_sq[FSN_MAX_PARAM_TENSORS];
+  int64_t numel[FSN_MAX_PARAM_TENSORS];
+} fsn_param_list;
+
+size_t fsn_clip_adam_scratch_bytes(void);
+int fsn_clip_adam(const fsn_param_list* L, float max_norm, float grad_scale, float lr, float beta1, float beta2,
+                  float eps, int step, float* norm_out, void* scratch, size_t scratch_bytes, fsn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import fullsubnet_oracle as O
-from conftest import rel_max, WB_GAIN
+from conftest import rel_max, rel_l2, WB_GAIN
 
 T = torch.from_numpy
 
@@ -137,3 +137,63 @@ def test_improved_fullsubnet_oracle_matches_reference(golden):
         assert np.abs(wav.numpy() - g[tag + "_wav"]).max() < 2e-6 * max(1.0, np.abs(g[tag + "_wav"]).max()), tag
     with pytest.raises(ValueError):
         IO.freq_unfold(torch.zeros(1, 1, 40, 3), 0, 21, 4, 15)
+
+
+# ------------------------------------------------------------------ training step (A11)
+def test_train_oracle_matches_reference_small(golden):
+    from oracle import train_oracle as TO
+    from oracle.make_golden_train import SMALL
+    g = golden("train_small")
+    sd = O.make_state_dict(seed=7, args=SMALL, sb_fc_gain=8.0)
+    noisy, clean = T(g["noisy"]), T(g["clean"])
+    state = None
+    for it in range(2):
+        r = TO.train_step(noisy, clean, sd, SMALL, state=state, n_fft=64, hop=32, win=64)
+        assert abs(float(r["loss"]) - g["loss"][it]) < 1e-6 * g["loss"][it]
+        assert abs(float(r["gnorm"]) - g["gnorm"][it]) < 1e-5 * g["gnorm"][it]
+        if it == 0:
+            assert rel_max(r["cirm"], g["cirm"]) < 2e-5  # near-0/0 bins of the ratio mask carry rounding noise
+            for k in sd:
+                assert rel_l2(r["grads"][k], g["grad." + k]) < 1e-5, k
+        sd, state = r["sd"], r["state"]
+        for k in sd:
+            assert np.abs(sd[k].numpy() - g[f"p{it}." + k]).max() < 2e-6, (it, k)
+
+
+def test_train_oracle_matches_reference_full(golden):
+    from oracle import train_oracle as TO
+    g = golden("train_full")
+    sd = O.make_state_dict(seed=0, sb_fc_gain=40.0)
+    r = TO.train_step(T(g["noisy"]), T(g["clean"]), sd)
+    assert abs(float(r["loss"]) - g["loss"][0]) < 1e-6 * g["loss"][0]
+    assert abs(float(r["gnorm"]) - g["gnorm"][0]) < 1e-4 * g["gnorm"][0] and float(r["gnorm"]) > 10  # clip active
+    for k in sd:
+        assert rel_l2(r["grads"][k].reshape(-1)[::97], g["gsub." + k]) < 1e-4, k
+        assert np.abs(r["sd"][k].numpy().reshape(-1)[::97] - g["psub." + k]).max() < 2e-6, k
+
+
+def test_manual_bptt_equals_autograd(golden):
+    """The hand-derived backward the CUDA kernels implement (closed-form norm gradient, drop_band row map)."""
+    from oracle import train_oracle as TO
+    from oracle.make_golden_train import SMALL
+    g = golden("train_small")
+    sd = O.make_state_dict(seed=7, args=SMALL, sb_fc_gain=8.0)
+    nm, cirm = TO.targets(T(g["noisy"]), T(g["clean"]), 2, 64, 32, 64)
+    loss, grads, crm = TO.manual_backward(nm, cirm, sd, SMALL)
+    assert abs(float(loss) - g["loss"][0]) < 1e-6 * g["loss"][0]
+    assert np.abs(crm.numpy() - g["crm"]).max() < 1e-5
+    for k in sd:
+        assert rel_l2(grads[k], g["grad." + k]) < 1e-5, k
+    # B = 1 (no drop_band) and G = 1
+    for B, G in ((1, 2), (3, 1)):
+        a = dict(SMALL, num_groups_in_drop_band=G)
+        if B > 1:
+            nm1, cirm1 = TO.targets(T(g["noisy"])[:B], T(g["clean"])[:B], G, 64, 32, 64)
+        else:  # the trainer's drop_band asserts B > G (feature.py:317-319); Model.forward itself accepts B = 1
+            nm1, _, nr, ni = O.stft(T(g["noisy"])[:1], 64, 32, 64)
+            cirm1 = O.build_complex_ideal_ratio_mask(nr, ni, *O.stft(T(g["clean"])[:1], 64, 32, 64)[2:])
+        l0, g0, _ = TO.loss_and_grads(nm1, cirm1, sd, a)
+        l1, g1, _ = TO.manual_backward(nm1, cirm1, sd, a)
+        assert abs(float(l0) - float(l1)) < 1e-6 * float(l0)
+        for k in sd:
+            assert rel_l2(g1[k], g0[k]) < 1e-5, (B, G, k)
