@@ -152,11 +152,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=256, help="clips per GPU (configs[1]: 256)")
     ap.add_argument("--precision", default="auto")
-    ap.add_argument("--model", default="fullsubnet", choices=["fullsubnet", "fast_fullsubnet"],
-                    help="fullsubnet = BASELINE configs[1] (the headline); fast_fullsubnet = configs[3] (use --batch 512)")
+    ap.add_argument("--model", default="fullsubnet", choices=["fullsubnet", "fast_fullsubnet", "fullsubnet_train"],
+                    help="fullsubnet = BASELINE configs[1] (the headline); fast_fullsubnet = configs[3] (use --batch 512); "
+                         "fullsubnet_train = configs[2], the training step (bench_train.py)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.model == "fullsubnet_train":
+        import bench_train
+        return bench_train.main(args)
     if args.impl == "reference":
         return run_reference(args)
 

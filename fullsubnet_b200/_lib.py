@@ -110,6 +110,7 @@ _SIGNATURES = {
     "fsn_clip_adam_scratch_bytes": (_S, []),
     "fsn_clip_adam": (C.c_int, [C.POINTER(ParamList), _F, _F, _F, _F, _F, _F, _I, _P, _P, _S, _P]),
     "fsn_last_launch_count": (C.c_int64, []),
+    "fsn_total_launch_count": (C.c_int64, []),
     "fsn_set_profiling": (C.c_int, [_I]),
     "fsn_last_stage_ms": (C.c_float, [_I]),
 }

@@ -11,6 +11,7 @@ namespace fsn {
 
 void set_error(const char* fmt, ...);
 int64_t& launch_counter();
+int64_t& total_launch_counter();
 
 inline int check_cuda(cudaError_t e, const char* what) {
   if (e != cudaSuccess) {
@@ -23,6 +24,7 @@ inline int check_cuda(cudaError_t e, const char* what) {
 #define FSN_CHECK_LAUNCH(what)                                   \
   do {                                                           \
     ::fsn::launch_counter()++;                                   \
+    ::fsn::total_launch_counter()++;                             \
     int _rc = ::fsn::check_cuda(cudaGetLastError(), what);       \
     if (_rc) return _rc;                                         \
   } while (0)

@@ -20,6 +20,8 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 int64_t& launch_counter() { return g_launches; }
+static int64_t g_total_launches = 0;
+int64_t& total_launch_counter() { return g_total_launches; }
 
 // opt-in stage timing (bench.py): 5 events bracket the 4 stages
 static thread_local bool g_prof = false;
@@ -201,6 +203,7 @@ using namespace fsn;
 extern "C" int fsn_version(void) { return 100; }
 extern "C" const char* fsn_last_error(void) { return g_err; }
 extern "C" int64_t fsn_last_launch_count(void) { return g_launches; }
+extern "C" int64_t fsn_total_launch_count(void) { return g_total_launches; }
 extern "C" int fsn_set_profiling(int enable) { g_prof = enable != 0; return FSN_OK; }
 extern "C" float fsn_last_stage_ms(int stage) {
   if (stage < 0 || stage > 3 || !g_ev_valid[stage] || !g_ev_valid[stage + 1]) return -1.0f;

@@ -227,6 +227,8 @@ float fsn_last_stage_ms(int stage);
 /* number of kernel launches issued by the last fsn_model_forward / fsn_enhance on this thread
  * (bench.py reports it as gpu_launches) */
 int64_t fsn_last_launch_count(void);
+/* kernels launched by this library since it was loaded (never reset): difference two readings */
+int64_t fsn_total_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Training step: recipes/dns_interspeech_2020/fullsubnet/trainer.py:56-68, fp32.
