@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libfsn_b200.so")
 
 FSN_OK, FSN_ERR_SHAPE, FSN_ERR_UNSUPPORTED, FSN_ERR_CUDA, FSN_ERR_WORKSPACE = 0, 1, 2, 3, 4
 ACT = {None: 0, False: 0, "": 0, "ReLU": 1, "Tanh": 2, "ReLU6": 3}
-PREC = {"fp32": 0, "f16_tc": 1}
+PREC = {"fp32": 0, "f16_tc": 1, "tf32_tc": 2}
 
 
 class ModelDesc(C.Structure):
@@ -109,6 +109,7 @@ _SIGNATURES = {
     "fsn_mse_loss": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _P, _S, _P]),
     "fsn_clip_adam_scratch_bytes": (_S, []),
     "fsn_clip_adam": (C.c_int, [C.POINTER(ParamList), _F, _F, _F, _F, _F, _F, _I, _P, _P, _S, _P]),
+    "fsn_debug_tgemm": (C.c_int, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _P, _L, _P]),
     "fsn_last_launch_count": (C.c_int64, []),
     "fsn_total_launch_count": (C.c_int64, []),
     "fsn_set_profiling": (C.c_int, [_I]),

@@ -47,6 +47,11 @@ struct StepParams {
 
 int lstm_step_launch(const StepParams& p, int mode, cudaStream_t st);
 
+// tf32 tcgen05 GEMM (fsn_tgemm.cu): C[M,N] (+)= A[M,K] B[N,K]^T, fp32 row-major operands with 16-byte aligned rows
+bool tgemm_supported(const float* A, size_t lda, const float* Bm, size_t ldb, int K);
+int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float* C, size_t ldc, int M, int N, int K,
+                 bool accumulate, float* scratch, size_t scratch_floats, cudaStream_t st);
+
 // shapes of one Model.forward call (fsn_model.cu)
 struct Dims {
   int B, T, Tp, F, Fsub, G, R, Ksb;

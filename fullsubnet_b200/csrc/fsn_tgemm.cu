@@ -1,0 +1,245 @@
+// tf32 tensor-core GEMM for the training path:  C[M,N] (+)= A[M,K] * B[N,K]^T, all fp32 in global memory, both
+// operands K-contiguous ("K-major"), tcgen05.mma kind::tf32 with the accumulator in TMEM.
+//
+// One CTA = one 128 x BN output tile (BN = 128 or 256), optional split-K slice (blockIdx.z).
+//   warps 0-3  producers: every thread owns one row of the A tile and one (BN=128) or two (BN=256) rows of the B
+//              tile; per k-step (32 floats = one 128-byte swizzle row) it issues 16-byte cp.async copies straight
+//              into the 128B-swizzled K-major layout the UMMA descriptors expect (chunk ^= row & 7); rows / k beyond
+//              the matrix are zero-filled.  cp.async.wait_group + fence.proxy.async + mbarrier arrive hand the stage
+//              to the tensor core.  After the last k-step the same warps drain TMEM (warp w <-> lanes 32w..32w+31).
+//   warp 4     MMA issue (converged warp, one elected lane): 4 MMAs (K = 8) per stage, tcgen05.commit frees it.
+// No operand conversion pass: the tensor core reads fp32 bits as tf32 (10-bit mantissa, truncation).
+#include "fsn_internal.cuh"
+#include "fsn_tc_ptx.cuh"
+
+namespace fsn {
+namespace tg {
+
+using namespace ptx;
+
+constexpr int BM = 128, BK = 32;
+constexpr int A_BYTES = BM * BK * 4;  // 16 KB
+
+template <int BN> struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  // BN = 128: 3 stages (96 KB) so two CTAs share an SM - one drains its accumulator while the other runs its main loop
+  static constexpr int STAGES = (BN == 128) ? 3 : 4;
+  static constexpr int LAG = (BN == 128) ? 2 : 3;      // cp.async groups in flight per thread
+  static constexpr int MIN_CTAS = (BN == 128) ? 2 : 1;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct Bars {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t acc_full;
+  uint32_t tmem_base;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(160, Cfg<BN>::MIN_CTAS)
+tgemm_kernel(const float* __restrict__ A, size_t lda, const float* __restrict__ Bm, size_t ldb, float* __restrict__ C,
+             size_t ldc, int M, int N, int K, int k_per_split, int accumulate, size_t split_stride) {
+  using CF = Cfg<BN>;
+  constexpr int STAGES = CF::STAGES, LAG = CF::LAG;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Bars& bars = *reinterpret_cast<Bars*>(smem + STAGES * CF::STAGE_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int kb = blockIdx.z * k_per_split;
+  const int ke = (kb + k_per_split < K) ? kb + k_per_split : K;
+  const int nk = (ke - kb + BK - 1) / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.full[s], 128); mbar_init(&bars.empty[s], 1); }
+    mbar_init(&bars.acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
+                 "n"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars.tmem_base;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers
+    // lane -> (16-byte chunk c = tid & 7 of a 128-byte row, rows (tid >> 3) + 16 j): 8 lanes read one full line
+    const int c = tid & 7, rbase = tid >> 3;
+    const uint32_t sw = (uint32_t)(rbase & 7);  // (rbase + 16 j) & 7
+    const uint32_t dst_off = (uint32_t)((rbase >> 3) * 1024 + (rbase & 7) * 128) + (((uint32_t)c ^ sw) << 4);
+    const uint32_t smem_base = smem_u32(smem);
+    const float* a_row = A + (size_t)(m0 + rbase) * lda + c * 4;
+    const float* b_row = Bm + (size_t)(n0 + rbase) * ldb + c * 4;
+    for (int i = 0; i < nk + LAG; ++i) {
+      if (i < nk) {
+        const int s = i % STAGES;
+        if (i >= STAGES) mbar_wait<false>(&bars.empty[s], (uint32_t)(((i / STAGES) - 1) & 1));
+        const int k0 = kb + i * BK;
+        int rem = (ke - (k0 + c * 4)) * 4;
+        rem = rem < 0 ? 0 : (rem > 16 ? 16 : rem);
+        const uint32_t sa = smem_base + s * CF::STAGE_BYTES + dst_off;
+#pragma unroll
+        for (int j = 0; j < BM / 16; ++j) {
+          const uint32_t nb = (m0 + rbase + 16 * j < M) ? (uint32_t)rem : 0u;
+          cp_async16_zfill(sa + j * 2048, nb ? (const void*)(a_row + (size_t)(16 * j) * lda + k0) : (const void*)A, nb);
+        }
+#pragma unroll
+        for (int j = 0; j < BN / 16; ++j) {
+          const uint32_t nb = (n0 + rbase + 16 * j < N) ? (uint32_t)rem : 0u;
+          cp_async16_zfill(sa + A_BYTES + j * 2048, nb ? (const void*)(b_row + (size_t)(16 * j) * ldb + k0) : (const void*)Bm,
+                           nb);
+        }
+      }
+      cp_async_commit();
+      if (i >= LAG) {
+        cp_async_wait<LAG>();   // group i-LAG (k-step i-LAG) has landed
+        fence_proxy_async();    // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&bars.full[(i - LAG) % STAGES]);
+      }
+    }
+    // ------------------------------------------------------------------ epilogue: TMEM -> smem -> global
+    // (all MMAs have completed, so the stage buffers are free: each warp transposes 32x32 blocks through its own
+    //  padded slab and writes full 128-byte rows)
+    mbar_wait<true>(&bars.acc_full, 0);
+    tc_fence_after();
+    const int lane = tid & 31;
+    float* slab = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+    float* cbase = C + (size_t)blockIdx.z * split_stride;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int cb = 0; cb < BN / 32; ++cb) {
+      if (n0 + cb * 32 >= N) break;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v[8];
+        tc_ld8(taddr + cb * 32 + q * 8, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) slab[lane * 33 + q * 8 + j] = v[j];
+      }
+      __syncwarp();
+      const int col = n0 + cb * 32 + lane;
+      if (col < N) {
+        for (int r = 0; r < 32; ++r) {
+          const int grow = m0 + warp * 32 + r;
+          if (grow >= M) break;
+          float* d = cbase + (size_t)grow * ldc + col;
+          const float val = slab[r * 33 + lane];
+          *d = accumulate ? *d + val : val;
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issue
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t smem_base = smem_u32(smem);
+    for (int i = 0; i < nk; ++i) {
+      const int s = i % STAGES;
+      mbar_wait<false>(&bars.full[s], (uint32_t)((i / STAGES) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_base + s * CF::STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BK / 8; ++kk)
+          tc_mma1_tf32(tmem_base, desc_sw128(sa + kk * 32), desc_sw128(sb + kk * 32), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        tc_commit1(&bars.empty[s]);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) tc_commit1(&bars.acc_full);
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+  }
+}
+
+}  // namespace tg
+
+// fixed-order sum of split-K slabs (fsn_train.cu)
+int splitk_reduce_launch(const float* part, int S, int M, int N, float* C, size_t ldc, bool accumulate, cudaStream_t st);
+
+bool tgemm_supported(const float* A, size_t lda, const float* Bm, size_t ldb, int K) {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, major = 0, smem = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    ok = (major == 10 && smem >= tg::Cfg<128>::SMEM && getenv("FSN_NO_TGEMM") == nullptr) ? 1 : 0;
+  }
+  return ok == 1 && K >= 4 && (lda & 3) == 0 && (ldb & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(Bm) & 15) == 0;
+}
+
+// C[M,N] (+)= A[M,K] B[N,K]^T; `scratch` (>= scratch_floats) enables split-K for long-K / few-tile problems
+int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float* C, size_t ldc, int M, int N, int K,
+                 bool accumulate, float* scratch, size_t scratch_floats, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return FSN_OK;
+  FSN_REQUIRE(tgemm_supported(A, lda, Bm, ldb, K), FSN_ERR_UNSUPPORTED, "tgemm: operands must be 16-byte aligned rows");
+  static const int force_bn = getenv("FSN_TGEMM_BN") ? atoi(getenv("FSN_TGEMM_BN")) : 0;
+  const int BN = force_bn ? force_bn : ((N >= 256 && N % 256 == 0) ? 256 : 128);
+  const int tiles = cdiv(M, tg::BM) * cdiv(N, BN);
+  int S = 1;
+  if (scratch && K >= 8192 && tiles < 296) {
+    // minimise waves(tiles * S) / S over the SM slots (1 or 2 resident CTAs per SM), slices of >= 2048 k
+    const int slots = 148 * (BN == 128 ? 2 : 1);
+    double best = 1e30;
+    for (int s = 1; s <= 64 && s <= cdiv(K, 2048); ++s) {
+      if ((size_t)s * M * N > scratch_floats) break;
+      const double cost = (double)cdiv(tiles * s, slots) / s + 1e-4 * s;
+      if (cost < best) { best = cost; S = s; }
+    }
+  }
+  const int kps = cdiv(cdiv(K, S), tg::BK) * tg::BK;
+  S = cdiv(K, kps);
+  dim3 grid(cdiv(M, tg::BM), cdiv(N, BN), S);
+  float* dst = S > 1 ? scratch : C;
+  const size_t ldd = S > 1 ? (size_t)N : ldc;
+  const int acc = (S > 1) ? 0 : (accumulate ? 1 : 0);
+  int rc;
+  if (BN == 256) {
+    static bool attr = false;
+    if (!attr) {
+      if ((rc = check_cuda(cudaFuncSetAttribute(tg::tgemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                tg::Cfg<256>::SMEM), "tgemm smem attr")))
+        return rc;
+      attr = true;
+    }
+    tg::tgemm_kernel<256><<<grid, 160, tg::Cfg<256>::SMEM, st>>>(A, lda, Bm, ldb, dst, ldd, M, N, K, kps, acc,
+                                                                 (size_t)M * N);
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      if ((rc = check_cuda(cudaFuncSetAttribute(tg::tgemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                tg::Cfg<128>::SMEM), "tgemm smem attr")))
+        return rc;
+      attr = true;
+    }
+    tg::tgemm_kernel<128><<<grid, 160, tg::Cfg<128>::SMEM, st>>>(A, lda, Bm, ldb, dst, ldd, M, N, K, kps, acc,
+                                                                 (size_t)M * N);
+  }
+  FSN_CHECK_LAUNCH("tgemm_kernel");
+  if (S > 1) return splitk_reduce_launch(scratch, S, M, N, C, ldc, accumulate, st);
+  return FSN_OK;
+}
+
+}  // namespace fsn
+
+// debug / unit-test entry point (tests/test_gpu_train.py): C[M,N] (+)= A[M,K] B[N,K]^T on the tcgen05 path
+extern "C" int fsn_debug_tgemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M,
+                               int N, int K, int accumulate, float* scratch, int64_t scratch_floats,
+                               fsn_stream_t stream) {
+  return fsn::tgemm_launch(A, (size_t)lda, B, (size_t)ldb, C, (size_t)ldc, M, N, K, accumulate != 0, scratch,
+                           (size_t)scratch_floats, (cudaStream_t)stream);
+}

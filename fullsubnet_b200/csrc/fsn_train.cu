@@ -95,6 +95,13 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int S, int 
   *dst = accumulate ? *dst + s : s;
 }
 
+int splitk_reduce_launch(const float* part, int S, int M, int N, float* C, size_t ldc, bool accumulate, cudaStream_t st) {
+  const size_t n = (size_t)M * N;
+  splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, S, M, N, C, ldc, accumulate ? 1 : 0);
+  FSN_CHECK_LAUNCH("splitk_reduce_kernel");
+  return FSN_OK;
+}
+
 static const size_t SPLITK_SCRATCH_FLOATS = (size_t)16 << 20;  // 64 MB
 
 static int sgemm_launch(bool ta, const float* A, size_t lda, const float* Bm, size_t ldb, float* C, size_t ldc, int M,
@@ -250,6 +257,51 @@ __global__ void train_gather_kernel(const float* __restrict__ raw, const float* 
   }
 }
 
+// LSTM cell of one step from pre-activation gate sums (tensor-core path): G_t [R,4H] holds x W_ih^T + h W_hh^T and is
+// overwritten with the post-activation gates (i,f,g,o); writes c_t and h_t
+__global__ void lstm_cell_fwd_kernel(float* __restrict__ G, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                                     const float* __restrict__ C_prev, float* __restrict__ C_out, float* __restrict__ H_out,
+                                     int R, int H) {
+  const size_t n = (size_t)R * H;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int u = (int)(idx % H);
+    const size_t r = idx / H;
+    float* g = G + r * 4 * H + u;
+    const float si = sigmoidf_(g[0] + b_ih[u] + b_hh[u]);
+    const float sf = sigmoidf_(g[H] + b_ih[H + u] + b_hh[H + u]);
+    const float tg = tanhf(g[2 * H] + b_ih[2 * H + u] + b_hh[2 * H + u]);
+    const float so = sigmoidf_(g[3 * H] + b_ih[3 * H + u] + b_hh[3 * H + u]);
+    const float c = sf * (C_prev ? C_prev[idx] : 0.f) + si * tg;
+    g[0] = si; g[H] = sf; g[2 * H] = tg; g[3 * H] = so;
+    C_out[idx] = c;
+    H_out[idx] = so * tanhf(c);
+  }
+}
+
+// out[c, r] = in[r, c]   (in [rows, cols] row-major -> out [cols, rows]); operands of the K-major tensor-core GEMM
+__global__ void transpose_kernel(const float* __restrict__ in, size_t rows, int cols, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const size_t r0 = (size_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const size_t r = r0 + i;
+    const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i;
+    const size_t r = r0 + threadIdx.x;
+    if (c < cols && r < rows) out[(size_t)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+static int transpose_launch(const float* in, size_t rows, int cols, float* out, cudaStream_t st) {
+  dim3 grid((unsigned)((rows + 31) / 32), cdiv(cols, 32));
+  transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(in, rows, cols, out);
+  FSN_CHECK_LAUNCH("transpose_kernel");
+  return FSN_OK;
+}
+
 // ------------------------------------------------------------------------------------------ backward kernels
 // dout[t,r,o] = dcrm[b',o,f',t-la] (0 for the look-ahead steps)  (model.py:129-135 backwards)
 __global__ void train_dout_kernel(const float* __restrict__ dcrm, float* __restrict__ dout, int R, int Fsub, int T,
@@ -360,6 +412,9 @@ struct TrainWs {
   float *xsb, *dxsb, *dout, *dz, *dfh1;
   float *dh_rec[2], *dc[2], *dh_mid, *dot;
   float *splitk, *colsum;
+  // FSN_PREC_TF32_TC: transposed weights ([H,4H], [K0,4H]) and transposed dG / layer inputs for the weight gradients
+  float *sb_whhT[2], *sb_wihT[2], *fb_whhT[2], *fb_wihT1;
+  float *gT, *xT;
   size_t bytes;
 };
 
@@ -393,6 +448,18 @@ static void carve_train(const fsn_model_desc* d, const Dims& m, void* base, Trai
   w.splitk = c.take(SPLITK_SCRATCH_FLOATS);
   const size_t maxcols = 4 * (Hf > Hs ? Hf : Hs) > F ? 4 * (Hf > Hs ? Hf : Hs) : F;
   w.colsum = c.take((size_t)COLSUM_MAX_S * maxcols);
+  if (d->precision == FSN_PREC_TF32_TC) {
+    for (int l = 0; l < 2; ++l) {
+      w.sb_whhT[l] = c.take(Hs * 4 * Hs);
+      w.sb_wihT[l] = c.take((l == 0 ? (size_t)m.Ksb : Hs) * 4 * Hs);
+      w.fb_whhT[l] = c.take(Hf * 4 * Hf);
+    }
+    w.fb_wihT1 = c.take(Hf * 4 * Hf);
+    const size_t g_sb = Tp * R * 4 * Hs, g_fb = Tp * B * 4 * Hf;
+    w.gT = c.take(g_sb > g_fb ? g_sb : g_fb);
+    size_t x_sb = Tp * R * (Hs > (size_t)m.Ksb ? Hs : (size_t)m.Ksb), x_fb = Tp * B * (Hf > F ? Hf : F);
+    w.xT = c.take(x_sb > x_fb ? x_sb : x_fb);
+  }
   w.bytes = c.off;
 }
 
@@ -422,11 +489,40 @@ static int layer_forward_save(const fsn_seq_weights* w, int l, const float* X, i
   return FSN_OK;
 }
 
+// tensor-core variant: input projection of ALL steps as one GEMM into the gate buffer, then per step
+// G_t += h_{t-1} W_hh^T (tcgen05 tf32) and the fused cell kernel
+static int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R, int K0, int H, int Tp,
+                                 const LayerSave& s, cudaStream_t st) {
+  int rc;
+  const int rows = Tp * R;
+  if (tgemm_supported(X, K0, w->w_ih[l], K0, K0)) {
+    if ((rc = tgemm_launch(X, K0, w->w_ih[l], K0, s.G, 4 * H, rows, 4 * H, K0, false, nullptr, 0, st))) return rc;
+  } else if ((rc = fc_gemm_launch(X, w->w_ih[l], nullptr, s.G, rows, K0, 4 * H, FSN_ACT_NONE, st))) {
+    return rc;  // rows of X not 16-byte aligned (K0 % 4 != 0): fp32 SIMT GEMM
+  }
+  const size_t n = (size_t)R * H;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  for (int t = 0; t < Tp; ++t) {
+    float* Gt = s.G + (size_t)t * R * 4 * H;
+    if (t > 0)
+      if ((rc = tgemm_launch(s.H + (size_t)(t - 1) * R * H, H, w->w_hh[l], H, Gt, 4 * H, R, 4 * H, H, true, nullptr, 0, st)))
+        return rc;
+    lstm_cell_fwd_kernel<<<blocks, 256, 0, st>>>(Gt, w->b_ih[l], w->b_hh[l], t > 0 ? s.C + (size_t)(t - 1) * R * H : nullptr,
+                                                 s.C + (size_t)t * R * H, s.H + (size_t)t * R * H, R, H);
+    FSN_CHECK_LAUNCH("lstm_cell_fwd_kernel");
+  }
+  return FSN_OK;
+}
+
+static bool tc_layer_ok(const fsn_model_desc* d, int H) { return d->precision == FSN_PREC_TF32_TC && (H & 3) == 0; }
+
 struct LayerBwd {
   const float *w_ih, *w_hh;
   LayerSave s;
   int R, K0, H;
   float *dh_rec, *dc;
+  const float *w_hhT, *w_ihT;  // tensor-core path: [H,4H] / [K0,4H] transposed copies (else nullptr)
 };
 
 // step t of one layer: pointwise gate gradients, then dh_rec = dG W_hh and (optionally) dx = dG W_ih
@@ -448,12 +544,16 @@ static int layer_bwd_step(const LayerBwd& L, int t, int Tp, const float* dh_abov
   lstm_bwd_point_kernel<<<blocks, 256, 0, st>>>(p);
   FSN_CHECK_LAUNCH("lstm_bwd_point_kernel");
   int rc;
-  if (t > 0)
-    if ((rc = sgemm_launch(false, p.G, 4 * L.H, L.w_hh, L.H, L.dh_rec, L.H, L.R, L.H, 4 * L.H, false, nullptr, st)))
-      return rc;
-  if (dx)
-    if ((rc = sgemm_launch(false, p.G, 4 * L.H, L.w_ih, L.K0, dx, L.K0, L.R, L.K0, 4 * L.H, false, nullptr, st)))
-      return rc;
+  if (t > 0) {
+    if (L.w_hhT) rc = tgemm_launch(p.G, 4 * L.H, L.w_hhT, 4 * L.H, L.dh_rec, L.H, L.R, L.H, 4 * L.H, false, nullptr, 0, st);
+    else         rc = sgemm_launch(false, p.G, 4 * L.H, L.w_hh, L.H, L.dh_rec, L.H, L.R, L.H, 4 * L.H, false, nullptr, st);
+    if (rc) return rc;
+  }
+  if (dx) {
+    if (L.w_ihT) rc = tgemm_launch(p.G, 4 * L.H, L.w_ihT, 4 * L.H, dx, L.K0, L.R, L.K0, 4 * L.H, false, nullptr, 0, st);
+    else         rc = sgemm_launch(false, p.G, 4 * L.H, L.w_ih, L.K0, dx, L.K0, L.R, L.K0, 4 * L.H, false, nullptr, st);
+    if (rc) return rc;
+  }
   return FSN_OK;
 }
 
@@ -463,6 +563,22 @@ static int layer_weight_grads(const LayerBwd& L, int Tp, const float* X, float* 
   const int H4 = 4 * L.H;
   const int rows = Tp * L.R;
   int rc;
+  if (L.w_hhT && (L.R & 3) == 0) {
+    // tensor-core path: K-major operands = transposed copies dG^T [4H, rows], X^T [K0, rows], H^T [H, rows]
+    if ((rc = transpose_launch(L.s.G, (size_t)rows, H4, w.gT, st))) return rc;
+    if ((rc = transpose_launch(X, (size_t)rows, L.K0, w.xT, st))) return rc;
+    if ((rc = tgemm_launch(w.gT, rows, w.xT, rows, g_w_ih, L.K0, H4, L.K0, rows, false, w.splitk, SPLITK_SCRATCH_FLOATS, st)))
+      return rc;
+    if (Tp > 1) {
+      if ((rc = transpose_launch(L.s.H, (size_t)rows, L.H, w.xT, st))) return rc;
+      if ((rc = tgemm_launch(w.gT + L.R, rows, w.xT, rows, g_w_hh, L.H, H4, L.H, rows - L.R, false, w.splitk,
+                             SPLITK_SCRATCH_FLOATS, st)))
+        return rc;
+    } else if ((rc = check_cuda(cudaMemsetAsync(g_w_hh, 0, (size_t)H4 * L.H * sizeof(float), st), "memset"))) {
+      return rc;
+    }
+    return colsum_launch(L.s.G, (size_t)rows, H4, H4, g_b_ih, g_b_hh, w.colsum, st);
+  }
   if ((rc = sgemm_launch(true, L.s.G, H4, X, L.K0, g_w_ih, L.K0, H4, L.K0, rows, false, w.splitk, st))) return rc;
   if (Tp > 1) {
     if ((rc = sgemm_launch(true, L.s.G + (size_t)L.R * H4, H4, L.s.H, L.H, g_w_hh, L.H, H4, L.H, rows - L.R, false,
@@ -508,8 +624,14 @@ extern "C" int fsn_train_forward(const fsn_model_desc* d, const fsn_seq_weights*
                                                                                      F, T, Tp);
   FSN_CHECK_LAUNCH("train_transpose_kernel");
   // full-band stack + Linear/activation (model.py:92-95)
-  if ((rc = layer_forward_save(fb, 0, w.xfb, B, F, Hf, Tp, w.fb[0], st))) return rc;
-  if ((rc = layer_forward_save(fb, 1, w.fb[0].H, B, Hf, Hf, Tp, w.fb[1], st))) return rc;
+  const bool tc_fb = tc_layer_ok(d, Hf), tc_sb = tc_layer_ok(d, Hs);
+  if (tc_fb) {
+    if ((rc = layer_forward_save_tc(fb, 0, w.xfb, B, F, Hf, Tp, w.fb[0], st))) return rc;
+    if ((rc = layer_forward_save_tc(fb, 1, w.fb[0].H, B, Hf, Hf, Tp, w.fb[1], st))) return rc;
+  } else {
+    if ((rc = layer_forward_save(fb, 0, w.xfb, B, F, Hf, Tp, w.fb[0], st))) return rc;
+    if ((rc = layer_forward_save(fb, 1, w.fb[0].H, B, Hf, Hf, Tp, w.fb[1], st))) return rc;
+  }
   if ((rc = fc_gemm_launch(w.fb[1].H, fb->fc_w, fb->fc_b, w.fbz, Tp * B, Hf, F, d->fb_activation, st))) return rc;
   // second norm in closed form (model.py:110-111)
   train_tm_stats_kernel<<<B, 256, 0, st>>>(w.fbz, B, F, Tp, d->fb_num_neighbors, w.sums_fb);
@@ -520,8 +642,13 @@ extern "C" int fsn_train_forward(const fsn_model_desc* d, const fsn_seq_weights*
   train_gather_kernel<<<148 * 8, 256, 0, st>>>(w.raw, w.fbz, w.inv2, w.xsb, map, Tp, m.R, d->sb_num_neighbors,
                                                d->fb_num_neighbors);
   FSN_CHECK_LAUNCH("train_gather_kernel");
-  if ((rc = layer_forward_save(sb, 0, w.xsb, m.R, m.Ksb, Hs, Tp, w.sb[0], st))) return rc;
-  if ((rc = layer_forward_save(sb, 1, w.sb[0].H, m.R, Hs, Hs, Tp, w.sb[1], st))) return rc;
+  if (tc_sb) {
+    if ((rc = layer_forward_save_tc(sb, 0, w.xsb, m.R, m.Ksb, Hs, Tp, w.sb[0], st))) return rc;
+    if ((rc = layer_forward_save_tc(sb, 1, w.sb[0].H, m.R, Hs, Hs, Tp, w.sb[1], st))) return rc;
+  } else {
+    if ((rc = layer_forward_save(sb, 0, w.xsb, m.R, m.Ksb, Hs, Tp, w.sb[0], st))) return rc;
+    if ((rc = layer_forward_save(sb, 1, w.sb[0].H, m.R, Hs, Hs, Tp, w.sb[1], st))) return rc;
+  }
   for (int t = d->look_ahead; t < Tp; ++t)
     if ((rc = sb_fc_step_launch(w.sb[1].H + (size_t)t * m.R * Hs, m.R, Hs, sb->fc_w, sb->fc_b, 2, d->sb_activation, crm,
                                 m.Fsub, m.T, t - d->look_ahead, st)))
@@ -552,8 +679,22 @@ extern "C" int fsn_train_backward(const fsn_model_desc* d, const fsn_seq_weights
   if ((rc = sgemm_launch(true, w.dout, 2, w.sb[1].H, Hs, gsb->fc_w, Hs, 2, Hs, Tp * R, false, w.splitk, st))) return rc;
   if ((rc = colsum_launch(w.dout, (size_t)Tp * R, 2, 2, gsb->fc_b, nullptr, w.colsum, st))) return rc;
   // ---- sub-band stack, both layers one step apart
-  LayerBwd s1{sb->w_ih[1], sb->w_hh[1], w.sb[1], R, Hs, Hs, w.dh_rec[1], w.dc[1]};
-  LayerBwd s0{sb->w_ih[0], sb->w_hh[0], w.sb[0], R, K, Hs, w.dh_rec[0], w.dc[0]};
+  const bool tc_fb = tc_layer_ok(d, Hf), tc_sb = tc_layer_ok(d, Hs);
+  if (tc_sb) {
+    for (int l = 0; l < 2; ++l) {
+      if ((rc = transpose_launch(sb->w_hh[l], (size_t)4 * Hs, Hs, w.sb_whhT[l], st))) return rc;
+      if ((rc = transpose_launch(sb->w_ih[l], (size_t)4 * Hs, l == 0 ? K : Hs, w.sb_wihT[l], st))) return rc;
+    }
+  }
+  if (tc_fb) {
+    for (int l = 0; l < 2; ++l)
+      if ((rc = transpose_launch(fb->w_hh[l], (size_t)4 * Hf, Hf, w.fb_whhT[l], st))) return rc;
+    if ((rc = transpose_launch(fb->w_ih[1], (size_t)4 * Hf, Hf, w.fb_wihT1, st))) return rc;
+  }
+  LayerBwd s1{sb->w_ih[1], sb->w_hh[1], w.sb[1], R, Hs, Hs, w.dh_rec[1], w.dc[1], tc_sb ? w.sb_whhT[1] : nullptr,
+              tc_sb ? w.sb_wihT[1] : nullptr};
+  LayerBwd s0{sb->w_ih[0], sb->w_hh[0], w.sb[0], R, K, Hs, w.dh_rec[0], w.dc[0], tc_sb ? w.sb_whhT[0] : nullptr,
+              tc_sb ? w.sb_wihT[0] : nullptr};
   for (int t = Tp - 1; t >= 0; --t) {
     if ((rc = layer_bwd_step(s1, t, Tp, nullptr, w.dout + (size_t)t * R * 2, sb->fc_w, 2, w.dh_mid, st))) return rc;
     if ((rc = layer_bwd_step(s0, t, Tp, w.dh_mid, nullptr, nullptr, 0, w.dxsb + (size_t)t * R * K, st))) return rc;
@@ -571,8 +712,9 @@ extern "C" int fsn_train_backward(const fsn_model_desc* d, const fsn_seq_weights
   if ((rc = colsum_launch(w.dz, (size_t)Tp * B, F, F, gfb->fc_b, nullptr, w.colsum, st))) return rc;
   if ((rc = sgemm_launch(false, w.dz, F, fb->fc_w, Hf, w.dfh1, Hf, Tp * B, Hf, F, false, nullptr, st))) return rc;
   // ---- full-band stack
-  LayerBwd f1{fb->w_ih[1], fb->w_hh[1], w.fb[1], B, Hf, Hf, w.dh_rec[1], w.dc[1]};
-  LayerBwd f0{fb->w_ih[0], fb->w_hh[0], w.fb[0], B, F, Hf, w.dh_rec[0], w.dc[0]};
+  LayerBwd f1{fb->w_ih[1], fb->w_hh[1], w.fb[1], B, Hf, Hf, w.dh_rec[1], w.dc[1], tc_fb ? w.fb_whhT[1] : nullptr,
+              tc_fb ? w.fb_wihT1 : nullptr};
+  LayerBwd f0{fb->w_ih[0], fb->w_hh[0], w.fb[0], B, F, Hf, w.dh_rec[0], w.dc[0], tc_fb ? w.fb_whhT[0] : nullptr, nullptr};
   for (int t = Tp - 1; t >= 0; --t) {
     if ((rc = layer_bwd_step(f1, t, Tp, w.dfh1 + (size_t)t * B * Hf, nullptr, nullptr, 0, w.dh_mid, st))) return rc;
     if ((rc = layer_bwd_step(f0, t, Tp, w.dh_mid, nullptr, nullptr, 0, nullptr, st))) return rc;

@@ -79,8 +79,8 @@ class Model(BaseModel):
         ok = _lib.load().fsn_fast_packed_bytes(C.byref(d)) > 0
         if self.precision == "auto":
             return "f16_tc" if ok else "fp32"
-        if self.precision not in _lib.PREC:
-            raise ValueError(f"precision must be one of {list(_lib.PREC)} or 'auto'")
+        if self.precision not in ("fp32", "f16_tc"):
+            raise ValueError("precision must be 'fp32', 'f16_tc' or 'auto'")
         if self.precision == "f16_tc" and not ok:
             raise NotImplementedError("f16_tc needs bottleneck_hidden_size = 384, 2 layers and input width <= 32")
         return self.precision

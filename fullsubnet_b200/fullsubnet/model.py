@@ -38,7 +38,7 @@ class _TrainForward(torch.autograd.Function):
         device = x.device
         lib = _lib.load()
         with torch.cuda.device(device):
-            desc = model._desc("fp32", int(model.num_groups_in_drop_band))
+            desc = model._desc(model._resolve_train_precision(), int(model.num_groups_in_drop_band))
             fb_w, sb_w = model.fb_model.weight_struct(), model.sb_model.weight_struct()
             n = lib.fsn_train_workspace_bytes(C.byref(desc), B, T)
             if n == 0:
@@ -97,6 +97,9 @@ class Model(BaseModel):
         self.num_groups_in_drop_band = num_groups_in_drop_band
         # arithmetic of the sub-band stack: "fp32" or "f16_tc" (tcgen05, fp16 operands / fp32 accumulate)
         self.precision = precision or os.environ.get("FSN_PRECISION", "auto")
+        # arithmetic of the training step's GEMMs: "fp32" (FMA) or "tf32_tc" (tcgen05 kind::tf32); the reference
+        # trains under fp16 autocast (trainer.py:56), so both are at least its precision
+        self.train_precision = os.environ.get("FSN_TRAIN_PRECISION", "auto")
         self._packed = None
         self._packed_key = None
         if weight_init:
@@ -105,11 +108,19 @@ class Model(BaseModel):
     # ---------------------------------------------------------------- C-ABI plumbing
     def _resolve_precision(self) -> str:
         if self.precision != "auto":
-            if self.precision not in _lib.PREC:
-                raise ValueError(f"precision must be one of {list(_lib.PREC)} or 'auto'")
+            if self.precision not in ("fp32", "f16_tc"):
+                raise ValueError("precision must be 'fp32', 'f16_tc' or 'auto'")
             return self.precision
         d = self._desc("f16_tc", 1)
         return "f16_tc" if _lib.load().fsn_sb_packed_bytes(C.byref(d)) > 0 else "fp32"
+
+    def _resolve_train_precision(self) -> str:
+        if self.train_precision == "auto":
+            ok = self.fb_model.hidden_size % 4 == 0 and self.sb_model.hidden_size % 4 == 0
+            return "tf32_tc" if ok else "fp32"
+        if self.train_precision not in ("fp32", "tf32_tc"):
+            raise ValueError("train_precision must be 'fp32', 'tf32_tc' or 'auto'")
+        return self.train_precision
 
     def _desc(self, precision: str, num_groups: int) -> "_lib.ModelDesc":
         return _lib.ModelDesc(

@@ -41,9 +41,12 @@ enum { FSN_ACT_NONE = 0, FSN_ACT_RELU = 1, FSN_ACT_TANH = 2, FSN_ACT_RELU6 = 3 }
 enum { FSN_NORM_OFFLINE_LAPLACE = 0 };
 /* arithmetic of the sub-band LSTM stack (99 % of the FLOPs):
  *   FSN_PREC_FP32     - fp32 FMA everywhere (bit-for-bit class of the reference CPU path, ~1e-6)
+ *   FSN_PREC_TF32_TC  - training step only (fsn_train_*): every GEMM of the forward, of back-propagation through
+ *                       time and of the weight gradients on tcgen05 kind::tf32 (fp32 data read as tf32, fp32
+ *                       accumulate in TMEM); gate / cell arithmetic and all reductions stay fp32
  *   FSN_PREC_F16_TC   - fp16 operands (11-bit significand, like TF32) x fp32 accumulate on the
  *                       tcgen05 tensor cores, fp32 cell state; cRM within 1e-3 rel (tests) */
-enum { FSN_PREC_FP32 = 0, FSN_PREC_F16_TC = 1 };
+enum { FSN_PREC_FP32 = 0, FSN_PREC_F16_TC = 1, FSN_PREC_TF32_TC = 2 };
 
 int fsn_version(void);
 const char* fsn_last_error(void);
@@ -277,6 +280,11 @@ typedef struct fsn_param_list {
 size_t fsn_clip_adam_scratch_bytes(void);
 int fsn_clip_adam(const fsn_param_list* L, float max_norm, float grad_scale, float lr, float beta1, float beta2,
                   float eps, int step, float* norm_out, void* scratch, size_t scratch_bytes, fsn_stream_t stream);
+
+/* unit-test hook for the tf32 tcgen05 GEMM of the training path: C[M,N] (+)= A[M,K] B[N,K]^T, fp32 row-major
+ * operands with 16-byte aligned rows; scratch (optional) enables split-K */
+int fsn_debug_tgemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
+                    int K, int accumulate, float* scratch, int64_t scratch_floats, fsn_stream_t stream);
 
 #ifdef __cplusplus
 }

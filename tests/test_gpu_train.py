@@ -10,7 +10,8 @@ from conftest import rel_l2, rel_max
 
 pytestmark = pytest.mark.gpu
 
-GRAD_TOL = 2e-4
+GRAD_TOL = {"fp32": 2e-4, "tf32_tc": 1e-2}   # tf32_tc: the north-star gate; measured ~1e-3
+LOSS_TOL = {"fp32": 1e-5, "tf32_tc": 1e-3}
 SUB = 97  # oracle/make_golden_train.py:SUBSAMPLE
 
 
@@ -29,10 +30,11 @@ def small_args():
     return dict(SMALL)
 
 
-def build(args, sd, dev):
+def build(args, sd, dev, prec="fp32"):
     from fullsubnet_b200.fullsubnet.model import Model
     m = Model(**args)
     m.load_state_dict(sd, strict=True)
+    m.train_precision = prec
     return m.to(dev).train()
 
 
@@ -50,14 +52,14 @@ def reference_like_step(model, noisy, clean, n_fft, hop, loss_fn):
     return loss, cIRM, cRM
 
 
-@pytest.mark.parametrize("fused", [True, False])
-def test_small_model_two_steps_match_reference(golden, dev, fused):
+@pytest.mark.parametrize("fused,prec", [(True, "fp32"), (False, "fp32"), (True, "tf32_tc")])
+def test_small_model_two_steps_match_reference(golden, dev, fused, prec):
     from fullsubnet_b200.loss import mse_loss
     from fullsubnet_b200.optim import FusedClipAdam
     from oracle import fullsubnet_oracle as O
     g = golden("train_small")
     args = small_args()
-    m = build(args, O.make_state_dict(seed=7, args=args, sb_fc_gain=8.0), dev)
+    m = build(args, O.make_state_dict(seed=7, args=args, sb_fc_gain=8.0), dev, prec)
     noisy, clean = T(g["noisy"], dev), T(g["clean"], dev)
     if fused:
         opt, loss_fn = FusedClipAdam(m.parameters(), lr=1e-3, betas=(0.9, 0.999), max_norm=10.0), mse_loss()
@@ -66,16 +68,19 @@ def test_small_model_two_steps_match_reference(golden, dev, fused):
     for it in range(2):
         opt.zero_grad()
         loss, cirm, crm = reference_like_step(m, noisy, clean, 64, 32, loss_fn)
-        assert abs(float(loss) - g["loss"][it]) <= 1e-5 * abs(g["loss"][it]), (float(loss), g["loss"][it])
+        assert abs(float(loss.detach()) - g["loss"][it]) <= LOSS_TOL[prec] * abs(g["loss"][it]), (float(loss), g["loss"][it])
         if it == 0:
             assert rel_max(cirm.cpu(), g["cirm"]) < 5e-5  # near-0/0 bins of the ratio mask carry rounding noise
-            assert rel_max(crm.detach().cpu(), g["crm"]) < 1e-5
+            assert rel_max(crm.detach().cpu(), g["crm"]) < (1e-5 if prec == "fp32" else 1e-3)
             worst = 0.0
             for k, p in m.named_parameters():
                 e = rel_l2(p.grad.cpu(), g["grad." + k])
                 worst = max(worst, e)
-                assert e < GRAD_TOL, (k, e)
-            print(f"small model ({'fused' if fused else 'torch'} optimiser): worst gradient rel-L2 {worst:.2e}")
+                assert e < GRAD_TOL[prec], (k, e)
+            print(f"small model ({'fused' if fused else 'torch'} optimiser, {prec}): worst gradient rel-L2 {worst:.2e}")
+        if prec != "fp32":
+            opt.step()  # Adam's first steps are +-lr whatever the magnitude: parameters are compared for fp32 only
+            continue
         if fused:
             opt.step()
             assert abs(float(opt.last_norm[0]) - g["gnorm"][it]) < 1e-4 * g["gnorm"][it]
@@ -87,27 +92,31 @@ def test_small_model_two_steps_match_reference(golden, dev, fused):
             assert np.abs(v.cpu().numpy() - g[f"p{it}." + k]).max() < 2e-5, (it, k)
 
 
-def test_full_size_model_step_matches_reference(golden, dev):
+@pytest.mark.parametrize("prec", ["fp32", "tf32_tc"])
+def test_full_size_model_step_matches_reference(golden, dev, prec):
     from fullsubnet_b200.loss import mse_loss
     from fullsubnet_b200.optim import FusedClipAdam
     from oracle import fullsubnet_oracle as O
     g = golden("train_full")
     args = dict(O.DEFAULT_MODEL_ARGS, weight_init=False)
-    m = build(args, O.make_state_dict(seed=0, args=args, sb_fc_gain=40.0), dev)
+    m = build(args, O.make_state_dict(seed=0, args=args, sb_fc_gain=40.0), dev, prec)
     opt = FusedClipAdam(m.parameters(), lr=1e-3, max_norm=10.0)
     loss, _, _ = reference_like_step(m, T(g["noisy"], dev), T(g["clean"], dev), 512, 256, mse_loss())
-    assert abs(float(loss) - g["loss"][0]) <= 1e-5 * g["loss"][0]
+    assert abs(float(loss.detach()) - g["loss"][0]) <= LOSS_TOL[prec] * g["loss"][0], float(loss)
     worst = 0.0
     for k, p in m.named_parameters():
         got = p.grad.cpu().numpy().reshape(-1)
         e = rel_l2(got[::SUB], g["gsub." + k])
         n = abs(np.sqrt((got.astype(np.float64) ** 2).sum()) - g["gl2." + k]) / g["gl2." + k]
         worst = max(worst, e, n)
-        assert e < GRAD_TOL and n < GRAD_TOL, (k, e, n)
-    print(f"full-size model: worst gradient error {worst:.2e}, loss {float(loss):.6f}")
+        assert e < GRAD_TOL[prec] and n < GRAD_TOL[prec], (k, e, n)
+    print(f"full-size model ({prec}): worst gradient error {worst:.2e}, loss {float(loss):.6f} (ref {g['loss'][0]:.6f})")
     opt.step()  # norm 19.9 > 10: the clip is active
-    assert abs(float(opt.last_norm[0]) - g["gnorm"][0]) < 1e-4 * g["gnorm"][0]
-    assert abs(float(opt.last_norm[1]) - 10.0 / (g["gnorm"][0] + 1e-6)) < 1e-4
+    tol = 1e-4 if prec == "fp32" else 5e-3
+    assert abs(float(opt.last_norm[0]) - g["gnorm"][0]) < tol * g["gnorm"][0]
+    assert abs(float(opt.last_norm[1]) - 10.0 / (g["gnorm"][0] + 1e-6)) < tol
+    if prec != "fp32":
+        return
     for k, v in m.state_dict().items():
         assert np.abs(v.cpu().numpy().reshape(-1)[::SUB] - g["psub." + k]).max() < 2e-5, k
 
@@ -176,3 +185,26 @@ def test_trainer_step_and_checkpoint_roundtrip(golden, dev, tmp_path):
     assert tr2.start_epoch == 3
     for k, v in m2.state_dict().items():
         assert torch.equal(v.cpu(), m.state_dict()[k].cpu())
+
+
+def test_tf32_tensor_core_gemm_matches_truncated_reference(dev):
+    """fsn_debug_tgemm: C (+)= A B^T on tcgen05 kind::tf32 == fp64 GEMM of the tf32-truncated operands."""
+    from fullsubnet_b200 import _lib
+    lib = _lib.load()
+
+    def trunc(x):
+        return (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    torch.manual_seed(1)
+    for (M, N, K, ld, acc, split) in ((128, 128, 32, 32, 0, 0), (200, 130, 100, 104, 0, 0), (256, 384, 1536, 1536, 1, 0),
+                                     (300, 512, 70, 72, 1, 0), (1536, 64, 40000, 40000, 0, 1)):
+        A, B = torch.randn(M, ld, device=dev), torch.randn(N, ld, device=dev)
+        C0 = torch.randn(M, N + 8, device=dev)
+        Cc = C0.clone()
+        scratch = torch.empty(16 << 20, device=dev) if split else None
+        _lib.check(lib.fsn_debug_tgemm(A.data_ptr(), ld, B.data_ptr(), ld, Cc.data_ptr(), N + 8, M, N, K, acc,
+                                       _lib.ptr(scratch), scratch.numel() if split else 0,
+                                       torch.cuda.current_stream().cuda_stream))
+        ref = trunc(A[:, :K]).double() @ trunc(B[:, :K]).double().T + (C0[:, :N].double() if acc else 0)
+        err = ((Cc[:, :N].double() - ref).abs().max() / ref.abs().max()).item()
+        assert err < 1e-4, (M, N, K, err)
+        assert torch.equal(Cc[:, N:], C0[:, N:])
