@@ -9,6 +9,10 @@
 //              to the tensor core.  After the last k-step the same warps drain TMEM (warp w <-> lanes 32w..32w+31).
 //   warp 4     MMA issue (converged warp, one elected lane): 4 MMAs (K = 8) per stage, tcgen05.commit frees it.
 // No operand conversion pass: the tensor core reads fp32 bits as tf32 (10-bit mantissa, truncation).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <string.h>
+
 #include "fsn_internal.cuh"
 #include "fsn_tc_ptx.cuh"
 
@@ -36,6 +40,70 @@ struct Bars {
   uint64_t acc_full;
   uint32_t tmem_base;
 };
+
+// drain the accumulator: TMEM -> registers -> per-warp padded smem slab -> full 128-byte rows in global memory
+// (all MMAs have completed, so the stage buffers are free)
+template <int BN>
+__device__ __forceinline__ void epilogue(uint8_t* smem, Bars& bars, uint32_t tmem_base, float* __restrict__ C, size_t ldc,
+                                         int M, int N, int m0, int n0, int accumulate, size_t split_stride) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  mbar_wait<true>(&bars.acc_full, 0);
+  tc_fence_after();
+  float* slab = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+  float* cbase = C + (size_t)blockIdx.z * split_stride;
+  const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  for (int cb = 0; cb < BN / 32; ++cb) {
+    if (n0 + cb * 32 >= N) break;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v[8];
+      tc_ld8(taddr + cb * 32 + q * 8, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) slab[lane * 33 + q * 8 + j] = v[j];
+    }
+    __syncwarp();
+    const int col = n0 + cb * 32 + lane;
+    if (col < N) {
+      const int row0 = m0 + warp * 32;
+#pragma unroll
+      for (int r8 = 0; r8 < 32; r8 += 8) {
+        float old[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)  // batch the read-modify-write loads: one memory round trip per 8 rows
+          old[j] = (accumulate && row0 + r8 + j < M) ? cbase[(size_t)(row0 + r8 + j) * ldc + col] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (row0 + r8 + j < M) cbase[(size_t)(row0 + r8 + j) * ldc + col] = old[j] + slab[(r8 + j) * 33 + lane];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int BN>
+__device__ __forceinline__ void mma_loop(uint8_t* smem, Bars& bars, uint32_t tmem_base, int nk) {
+  using CF = Cfg<BN>;
+  constexpr int STAGES = CF::STAGES;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  const uint32_t smem_base = smem_u32(smem);
+  for (int i = 0; i < nk; ++i) {
+    const int s = i % STAGES;
+    mbar_wait<false>(&bars.full[s], (uint32_t)((i / STAGES) & 1));
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t sa = smem_base + s * CF::STAGE_BYTES;
+      const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < BK / 8; ++kk)
+        tc_mma1_tf32(tmem_base, desc_sw128(sa + kk * 32), desc_sw128(sb + kk * 32), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+      tc_commit1(&bars.empty[s]);
+    }
+    __syncwarp();
+  }
+  if (elect_one()) tc_commit1(&bars.acc_full);
+  __syncwarp();
+}
 
 template <int BN>
 __global__ void __launch_bounds__(160, Cfg<BN>::MIN_CTAS)
@@ -103,58 +171,65 @@ tgemm_kernel(const float* __restrict__ A, size_t lda, const float* __restrict__ 
         mbar_arrive(&bars.full[(i - LAG) % STAGES]);
       }
     }
-    // ------------------------------------------------------------------ epilogue: TMEM -> smem -> global
-    // (all MMAs have completed, so the stage buffers are free: each warp transposes 32x32 blocks through its own
-    //  padded slab and writes full 128-byte rows)
-    mbar_wait<true>(&bars.acc_full, 0);
-    tc_fence_after();
-    const int lane = tid & 31;
-    float* slab = reinterpret_cast<float*>(smem) + warp * (32 * 33);
-    float* cbase = C + (size_t)blockIdx.z * split_stride;
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int cb = 0; cb < BN / 32; ++cb) {
-      if (n0 + cb * 32 >= N) break;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float v[8];
-        tc_ld8(taddr + cb * 32 + q * 8, v);
-        tc_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) slab[lane * 33 + q * 8 + j] = v[j];
-      }
-      __syncwarp();
-      const int col = n0 + cb * 32 + lane;
-      if (col < N) {
-        for (int r = 0; r < 32; ++r) {
-          const int grow = m0 + warp * 32 + r;
-          if (grow >= M) break;
-          float* d = cbase + (size_t)grow * ldc + col;
-          const float val = slab[r * 33 + lane];
-          *d = accumulate ? *d + val : val;
-        }
-      }
-      __syncwarp();
-    }
+    epilogue<BN>(smem, bars, tmem_base, C, ldc, M, N, m0, n0, accumulate, split_stride);
   } else {
-    // ------------------------------------------------------------------ MMA issue
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    const uint32_t smem_base = smem_u32(smem);
-    for (int i = 0; i < nk; ++i) {
-      const int s = i % STAGES;
-      mbar_wait<false>(&bars.full[s], (uint32_t)((i / STAGES) & 1));
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_base + s * CF::STAGE_BYTES;
-        const uint32_t sb = sa + A_BYTES;
-#pragma unroll
-        for (int kk = 0; kk < BK / 8; ++kk)
-          tc_mma1_tf32(tmem_base, desc_sw128(sa + kk * 32), desc_sw128(sb + kk * 32), idesc, (i > 0 || kk > 0) ? 1u : 0u);
-        tc_commit1(&bars.empty[s]);
+    mma_loop<BN>(smem, bars, tmem_base, nk);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+  }
+}
+
+// Same tile, operands fed by TMA: one elected lane issues two tiled loads per stage (128B hardware swizzle, rows / k
+// beyond the matrix zero-filled by the tensor map), the full barrier counts the transaction bytes.
+template <int BN>
+__global__ void __launch_bounds__(160, Cfg<BN>::MIN_CTAS)
+tgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
+                 size_t ldc, int M, int N, int K, int k_per_split, int accumulate, size_t split_stride) {
+  using CF = Cfg<BN>;
+  constexpr int STAGES = CF::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Bars& bars = *reinterpret_cast<Bars*>(smem + STAGES * CF::STAGE_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int kb = blockIdx.z * k_per_split;
+  const int ke = (kb + k_per_split < K) ? kb + k_per_split : K;
+  const int nk = (ke - kb + BK - 1) / BK;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
+    mbar_init(&bars.acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
+                 "n"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars.tmem_base;
+  if (warp < 4) {
+    if (warp == 0) {
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % STAGES;
+        if (i >= STAGES) mbar_wait<false>(&bars.empty[s], (uint32_t)(((i / STAGES) - 1) & 1));
+        if (elect_one()) {
+          uint8_t* sa = smem + s * CF::STAGE_BYTES;
+          mbar_expect_tx(&bars.full[s], CF::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, kb + i * BK, m0, &bars.full[s]);
+          tma_load_2d(sa + A_BYTES, &tmB, kb + i * BK, n0, &bars.full[s]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
-    if (elect_one()) tc_commit1(&bars.acc_full);
-    __syncwarp();
+    epilogue<BN>(smem, bars, tmem_base, C, ldc, M, N, m0, n0, accumulate, split_stride);
+  } else {
+    mma_loop<BN>(smem, bars, tmem_base, nk);
   }
   tc_fence_before();
   __syncthreads();
@@ -165,6 +240,36 @@ tgemm_kernel(const float* __restrict__ A, size_t lda, const float* __restrict__ 
 }
 
 }  // namespace tg
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+static PFN_cuTensorMapEncodeTiled_v12000 tmap_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (getenv("FSN_TGEMM_FEED") == nullptr || strcmp(getenv("FSN_TGEMM_FEED"), "cpasync") != 0)
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+          q == cudaDriverEntryPointSuccess)
+        fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+// fp32 [rows, K] row-major (ld floats) -> boxes of box_rows x 32 floats, 128B swizzle, zero fill outside
+static bool make_tmap(CUtensorMap* m, const float* base, int K, int rows, size_t ld, int box_rows) {
+  PFN_cuTensorMapEncodeTiled_v12000 fn = tmap_encoder();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)tg::BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+         CUDA_SUCCESS;
+}
 
 // fixed-order sum of split-K slabs (fsn_train.cu)
 int splitk_reduce_launch(const float* part, int S, int M, int N, float* C, size_t ldc, bool accumulate, cudaStream_t st);
@@ -208,6 +313,26 @@ int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float*
   const size_t ldd = S > 1 ? (size_t)N : ldc;
   const int acc = (S > 1) ? 0 : (accumulate ? 1 : 0);
   int rc;
+  CUtensorMap tmA, tmB;
+  if (make_tmap(&tmA, A, K, M, lda, tg::BM) && make_tmap(&tmB, Bm, K, N, ldb, BN)) {
+    static bool attr = false;
+    if (!attr) {
+      if ((rc = check_cuda(cudaFuncSetAttribute(tg::tgemm_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                tg::Cfg<256>::SMEM), "tgemm smem attr")))
+        return rc;
+      if ((rc = check_cuda(cudaFuncSetAttribute(tg::tgemm_tma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                tg::Cfg<128>::SMEM), "tgemm smem attr")))
+        return rc;
+      attr = true;
+    }
+    if (BN == 256)
+      tg::tgemm_tma_kernel<256><<<grid, 160, tg::Cfg<256>::SMEM, st>>>(tmA, tmB, dst, ldd, M, N, K, kps, acc, (size_t)M * N);
+    else
+      tg::tgemm_tma_kernel<128><<<grid, 160, tg::Cfg<128>::SMEM, st>>>(tmA, tmB, dst, ldd, M, N, K, kps, acc, (size_t)M * N);
+    FSN_CHECK_LAUNCH("tgemm_tma_kernel");
+    if (S > 1) return splitk_reduce_launch(scratch, S, M, N, C, ldc, accumulate, st);
+    return FSN_OK;
+  }
   if (BN == 256) {
     static bool attr = false;
     if (!attr) {

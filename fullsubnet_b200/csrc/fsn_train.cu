@@ -257,20 +257,23 @@ __global__ void train_gather_kernel(const float* __restrict__ raw, const float* 
   }
 }
 
-// LSTM cell of one step from pre-activation gate sums (tensor-core path): G_t [R,4H] holds x W_ih^T + h W_hh^T and is
-// overwritten with the post-activation gates (i,f,g,o); writes c_t and h_t
-__global__ void lstm_cell_fwd_kernel(float* __restrict__ G, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
-                                     const float* __restrict__ C_prev, float* __restrict__ C_out, float* __restrict__ H_out,
-                                     int R, int H) {
+// LSTM cell of one step (tensor-core path): G_t [R,4H] holds x_t W_ih^T (all steps from one hoisted GEMM), rec the
+// recurrent product of this step; G_t is overwritten with the post-activation gates (i,f,g,o); writes c_t and h_t
+__global__ void lstm_cell_fwd_kernel(float* __restrict__ G, const float* __restrict__ rec, const float* __restrict__ b_ih,
+                                     const float* __restrict__ b_hh, const float* __restrict__ C_prev,
+                                     float* __restrict__ C_out, float* __restrict__ H_out, int R, int H) {
   const size_t n = (size_t)R * H;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
     const int u = (int)(idx % H);
     const size_t r = idx / H;
     float* g = G + r * 4 * H + u;
-    const float si = sigmoidf_(g[0] + b_ih[u] + b_hh[u]);
-    const float sf = sigmoidf_(g[H] + b_ih[H + u] + b_hh[H + u]);
-    const float tg = tanhf(g[2 * H] + b_ih[2 * H + u] + b_hh[2 * H + u]);
-    const float so = sigmoidf_(g[3 * H] + b_ih[3 * H + u] + b_hh[3 * H + u]);
+    float z[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      z[q] = g[q * H] + b_ih[q * H + u] + b_hh[q * H + u];
+      if (rec) z[q] += rec[r * 4 * H + q * H + u];  // h_{t-1} W_hh^T of this step
+    }
+    const float si = sigmoidf_(z[0]), sf = sigmoidf_(z[1]), tg = tanhf(z[2]), so = sigmoidf_(z[3]);
     const float c = sf * (C_prev ? C_prev[idx] : 0.f) + si * tg;
     g[0] = si; g[H] = sf; g[2 * H] = tg; g[3 * H] = so;
     C_out[idx] = c;
@@ -414,7 +417,7 @@ struct TrainWs {
   float *splitk, *colsum;
   // FSN_PREC_TF32_TC: transposed weights ([H,4H], [K0,4H]) and transposed dG / layer inputs for the weight gradients
   float *sb_whhT[2], *sb_wihT[2], *fb_whhT[2], *fb_wihT1;
-  float *gT, *xT;
+  float *gT, *xT, *rec;
   size_t bytes;
 };
 
@@ -459,6 +462,7 @@ static void carve_train(const fsn_model_desc* d, const Dims& m, void* base, Trai
     w.gT = c.take(g_sb > g_fb ? g_sb : g_fb);
     size_t x_sb = Tp * R * (Hs > (size_t)m.Ksb ? Hs : (size_t)m.Ksb), x_fb = Tp * B * (Hf > F ? Hf : F);
     w.xT = c.take(x_sb > x_fb ? x_sb : x_fb);
+    w.rec = c.take(4 * RH);
   }
   w.bytes = c.off;
 }
@@ -492,7 +496,7 @@ static int layer_forward_save(const fsn_seq_weights* w, int l, const float* X, i
 // tensor-core variant: input projection of ALL steps as one GEMM into the gate buffer, then per step
 // G_t += h_{t-1} W_hh^T (tcgen05 tf32) and the fused cell kernel
 static int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R, int K0, int H, int Tp,
-                                 const LayerSave& s, cudaStream_t st) {
+                                 const LayerSave& s, float* rec, cudaStream_t st) {
   int rc;
   const int rows = Tp * R;
   if (tgemm_supported(X, K0, w->w_ih[l], K0, K0)) {
@@ -506,9 +510,10 @@ static int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X
   for (int t = 0; t < Tp; ++t) {
     float* Gt = s.G + (size_t)t * R * 4 * H;
     if (t > 0)
-      if ((rc = tgemm_launch(s.H + (size_t)(t - 1) * R * H, H, w->w_hh[l], H, Gt, 4 * H, R, 4 * H, H, true, nullptr, 0, st)))
+      if ((rc = tgemm_launch(s.H + (size_t)(t - 1) * R * H, H, w->w_hh[l], H, rec, 4 * H, R, 4 * H, H, false, nullptr, 0, st)))
         return rc;
-    lstm_cell_fwd_kernel<<<blocks, 256, 0, st>>>(Gt, w->b_ih[l], w->b_hh[l], t > 0 ? s.C + (size_t)(t - 1) * R * H : nullptr,
+    lstm_cell_fwd_kernel<<<blocks, 256, 0, st>>>(Gt, t > 0 ? rec : nullptr, w->b_ih[l], w->b_hh[l],
+                                                 t > 0 ? s.C + (size_t)(t - 1) * R * H : nullptr,
                                                  s.C + (size_t)t * R * H, s.H + (size_t)t * R * H, R, H);
     FSN_CHECK_LAUNCH("lstm_cell_fwd_kernel");
   }
@@ -626,8 +631,8 @@ extern "C" int fsn_train_forward(const fsn_model_desc* d, const fsn_seq_weights*
   // full-band stack + Linear/activation (model.py:92-95)
   const bool tc_fb = tc_layer_ok(d, Hf), tc_sb = tc_layer_ok(d, Hs);
   if (tc_fb) {
-    if ((rc = layer_forward_save_tc(fb, 0, w.xfb, B, F, Hf, Tp, w.fb[0], st))) return rc;
-    if ((rc = layer_forward_save_tc(fb, 1, w.fb[0].H, B, Hf, Hf, Tp, w.fb[1], st))) return rc;
+    if ((rc = layer_forward_save_tc(fb, 0, w.xfb, B, F, Hf, Tp, w.fb[0], w.rec, st))) return rc;
+    if ((rc = layer_forward_save_tc(fb, 1, w.fb[0].H, B, Hf, Hf, Tp, w.fb[1], w.rec, st))) return rc;
   } else {
     if ((rc = layer_forward_save(fb, 0, w.xfb, B, F, Hf, Tp, w.fb[0], st))) return rc;
     if ((rc = layer_forward_save(fb, 1, w.fb[0].H, B, Hf, Hf, Tp, w.fb[1], st))) return rc;
@@ -643,8 +648,8 @@ extern "C" int fsn_train_forward(const fsn_model_desc* d, const fsn_seq_weights*
                                                d->fb_num_neighbors);
   FSN_CHECK_LAUNCH("train_gather_kernel");
   if (tc_sb) {
-    if ((rc = layer_forward_save_tc(sb, 0, w.xsb, m.R, m.Ksb, Hs, Tp, w.sb[0], st))) return rc;
-    if ((rc = layer_forward_save_tc(sb, 1, w.sb[0].H, m.R, Hs, Hs, Tp, w.sb[1], st))) return rc;
+    if ((rc = layer_forward_save_tc(sb, 0, w.xsb, m.R, m.Ksb, Hs, Tp, w.sb[0], w.rec, st))) return rc;
+    if ((rc = layer_forward_save_tc(sb, 1, w.sb[0].H, m.R, Hs, Hs, Tp, w.sb[1], w.rec, st))) return rc;
   } else {
     if ((rc = layer_forward_save(sb, 0, w.xsb, m.R, m.Ksb, Hs, Tp, w.sb[0], st))) return rc;
     if ((rc = layer_forward_save(sb, 1, w.sb[0].H, m.R, Hs, Hs, Tp, w.sb[1], st))) return rc;
