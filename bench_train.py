@@ -149,22 +149,33 @@ def main(args):
     flops = 3.0 * B * (T + 2) * FLOP_FWD_PER_FRAME_STEP  # forward + 2x for backward (dX and dW)
     achieved = flops / (ms_step * 1e-3) / 1e12
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    precision = model._resolve_train_precision()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if precision == "tf32_tc" and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("tgemm_tma_kernel", {}).get("dram_bytes_per_launch")
     line = {
         "metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "rtf_x": value / (SR / HOP),
+        "vs_baseline": None, "dtype": "tf32xf32acc" if precision == "tf32_tc" else "f32", "data": "synthetic",
+        "rtf_x": value / (SR / HOP),
         "config": {"workload": f"fullsubnet training step, batch={B} x 3 s 16 kHz synthetic clips per GPU, cIRM MSE "
                                "loss, drop_band G=2, clip 10 + Adam 1e-3 (BASELINE configs[2])",
-                   "clips_per_gpu": B, "frames_per_clip": T, "precision": "fp32",
+                   "clips_per_gpu": B, "frames_per_clip": T, "precision": precision,
                    "l2": "256 MiB flush write between timed iterations",
                    "parallelism": f"dp{world}: one all-reduce of the 22.55 MB flat gradient buffer per step"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 2 * B * L * 4,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clocks,
-        "roofline": {"kernel": "whole training step (fp32 SIMT GEMMs: LSTM steps, BPTT, weight gradients)",
+        "roofline": {"kernel": "whole training step; dominant kernel tgemm_tma_kernel (tcgen05 kind::tf32, 69 % of the "
+                               "step: hoisted input projections, recurrent GEMMs, BPTT, weight gradients)"
+                               if precision == "tf32_tc" else "whole training step (fp32 FMA GEMMs)",
                      "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved / peak_tf, "traffic": None, "peak_source": f"{peak_kind} bf16_tflops_sustained",
-                     "flops_per_launch": flops, "ms_per_launch": ms_step},
+                     "frac": achieved / peak_tf, "traffic": traffic,
+                     "peak_source": f"{peak_kind} bf16_tflops_sustained (the dense tf32 rate is half of it)",
+                     "flops_per_launch": flops, "ms_per_launch": ms_step,
+                     "note": "achieved = algorithmic FLOPs of the whole step (3 x forward) / step time; traffic = DRAM "
+                             "bytes of one BPTT-step GEMM launch (profiles/traffic.json)"},
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         cores = pick_cpu_threads()

@@ -124,3 +124,33 @@ def test_improved_fullsubnet_state_dict_contract():
             m.eval()(torch.zeros(1, 2000))  # no CPU path
     with pytest.raises(NotImplementedError):
         Model(norm_type="cumulative_laplace_norm")
+
+
+def test_training_host_objects_without_gpu():
+    """Optimiser state is interchangeable with torch.optim.Adam; loss / optimiser / train forward refuse CPU tensors."""
+    from fullsubnet_b200.fullsubnet.model import Model
+    from fullsubnet_b200.loss import mse_loss, MSELoss
+    from fullsubnet_b200.optim import FusedClipAdam
+    from fullsubnet_b200.trainer import Trainer  # noqa: F401  (importable without CUDA)
+    m = Model(num_freqs=9, look_ahead=1, sequence_model="LSTM", fb_num_neighbors=0, sb_num_neighbors=2,
+              fb_output_activate_function="ReLU", sb_output_activate_function=False, fb_model_hidden_size=8,
+              sb_model_hidden_size=4, weight_init=False)
+    assert mse_loss is MSELoss
+    opt = FusedClipAdam(m.parameters(), lr=1e-3, max_norm=10.0)
+    ref = torch.optim.Adam(m.parameters(), lr=1e-3)
+    assert set(opt.state_dict()["param_groups"][0]) >= {"lr", "betas", "eps", "weight_decay", "amsgrad", "params"}
+    for p in m.parameters():
+        p.grad = torch.ones_like(p)
+    ref.step()
+    opt.load_state_dict(ref.state_dict())  # torch -> fused
+    assert int(opt.state[next(iter(m.parameters()))]["step"]) == 1
+    with pytest.raises(RuntimeError):
+        opt.step()  # no CPU path
+    with pytest.raises(RuntimeError):
+        mse_loss()(torch.zeros(1, 2, 3, 2), torch.zeros(1, 2, 3, 2))
+    with pytest.raises(RuntimeError):
+        m.train()(torch.zeros(3, 1, 9, 5))
+    assert m._resolve_train_precision() == "tf32_tc"
+    m.train_precision = "bf16"
+    with pytest.raises(ValueError):
+        m._resolve_train_precision()

@@ -37,3 +37,32 @@ def _worker(rank, world, port, n):
 def test_two_rank_gloo_sharded_enhance():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_worker, args=(2, port, 5), nprocs=2, join=True)
+
+
+# ------------------------------------------------------------------ training: one all-reduce over the flat gradient buffer
+def _grad_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fullsubnet_b200.fullsubnet.model import Model
+    torch.manual_seed(0)  # identical replicas
+    m = Model(num_freqs=9, look_ahead=1, sequence_model="LSTM", fb_num_neighbors=0, sb_num_neighbors=2,
+              fb_output_activate_function="ReLU", sb_output_activate_function=False, fb_model_hidden_size=8,
+              sb_model_hidden_size=4, weight_init=False)
+    for i, p in enumerate(m.parameters()):  # rank-dependent gradients, as after a local backward
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    flat = m.flat_grad()
+    assert flat.numel() == sum(p.numel() for p in m.parameters())
+    assert all(p.grad.data_ptr() == flat.data_ptr() + 4 * off for p, off in zip(m.parameters(), m._flat_offsets))
+    dist.all_reduce(flat)  # the single collective of the step; the 1/world mean is folded into the optimiser
+    for i, p in enumerate(m.parameters()):
+        assert torch.equal(p.grad, torch.full_like(p, 3.0 * (i + 1)))  # (1 + 2) * (i + 1): views saw the reduction
+    assert m.flat_grad().data_ptr() == flat.data_ptr()  # second call keeps the buffer
+    m.zero_grad(set_to_none=False)
+    assert float(flat.abs().sum()) == 0.0
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_flat_gradient_allreduce():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_grad_worker, args=(2, port), nprocs=2, join=True)
