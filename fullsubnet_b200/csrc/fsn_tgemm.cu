@@ -28,7 +28,8 @@ template <int BN> struct Cfg {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // BN = 128: 3 stages (96 KB) so two CTAs share an SM - one drains its accumulator while the other runs its main loop
-  static constexpr int STAGES = (BN == 128) ? 3 : 4;
+  static constexpr int STAGES = (BN == 128) ? 3 : (BN == 256 ? 4 : 3);
+  static constexpr int TMEM_COLS = (BN <= 128) ? 128 : (BN <= 256 ? 256 : 512);
   static constexpr int LAG = (BN == 128) ? 2 : 3;      // cp.async groups in flight per thread
   static constexpr int MIN_CTAS = (BN == 128) ? 2 : 1;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -85,7 +86,10 @@ template <int BN>
 __device__ __forceinline__ void mma_loop(uint8_t* smem, Bars& bars, uint32_t tmem_base, int nk) {
   using CF = Cfg<BN>;
   constexpr int STAGES = CF::STAGES;
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  constexpr int N0 = BN > 256 ? 256 : BN, N1 = BN - N0;  // one MMA covers at most 256 columns
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N0 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((N1 > 0 ? N1 : 8) >> 3) << 17) |
+                          ((uint32_t)(BM >> 4) << 24);
   const uint32_t smem_base = smem_u32(smem);
   for (int i = 0; i < nk; ++i) {
     const int s = i % STAGES;
@@ -95,8 +99,12 @@ __device__ __forceinline__ void mma_loop(uint8_t* smem, Bars& bars, uint32_t tme
       const uint32_t sa = smem_base + s * CF::STAGE_BYTES;
       const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-      for (int kk = 0; kk < BK / 8; ++kk)
+      for (int kk = 0; kk < BK / 8; ++kk) {
         tc_mma1_tf32(tmem_base, desc_sw128(sa + kk * 32), desc_sw128(sb + kk * 32), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        if (N1 > 0)  // columns 256.. of the tile: B rows 256.. start 256 * 128 bytes further
+          tc_mma1_tf32(tmem_base + 256, desc_sw128(sa + kk * 32), desc_sw128(sb + 256 * 128 + kk * 32), idesc1,
+                       (i > 0 || kk > 0) ? 1u : 0u);
+      }
       tc_commit1(&bars.empty[s]);
     }
     __syncwarp();
@@ -187,8 +195,9 @@ tgemm_kernel(const float* __restrict__ A, size_t lda, const float* __restrict__ 
 // beyond the matrix zero-filled by the tensor map), the full barrier counts the transaction bytes.
 template <int BN>
 __global__ void __launch_bounds__(160, Cfg<BN>::MIN_CTAS)
-tgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
-                 size_t ldc, int M, int N, int K, int k_per_split, int accumulate, size_t split_stride) {
+tgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmB2, float* __restrict__ C, size_t ldc, int M, int N, int K,
+                 int k_per_split, int accumulate, size_t split_stride) {
   using CF = Cfg<BN>;
   constexpr int STAGES = CF::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -206,7 +215,7 @@ tgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
-                 "n"(BN));
+                 "n"(CF::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -223,6 +232,7 @@ tgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_expect_tx(&bars.full[s], CF::STAGE_BYTES);
           tma_load_2d(sa, &tmA, kb + i * BK, m0, &bars.full[s]);
           tma_load_2d(sa + A_BYTES, &tmB, kb + i * BK, n0, &bars.full[s]);
+          if (BN > 256) tma_load_2d(sa + A_BYTES + 256 * 128, &tmB2, kb + i * BK, n0 + 256, &bars.full[s]);
         }
         __syncwarp();
       }
@@ -235,7 +245,7 @@ tgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(CF::TMEM_COLS));
   }
 }
 
@@ -293,12 +303,15 @@ int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float*
   if (M <= 0 || N <= 0 || K <= 0) return FSN_OK;
   FSN_REQUIRE(tgemm_supported(A, lda, Bm, ldb, K), FSN_ERR_UNSUPPORTED, "tgemm: operands must be 16-byte aligned rows");
   static const int force_bn = getenv("FSN_TGEMM_BN") ? atoi(getenv("FSN_TGEMM_BN")) : 0;
-  const int BN = force_bn ? force_bn : ((N >= 256 && N % 256 == 0) ? 256 : 128);
+  int BN = force_bn ? force_bn : ((N >= 256 && N % 256 == 0) ? 256 : 128);
+  // long-K, narrow output (weight gradients): the whole N extent in one CTA so the big A operand is read exactly once
+  static const bool wide = getenv("FSN_TGEMM_NO384") == nullptr;
+  if (!force_bn && wide && tmap_encoder() && scratch && K >= 65536 && N > 256 && N <= 384) BN = 384;
   const int tiles = cdiv(M, tg::BM) * cdiv(N, BN);
   int S = 1;
   if (scratch && K >= 8192 && tiles < 296) {
     // minimise waves(tiles * S) / S over the SM slots (1 or 2 resident CTAs per SM), slices of >= 2048 k
-    const int slots = 148 * (BN == 128 ? 2 : 1);
+    const int slots = 148 * (BN == 128 ? 2 : 1);  // resident CTAs
     double best = 1e30;
     for (int s = 1; s <= 64 && s <= cdiv(K, 2048); ++s) {
       if ((size_t)s * M * N > scratch_floats) break;
@@ -314,7 +327,9 @@ int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float*
   const int acc = (S > 1) ? 0 : (accumulate ? 1 : 0);
   int rc;
   CUtensorMap tmA, tmB;
-  if (make_tmap(&tmA, A, K, M, lda, tg::BM) && make_tmap(&tmB, Bm, K, N, ldb, BN)) {
+  CUtensorMap tmB2;
+  if (make_tmap(&tmA, A, K, M, lda, tg::BM) && make_tmap(&tmB, Bm, K, N, ldb, BN > 256 ? 256 : BN) &&
+      make_tmap(&tmB2, Bm, K, N, ldb, BN > 256 ? BN - 256 : 128)) {
     static bool attr = false;
     if (!attr) {
       if ((rc = check_cuda(cudaFuncSetAttribute(tg::tgemm_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -323,16 +338,25 @@ int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float*
       if ((rc = check_cuda(cudaFuncSetAttribute(tg::tgemm_tma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 tg::Cfg<128>::SMEM), "tgemm smem attr")))
         return rc;
+      if ((rc = check_cuda(cudaFuncSetAttribute(tg::tgemm_tma_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                tg::Cfg<384>::SMEM), "tgemm smem attr")))
+        return rc;
       attr = true;
     }
-    if (BN == 256)
-      tg::tgemm_tma_kernel<256><<<grid, 160, tg::Cfg<256>::SMEM, st>>>(tmA, tmB, dst, ldd, M, N, K, kps, acc, (size_t)M * N);
+    if (BN == 384)
+      tg::tgemm_tma_kernel<384><<<grid, 160, tg::Cfg<384>::SMEM, st>>>(tmA, tmB, tmB2, dst, ldd, M, N, K, kps, acc,
+                                                                       (size_t)M * N);
+    else if (BN == 256)
+      tg::tgemm_tma_kernel<256><<<grid, 160, tg::Cfg<256>::SMEM, st>>>(tmA, tmB, tmB2, dst, ldd, M, N, K, kps, acc,
+                                                                       (size_t)M * N);
     else
-      tg::tgemm_tma_kernel<128><<<grid, 160, tg::Cfg<128>::SMEM, st>>>(tmA, tmB, dst, ldd, M, N, K, kps, acc, (size_t)M * N);
+      tg::tgemm_tma_kernel<128><<<grid, 160, tg::Cfg<128>::SMEM, st>>>(tmA, tmB, tmB2, dst, ldd, M, N, K, kps, acc,
+                                                                       (size_t)M * N);
     FSN_CHECK_LAUNCH("tgemm_tma_kernel");
     if (S > 1) return splitk_reduce_launch(scratch, S, M, N, C, ldc, accumulate, st);
     return FSN_OK;
   }
+  FSN_REQUIRE(BN != 384, FSN_ERR_CUDA, "tgemm: tensor-map encoding failed for the 128x384 tile");
   if (BN == 256) {
     static bool attr = false;
     if (!attr) {

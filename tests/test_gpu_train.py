@@ -196,7 +196,9 @@ def test_tf32_tensor_core_gemm_matches_truncated_reference(dev):
         return (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
     torch.manual_seed(1)
     for (M, N, K, ld, acc, split) in ((128, 128, 32, 32, 0, 0), (200, 130, 100, 104, 0, 0), (256, 384, 1536, 1536, 1, 0),
-                                     (300, 512, 70, 72, 1, 0), (1536, 64, 40000, 40000, 0, 1)):
+                                     (300, 512, 70, 72, 1, 0), (1536, 64, 40000, 40000, 0, 1),
+                                     # long K, 256 < N <= 384: the 128 x 384 tile of the weight-gradient GEMMs
+                                     (1536, 384, 70000, 70000, 0, 1), (200, 300, 66000, 66000, 1, 1)):
         A, B = torch.randn(M, ld, device=dev), torch.randn(N, ld, device=dev)
         C0 = torch.randn(M, N + 8, device=dev)
         Cc = C0.clone()
