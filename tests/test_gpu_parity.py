@@ -189,10 +189,14 @@ def test_tc_drop_band_training_layout_and_unsupported_shapes(golden, dev):
     g = golden("model_small")
     sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
     small = make_model(small_args(), sd, dev, "f16_tc")  # hidden 24: not a multiple of 128
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError), torch.no_grad():
         small(T(g["mag"], dev).unsqueeze(1)[:1])
     auto = make_model(small_args(), sd, dev, "auto")  # auto falls back to the fp32 kernels
-    assert rel_max(auto(T(g["mag"], dev).unsqueeze(1)[:1]).cpu(), g["crm_b1"]) < 2e-5
+    with torch.no_grad():
+        assert rel_max(auto(T(g["mag"], dev).unsqueeze(1)[:1]).cpu(), g["crm_b1"]) < 2e-5
+    # with grad enabled the same call runs the activation-saving training kernels (fp32 here) and is differentiable
+    tr = auto(T(g["mag"], dev).unsqueeze(1)[:1])
+    assert tr.requires_grad and rel_max(tr.detach().cpu(), g["crm_b1"]) < 2e-5
 
 
 def test_full_size_batch_properties(dev):
