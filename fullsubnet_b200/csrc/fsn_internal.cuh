@@ -41,11 +41,17 @@ struct StepParams {
   int row_scale_div;  // scale index = row / row_scale_div (0 or 1: per row)
   // SEG0_GATHER: sub-band unit of row r at frame t (base_model.py:13-46 + model.py:98-111)
   const float* magT; const float* fbT; const float* inv2;
+  const float* unit_scale;  // nullable: per-row scale of this step (cumulative norm) instead of inv2[clip]
   int F, Tp, t, Ns, Nf;
   RowMap map;
 };
 
 int lstm_step_launch(const StepParams& p, int mode, cudaStream_t st);
+// cumulative_laplace_norm (base_model.py:220-251): scale1T[t*B+b] from the frame sums fs[b*Tp+t].x, and
+// scaleT[t*R+r] of every sub-band unit (running mean over its K rows and the frames so far)
+int cum_clip_scale_launch(const float2* fs, int B, int Tp, int F, float eps, float* scale1T, cudaStream_t st);
+int cum_unit_scale_launch(const float* magT, const float* fbT, RowMap map, int R, int Tp, int Ns, int Nf, float eps,
+                          float* scaleT, cudaStream_t st);
 
 // tf32 tcgen05 GEMM (fsn_tgemm.cu): C[M,N] (+)= A[M,K] B[N,K]^T, fp32 row-major operands with 16-byte aligned rows
 bool tgemm_supported(const float* A, size_t lda, const float* Bm, size_t ldb, int K);
@@ -96,6 +102,7 @@ int fb_persistent_launch(const fsn_seq_weights* w, const float* x_chunk, const f
 struct SbTcArgs {
   const void* packed;       // tile-ordered fp16 weights (fsn_pack_sb_weights)
   const float* magT; const float* fbT; const float* inv2;
+  const float* unit_scale;  // nullable: per-row scale of this step (cumulative norm) instead of inv2[clip]
   float* crm;
   int B, F, Tp, la, Ns, Nf, H, act;
   int steps, shrink;      // pair kernel only: LSTM steps (0 = Tp) and time down-sampling of the gathered input (0/1 = none)

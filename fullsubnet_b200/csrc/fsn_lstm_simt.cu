@@ -90,7 +90,7 @@ __device__ __forceinline__ float load_seg0(const StepParams& p, int row, int k, 
     float v;
     if (k < nmag) v = p.magT[base + reflect_idx(src_f + k - p.Ns, p.F)];
     else          v = p.fbT[base + reflect_idx(src_f + (k - nmag) - p.Nf, p.F)];
-    return v * p.inv2[src_b];
+    return v * (p.unit_scale ? p.unit_scale[row] : p.inv2[src_b]);
   }
 }
 
@@ -185,6 +185,49 @@ __global__ void __launch_bounds__(256) lstm_step_kernel(const StepParams p) {
       }
     }
   }
+}
+
+// ---- cumulative_laplace_norm (base_model.py:220-251): one thread per clip / per sub-band unit, sequential in time
+__global__ void cum_clip_scale_kernel(const float2* __restrict__ fs, int B, int Tp, int F, float eps,
+                                      float* __restrict__ scale1T) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float run = 0.f;
+  for (int t = 0; t < Tp; ++t) {
+    run += fs[(size_t)b * Tp + t].x;
+    scale1T[(size_t)t * B + b] = 1.0f / (run / ((float)F * (float)(t + 1)) + eps);
+  }
+}
+
+__global__ void cum_unit_scale_kernel(const float* __restrict__ magT, const float* __restrict__ fbT, RowMap map, int R,
+                                      int Tp, int Ns, int Nf, float eps, float* __restrict__ scaleT) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  int b, f;
+  row_to_unit(map, r, b, f);
+  const int K = 2 * Ns + 1 + 2 * Nf + 1;
+  float run = 0.f;
+  for (int t = 0; t < Tp; ++t) {
+    const size_t base = ((size_t)b * Tp + t) * map.F;
+    float s = 0.f;
+    for (int k = -Ns; k <= Ns; ++k) s += magT[base + reflect_idx(f + k, map.F)];
+    for (int k = -Nf; k <= Nf; ++k) s += fbT[base + reflect_idx(f + k, map.F)];
+    run += s;
+    scaleT[(size_t)t * R + r] = 1.0f / (run / ((float)K * (float)(t + 1)) + eps);
+  }
+}
+
+int cum_clip_scale_launch(const float2* fs, int B, int Tp, int F, float eps, float* scale1T, cudaStream_t st) {
+  cum_clip_scale_kernel<<<cdiv(B, 64), 64, 0, st>>>(fs, B, Tp, F, eps, scale1T);
+  FSN_CHECK_LAUNCH("cum_clip_scale_kernel");
+  return FSN_OK;
+}
+
+int cum_unit_scale_launch(const float* magT, const float* fbT, RowMap map, int R, int Tp, int Ns, int Nf, float eps,
+                          float* scaleT, cudaStream_t st) {
+  cum_unit_scale_kernel<<<cdiv(R, 128), 128, 0, st>>>(magT, fbT, map, R, Tp, Ns, Nf, eps, scaleT);
+  FSN_CHECK_LAUNCH("cum_unit_scale_kernel");
+  return FSN_OK;
 }
 
 int lstm_step_launch(const StepParams& p, int mode, cudaStream_t st) {

@@ -48,6 +48,7 @@ struct ModelWs {
   float *magT, *fbT, *inv1, *inv2;
   float2 *fs, *sums_mag, *sums_fb;
   float *fb_h0[2], *fb_c0, *fb_c1, *fb_h1all, *fb_pp;
+  float *cum1, *cum2;  // cumulative norm: per-(step, clip) and per-(step, unit) scales
   unsigned int* fb_barrier;
   float *sb_h0[2], *sb_h1[2], *sb_c0, *sb_c1;
   size_t bytes;
@@ -57,8 +58,10 @@ int make_dims(const fsn_model_desc* d, int B, int T, Dims& m) {
   FSN_REQUIRE(d && d->num_freqs > 1 && d->fb_hidden > 0 && d->sb_hidden > 0 && d->look_ahead >= 0, FSN_ERR_SHAPE,
               "model: bad descriptor");
   FSN_REQUIRE(B > 0 && T > 0, FSN_ERR_SHAPE, "model: empty input (B=%d, T=%d)", B, T);
-  FSN_REQUIRE(d->norm_type == FSN_NORM_OFFLINE_LAPLACE, FSN_ERR_UNSUPPORTED,
-              "You must set up a type of Norm. (only offline_laplace_norm is built)");
+  FSN_REQUIRE(d->norm_type == FSN_NORM_OFFLINE_LAPLACE || d->norm_type == FSN_NORM_CUMULATIVE_LAPLACE,
+              FSN_ERR_UNSUPPORTED, "You must set up a type of Norm. (offline_laplace_norm / cumulative_laplace_norm are built)");
+  FSN_REQUIRE(d->norm_type == FSN_NORM_OFFLINE_LAPLACE || d->precision == FSN_PREC_FP32, FSN_ERR_UNSUPPORTED,
+              "cumulative_laplace_norm is built for the fp32 path only");
   FSN_REQUIRE(d->sb_num_neighbors >= 0 && d->fb_num_neighbors >= 0 && d->sb_num_neighbors < d->num_freqs &&
                   d->fb_num_neighbors < d->num_freqs,
               FSN_ERR_SHAPE, "model: reflect padding needs num_neighbors < num_freqs");
@@ -99,6 +102,11 @@ static void carve_model(const fsn_model_desc* d, const Dims& m, void* base, Mode
     w.sb_c0 = c.take<float>(RH);
     w.sb_c1 = c.take<float>(RH);
   }
+  w.cum1 = w.cum2 = nullptr;
+  if (d->norm_type == FSN_NORM_CUMULATIVE_LAPLACE) {
+    w.cum1 = c.take<float>((size_t)m.Tp * m.B);
+    w.cum2 = c.take<float>((size_t)m.Tp * m.R);
+  }
   w.bytes = c.off;
 }
 
@@ -110,10 +118,13 @@ static int model_core(const fsn_model_desc* d, const fsn_seq_weights* fb, const 
   // per-clip statistics of the look-ahead-padded magnitude (model.py:92, :111)
   if ((rc = clip_stats_launch(w.magT, B, Tp, F, d->sb_num_neighbors, w.fs, w.sums_mag, st))) return rc;
   if ((rc = norm_scales_launch(w.sums_mag, w.sums_mag, B, (float)F * Tp, 1.f, w.inv1, nullptr, st))) return rc;
+  const bool cum = d->norm_type == FSN_NORM_CUMULATIVE_LAPLACE;
+  const float cum_eps = 1.1920928955078125e-07f;  // audio_zen/constant.py:9 (np.finfo(np.float32).eps)
+  if (cum && (rc = cum_clip_scale_launch(w.fs, B, Tp, F, cum_eps, w.cum1, st))) return rc;
 
   // ---- full-band stack (model.py:92-95): 2-layer LSTM(F -> Hf -> Hf), rows = clips
   static const bool fb_stepwise = getenv("FSN_FB_STEPWISE") != nullptr;  // debug: force the per-step kernels
-  if (!fb_stepwise && fb_persistent_supported(F, Hf, Hf)) {
+  if (!fb_stepwise && !cum && fb_persistent_supported(F, Hf, Hf)) {
     // one persistent cooperative kernel per chunk of <= 256 clips: weights resident in shared memory,
     // layer wavefront, one grid barrier per time step
     for (int b0 = 0; b0 < B; b0 += 256) {
@@ -133,7 +144,8 @@ static int model_core(const fsn_model_desc* d, const fsn_seq_weights* fb, const 
     p.h_prev = w.fb_h0[(t + 1) & 1]; p.h_prev_stride = Hf;
     p.h_out = w.fb_h0[t & 1]; p.h_out_stride = Hf;
     p.c = w.fb_c0;
-    p.x0 = w.magT + (size_t)t * F; p.x0_row_stride = (size_t)Tp * F; p.row_scale = w.inv1;
+    p.x0 = w.magT + (size_t)t * F; p.x0_row_stride = (size_t)Tp * F;
+    p.row_scale = cum ? w.cum1 + (size_t)t * B : w.inv1;  // cumulative: scale of (step t, clip b)
     if ((rc = lstm_step_launch(p, SEG0_DENSE, st))) return rc;
     // layer 1: x_t = h0_t, output kept for every t (input of the Linear layer)
     p.K0 = Hf;
@@ -155,6 +167,9 @@ static int model_core(const fsn_model_desc* d, const fsn_seq_weights* fb, const 
 
   prof_mark(2, st);
   RowMap map{B, F, m.Fsub, m.G};
+  if (cum && (rc = cum_unit_scale_launch(w.magT, w.fbT, map, m.R, Tp, d->sb_num_neighbors, d->fb_num_neighbors, cum_eps,
+                                         w.cum2, st)))
+    return rc;
   if (d->precision == FSN_PREC_F16_TC) {
     FSN_REQUIRE(sb_packed, FSN_ERR_SHAPE, "model: FSN_PREC_F16_TC needs packed sub-band weights");
     SbTcArgs a;
@@ -178,6 +193,7 @@ static int model_core(const fsn_model_desc* d, const fsn_seq_weights* fb, const 
     p.h_out = w.sb_h0[t & 1]; p.h_out_stride = Hs;
     p.c = w.sb_c0;
     p.magT = w.magT; p.fbT = w.fbT; p.inv2 = w.inv2;
+    p.unit_scale = cum ? w.cum2 + (size_t)t * m.R : nullptr;
     p.F = F; p.Tp = Tp; p.t = t; p.Ns = d->sb_num_neighbors; p.Nf = d->fb_num_neighbors; p.map = map;
     if ((rc = lstm_step_launch(p, SEG0_GATHER, st))) return rc;
     p.K0 = Hs;

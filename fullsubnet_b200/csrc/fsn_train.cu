@@ -468,6 +468,8 @@ static void carve_train(const fsn_model_desc* d, const Dims& m, void* base, Trai
 }
 
 static int train_check(const fsn_model_desc* d) {
+  FSN_REQUIRE(d->norm_type == FSN_NORM_OFFLINE_LAPLACE, FSN_ERR_UNSUPPORTED,
+              "training: only offline_laplace_norm is built");
   FSN_REQUIRE(d->fb_num_neighbors == 0, FSN_ERR_UNSUPPORTED,
               "training: fb_num_neighbors > 0 is not built (every shipped recipe uses 0)");
   return FSN_OK;

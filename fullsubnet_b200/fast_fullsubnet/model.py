@@ -64,6 +64,8 @@ class Model(BaseModel):
         self.encoder_input_size = encoder_input_size
         self.noisy_input_num_neighbors = noisy_input_num_neighbors
         self.enc_output_num_neighbors = encoder_output_num_neighbors
+        if norm_type != "offline_laplace_norm":
+            raise NotImplementedError(f"norm_type {norm_type!r} is not built for fast_fullsubnet (SURVEY 8f)")
         self.norm = self.norm_wrapper(norm_type)
         # arithmetic of the bottleneck stack (92 % of the FLOPs): 'fp32' | 'f16_tc' (tcgen05 pair kernel) | 'auto'
         self.precision = precision or os.environ.get("FSN_PRECISION", "auto")

@@ -7,7 +7,7 @@ import torch.nn.init as init
 
 
 class BaseModel(nn.Module):
-    NORM_TYPES = {"offline_laplace_norm": 0}
+    NORM_TYPES = {"offline_laplace_norm": 0, "cumulative_laplace_norm": 1}
     _UPSTREAM_NORMS = ("offline_laplace_norm", "cumulative_laplace_norm", "offline_gaussian_norm",
                        "cumulative_layer_norm", "forgetting_norm")
 

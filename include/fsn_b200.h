@@ -38,7 +38,9 @@ enum {
 };
 
 enum { FSN_ACT_NONE = 0, FSN_ACT_RELU = 1, FSN_ACT_TANH = 2, FSN_ACT_RELU6 = 3 };
-enum { FSN_NORM_OFFLINE_LAPLACE = 0 };
+/* FSN_NORM_CUMULATIVE_LAPLACE (audio_zen/model/base_model.py:220-251): causal running mean per clip (first norm) and
+ * per sub-band unit (second norm); built for the fp32 inference path of fsn_model_forward / fsn_enhance */
+enum { FSN_NORM_OFFLINE_LAPLACE = 0, FSN_NORM_CUMULATIVE_LAPLACE = 1 };
 /* arithmetic of the sub-band LSTM stack (99 % of the FLOPs):
  *   FSN_PREC_FP32     - fp32 FMA everywhere (bit-for-bit class of the reference CPU path, ~1e-6)
  *   FSN_PREC_TF32_TC  - training step only (fsn_train_*): every GEMM of the forward, of back-propagation through

@@ -274,3 +274,26 @@ def test_improved_fullsubnet_matches_reference(golden, dev, tag):
     bad = Model(**dict(args, freq_cutoffs=[21] + list(args["freq_cutoffs"][1:]))).to(dev).eval()
     with pytest.raises(ValueError), torch.no_grad():
         bad(y)
+
+
+# ------------------------------------------------------------------ cumulative_laplace_norm
+def test_cumulative_laplace_norm_matches_reference(golden, dev):
+    from fullsubnet_b200.fullsubnet.model import Model
+    from oracle import fullsubnet_oracle as O
+    g = golden("model_cum")
+    args = dict(small_args(), norm_type="cumulative_laplace_norm")
+    m = make_model(args, O.make_state_dict(seed=7, args=args), dev, "auto")
+    assert m._resolve_precision() == "fp32"
+    mag = T(g["small_mag"], dev).unsqueeze(1)
+    with torch.no_grad():
+        assert rel_max(m(mag[:1]).cpu(), g["small_b1"]) < 2e-5
+        assert rel_max(m(mag).cpu(), g["small_g2"]) < 2e-5  # B=3: drop_band + per-unit running means
+    full = dict(O.DEFAULT_MODEL_ARGS, norm_type="cumulative_laplace_norm")
+    mf = make_model(full, O.make_state_dict(seed=0, args=full, sb_fc_gain=60.0), dev, "auto")
+    wav, crm = mf.enhance(T(g["full_y"], dev), return_crm=True)
+    assert rel_max(crm.cpu(), g["full_crm"]) < 5e-5
+    assert np.abs(wav.cpu().numpy() - g["full_wav"]).max() < WAV_TOL
+    with pytest.raises(NotImplementedError), torch.no_grad():
+        make_model(full, O.make_state_dict(seed=0, args=full), dev, "f16_tc")(torch.rand(1, 1, 257, 4, device=dev))
+    with pytest.raises(NotImplementedError):
+        mf.train()(torch.rand(3, 1, 257, 5, device=dev))  # training: offline norm only

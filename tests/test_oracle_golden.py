@@ -197,3 +197,20 @@ def test_manual_bptt_equals_autograd(golden):
         assert abs(float(l0) - float(l1)) < 1e-6 * float(l0)
         for k in sd:
             assert rel_l2(g1[k], g0[k]) < 1e-5, (B, G, k)
+
+
+def test_cumulative_laplace_norm_oracle_matches_reference(golden):
+    """norm_type = cumulative_laplace_norm (base_model.py:220-251) through the whole model."""
+    g = golden("model_cum")
+    small = dict(num_freqs=33, look_ahead=2, sequence_model="LSTM", fb_num_neighbors=0, sb_num_neighbors=3,
+                 fb_output_activate_function="ReLU", sb_output_activate_function=False, fb_model_hidden_size=32,
+                 sb_model_hidden_size=24, norm_type="cumulative_laplace_norm", num_groups_in_drop_band=2)
+    sd = O.make_state_dict(seed=7, args=small)
+    mag = T(g["small_mag"]).unsqueeze(1)
+    assert rel_max(O.model_forward(mag[:1], sd, small), g["small_b1"]) < 2e-5
+    assert rel_max(O.model_forward(mag, sd, small), g["small_g2"]) < 2e-5
+    full = dict(O.DEFAULT_MODEL_ARGS, norm_type="cumulative_laplace_norm")
+    sdf = O.make_state_dict(seed=0, args=full, sb_fc_gain=60.0)
+    wav, crm = O.enhance(T(g["full_y"]), sdf, full, return_crm=True)
+    assert rel_max(crm, g["full_crm"]) < 5e-5
+    assert np.abs(wav.numpy() - g["full_wav"]).max() < 1e-5
