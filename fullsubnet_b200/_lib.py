@@ -110,6 +110,7 @@ _SIGNATURES = {
     "fsn_clip_adam_scratch_bytes": (_S, []),
     "fsn_clip_adam": (C.c_int, [C.POINTER(ParamList), _F, _F, _F, _F, _F, _F, _I, _P, _P, _S, _P]),
     "fsn_debug_tgemm": (C.c_int, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _P, _L, _P]),
+    "fsn_last_error_code": (C.c_int, []),
     "fsn_last_launch_count": (C.c_int64, []),
     "fsn_total_launch_count": (C.c_int64, []),
     "fsn_set_profiling": (C.c_int, [_I]),
@@ -146,6 +147,13 @@ def check(rc: int) -> None:
     if rc == FSN_ERR_UNSUPPORTED:
         raise NotImplementedError(msg)
     raise RuntimeError(f"libfsn_b200 error {rc}: {msg}")
+
+
+def check_workspace(nbytes: int) -> int:
+    """*_workspace_bytes() return 0 on failure: raise what the failed shape / configuration check asked for."""
+    if nbytes == 0:
+        check(load().fsn_last_error_code() or FSN_ERR_SHAPE)
+    return nbytes
 
 
 def require_cuda(t: torch.Tensor, what: str) -> torch.Tensor:

@@ -10,12 +10,14 @@
 namespace fsn {
 
 void set_error(const char* fmt, ...);
+int& last_error_code();
 int64_t& launch_counter();
 int64_t& total_launch_counter();
 
 inline int check_cuda(cudaError_t e, const char* what) {
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
+    last_error_code() = FSN_ERR_CUDA;
     return FSN_ERR_CUDA;
   }
   return FSN_OK;
@@ -33,6 +35,7 @@ inline int check_cuda(cudaError_t e, const char* what) {
   do {                                \
     if (!(cond)) {                    \
       ::fsn::set_error(__VA_ARGS__);  \
+      ::fsn::last_error_code() = code; \
       return code;                    \
     }                                 \
   } while (0)

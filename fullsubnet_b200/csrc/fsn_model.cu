@@ -19,6 +19,8 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static thread_local int g_err_code = 0;
+int& last_error_code() { return g_err_code; }
 int64_t& launch_counter() { return g_launches; }
 static int64_t g_total_launches = 0;
 int64_t& total_launch_counter() { return g_total_launches; }
@@ -218,6 +220,7 @@ using namespace fsn;
 
 extern "C" int fsn_version(void) { return 100; }
 extern "C" const char* fsn_last_error(void) { return g_err; }
+extern "C" int fsn_last_error_code(void) { return g_err_code; }
 extern "C" int64_t fsn_last_launch_count(void) { return g_launches; }
 extern "C" int64_t fsn_total_launch_count(void) { return g_total_launches; }
 extern "C" int fsn_set_profiling(int enable) { g_prof = enable != 0; return FSN_OK; }

@@ -42,7 +42,7 @@ class _TrainForward(torch.autograd.Function):
             fb_w, sb_w = model.fb_model.weight_struct(), model.sb_model.weight_struct()
             n = lib.fsn_train_workspace_bytes(C.byref(desc), B, T)
             if n == 0:
-                _lib.check(_lib.FSN_ERR_SHAPE)
+                _lib.check_workspace(n)
             ws = torch.empty(n, dtype=torch.uint8, device=device)
             G = desc.num_groups_in_drop_band if B > 1 and desc.num_groups_in_drop_band > 1 else 1
             out = torch.empty(B, 2, F // G if G > 1 else F, T, dtype=torch.float32, device=device)
@@ -171,7 +171,7 @@ class Model(BaseModel):
             f_out = num_freqs // G if G > 1 else num_freqs
             ws_bytes = lib.fsn_model_workspace_bytes(C.byref(desc), batch_size, num_frames)
             if ws_bytes == 0:
-                _lib.check(_lib.FSN_ERR_SHAPE)
+                _lib.check_workspace(ws_bytes)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
             out = torch.empty(batch_size, 2, f_out, num_frames, dtype=torch.float32, device=device)
             _lib.check(lib.fsn_model_forward(C.byref(desc), C.byref(fb_w), C.byref(sb_w), _lib.ptr(packed),
@@ -224,7 +224,7 @@ class Model(BaseModel):
             desc, fb_w, sb_w, packed = self._prepare(device, 1)
             ws_bytes = lib.fsn_enhance_workspace_bytes(C.byref(desc), B, L, n_fft, hop_length)
             if ws_bytes == 0:
-                _lib.check(_lib.FSN_ERR_SHAPE)
+                _lib.check_workspace(ws_bytes)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
             out = torch.empty(B, L, dtype=torch.float32, device=device)
             crm = torch.empty(B, 2, n_fft // 2 + 1, 1 + L // hop_length, dtype=torch.float32,

@@ -100,7 +100,7 @@ class Model(BaseModel):
             d, w = self._structs()
             n = lib.fsn_improved_workspace_bytes(C.byref(d), B, L)
             if n == 0:
-                _lib.check(_lib.FSN_ERR_SHAPE)
+                _lib.check_workspace(n)
             ws = torch.empty(n, dtype=torch.uint8, device=x.device)
             out = torch.empty(B, 1, L, dtype=torch.float32, device=x.device)
             crm = torch.empty(B, 2, self.num_freqs, 1 + L // self.hop_length, dtype=torch.float32,

@@ -52,6 +52,9 @@ enum { FSN_PREC_FP32 = 0, FSN_PREC_F16_TC = 1, FSN_PREC_TF32_TC = 2 };
 
 int fsn_version(void);
 const char* fsn_last_error(void);
+/* status code (FSN_ERR_*) of the last failed call on this thread: lets the *_workspace_bytes() functions, which
+ * return 0 on failure, report WHY (shape error vs unsupported configuration) */
+int fsn_last_error_code(void);
 /* compile-time facts for the host (sm arch the kernels were built for, e.g. 100) */
 int fsn_built_arch(void);
 

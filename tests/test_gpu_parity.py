@@ -293,7 +293,13 @@ def test_cumulative_laplace_norm_matches_reference(golden, dev):
     wav, crm = mf.enhance(T(g["full_y"], dev), return_crm=True)
     assert rel_max(crm.cpu(), g["full_crm"]) < 5e-5
     assert np.abs(wav.cpu().numpy() - g["full_wav"]).max() < WAV_TOL
+
+
+def test_cumulative_laplace_norm_unsupported_combinations(dev):
+    from oracle import fullsubnet_oracle as O
+    full = dict(O.DEFAULT_MODEL_ARGS, norm_type="cumulative_laplace_norm")
+    sd = O.make_state_dict(seed=0, args=full)
     with pytest.raises(NotImplementedError), torch.no_grad():
-        make_model(full, O.make_state_dict(seed=0, args=full), dev, "f16_tc")(torch.rand(1, 1, 257, 4, device=dev))
+        make_model(full, sd, dev, "f16_tc")(torch.rand(1, 1, 257, 4, device=dev))  # tensor-core path: offline norm only
     with pytest.raises(NotImplementedError):
-        mf.train()(torch.rand(3, 1, 257, 5, device=dev))  # training: offline norm only
+        make_model(full, sd, dev, "auto").train()(torch.rand(3, 1, 257, 5, device=dev))  # training: offline norm only
