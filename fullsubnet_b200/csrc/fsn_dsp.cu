@@ -270,11 +270,26 @@ static int ew_grid(int64_t n) {
 
 static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
+// fsn_dsp_dft.cu: direct-DFT variants for even transform sizes that are not a power of two (e.g. 960)
+int stft_dft_launch(const float* wav, int B, int L, int n_fft, int hop, int win_length, int T, int Tg, float* mag,
+                    float* phase, float* real, float* imag, float* magT, int T_pad, cudaStream_t st);
+int istft_dft_launch(const float* real, const float* imag, int cstride, const float* crm, int mask_mode, int B, int T,
+                     int n_fft, int hop, int win_length, int out_len, float* wav, cudaStream_t st);
+static bool dft_size_ok(int n) { return !is_pow2(n) && (n & 1) == 0 && n >= 16 && n <= 1200; }
+
 int stft_launch(const float* wav, int B, int L, int n_fft, int hop, int win_length, float* mag, float* phase,
                 float* real, float* imag, float* magT, int T_pad, cudaStream_t st) {
   FSN_REQUIRE(B > 0 && L > 0, FSN_ERR_SHAPE, "stft: empty input (B=%d, L=%d)", B, L);
+  if (dft_size_ok(n_fft)) {
+    FSN_REQUIRE(hop > 0 && win_length > 0 && win_length <= n_fft, FSN_ERR_SHAPE, "stft: bad hop/win_length");
+    FSN_REQUIRE(n_fft / 2 < L, FSN_ERR_SHAPE, "stft: reflect padding %d needs L > pad (L=%d)", n_fft / 2, L);
+    FSN_REQUIRE(!magT || T_pad >= 1 + L / hop, FSN_ERR_SHAPE, "stft: T_pad < T");
+    const int Td = 1 + L / hop;
+    return stft_dft_launch(wav, B, L, n_fft, hop, win_length, Td, magT ? (T_pad > Td ? T_pad : Td) : Td, mag, phase, real,
+                           imag, magT, T_pad, st);
+  }
   FSN_REQUIRE(is_pow2(n_fft) && n_fft >= 16 && n_fft <= 2048, FSN_ERR_UNSUPPORTED,
-              "stft: n_fft=%d unsupported (power of two in [16,2048])", n_fft);
+              "stft: n_fft=%d unsupported (power of two in [16,2048], or even and <= 1200)", n_fft);
   FSN_REQUIRE(hop > 0 && win_length > 0 && win_length <= n_fft, FSN_ERR_SHAPE, "stft: bad hop/win_length");
   FSN_REQUIRE(n_fft / 2 < L, FSN_ERR_SHAPE, "stft: reflect padding %d needs L > pad (L=%d)", n_fft / 2, L);
   const int T = 1 + L / hop;
@@ -296,8 +311,16 @@ int stft_launch(const float* wav, int B, int L, int n_fft, int hop, int win_leng
 int istft_launch(const float* real, const float* imag, int cstride, const float* crm, int B, int T, int n_fft,
                  int hop, int win_length, int length, float* wav, cudaStream_t st, int mask_mode) {
   FSN_REQUIRE(B > 0 && T > 0, FSN_ERR_SHAPE, "istft: empty input");
+  if (dft_size_ok(n_fft)) {
+    FSN_REQUIRE(hop > 0 && hop <= n_fft && win_length > 0 && win_length <= n_fft, FSN_ERR_SHAPE,
+                "istft: bad hop/win_length");
+    FSN_REQUIRE(cstride == 1 || cstride == 2, FSN_ERR_SHAPE, "istft: cstride must be 1 or 2");
+    const int olen = length > 0 ? length : hop * (T - 1);
+    FSN_REQUIRE(olen > 0, FSN_ERR_SHAPE, "istft: output length %d", olen);
+    return istft_dft_launch(real, imag, cstride, crm, mask_mode, B, T, n_fft, hop, win_length, olen, wav, st);
+  }
   FSN_REQUIRE(is_pow2(n_fft) && n_fft >= 16 && n_fft <= 2048, FSN_ERR_UNSUPPORTED,
-              "istft: n_fft=%d unsupported (power of two in [16,2048])", n_fft);
+              "istft: n_fft=%d unsupported (power of two in [16,2048], or even and <= 1200)", n_fft);
   FSN_REQUIRE(hop > 0 && hop <= n_fft && win_length > 0 && win_length <= n_fft, FSN_ERR_SHAPE,
               "istft: bad hop/win_length");
   FSN_REQUIRE(cstride == 1 || cstride == 2, FSN_ERR_SHAPE, "istft: cstride must be 1 or 2");

@@ -109,8 +109,9 @@ static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
 static int imp_dims(const fsn_improved_desc* d, int B, int L, ImpDims& m) {
   FSN_REQUIRE(d && B > 0 && L > 0, FSN_ERR_SHAPE, "improved model: empty input");
-  FSN_REQUIRE(is_pow2(d->n_fft) && d->n_fft <= 2048, FSN_ERR_UNSUPPORTED,
-              "improved model: n_fft=%d needs a mixed-radix FFT (only powers of two <= 2048 are built)", d->n_fft);
+  FSN_REQUIRE((is_pow2(d->n_fft) && d->n_fft <= 2048) || (d->n_fft % 2 == 0 && d->n_fft >= 16 && d->n_fft <= 1200),
+              FSN_ERR_UNSUPPORTED, "improved model: n_fft=%d unsupported (power of two <= 2048, or even and <= 1200)",
+              d->n_fft);
   FSN_REQUIRE(d->num_freqs == d->n_fft / 2 + 1, FSN_ERR_SHAPE, "improved model: num_freqs != n_fft/2+1");
   FSN_REQUIRE(d->num_sections >= 1 && d->num_sections <= FSN_IMP_MAX_SECTIONS, FSN_ERR_SHAPE, "improved model: sections");
   m.B = B; m.L = L; m.T = 1 + L / d->hop_length; m.F = d->num_freqs; m.Fu = m.F - 1; m.S = d->num_sections;

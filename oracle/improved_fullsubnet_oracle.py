@@ -24,6 +24,11 @@ ARGS_48K_1024 = dict(DEFAULT_IMPROVED_ARGS, n_fft=1024, hop_length=512, win_leng
                      freq_cutoffs=[32, 128, 256], sb_num_center_freqs=[1, 4, 16, 64],
                      sb_num_neighbor_freqs=[15, 15, 15, 15], fb_num_center_freqs=[1, 4, 16, 64],
                      fb_num_neighbor_freqs=[15, 15, 15, 15])
+# the reference's own 48 kHz example (improved_fullsubnet/model.py:603-620): n_fft = 960 is not a power of two
+ARGS_48K_960 = dict(DEFAULT_IMPROVED_ARGS, n_fft=960, hop_length=480, win_length=960, num_freqs=481,
+                    freq_cutoffs=[20, 120, 240], sb_num_center_freqs=[1, 4, 20, 60],
+                    sb_num_neighbor_freqs=[15, 15, 15, 15], fb_num_center_freqs=[1, 4, 20, 60],
+                    fb_num_neighbor_freqs=[15, 15, 15, 15])
 
 
 def offline_laplace_norm(x: torch.Tensor) -> torch.Tensor:

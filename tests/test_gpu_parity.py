@@ -303,3 +303,32 @@ def test_cumulative_laplace_norm_unsupported_combinations(dev):
         make_model(full, sd, dev, "f16_tc")(torch.rand(1, 1, 257, 4, device=dev))  # tensor-core path: offline norm only
     with pytest.raises(NotImplementedError):
         make_model(full, sd, dev, "auto").train()(torch.rand(3, 1, 257, 5, device=dev))  # training: offline norm only
+
+
+# ------------------------------------------------------------------ n_fft = 960 (direct-DFT kernels, fsn_dsp_dft.cu)
+def test_non_power_of_two_stft_istft(golden, dev):
+    from fullsubnet_b200.acoustics.feature import stft, istft
+    g = golden("improved_960")
+    mag, _, re, im = stft(T(g["y"], dev), 960, 480, 960)
+    assert mag.shape == g["mag"].shape
+    scale = float(np.abs(g["mag"]).max())
+    assert np.abs(re.cpu().numpy() - g["real"]).max() < 2e-5 * scale
+    assert np.abs(im.cpu().numpy() - g["imag"]).max() < 2e-5 * scale
+    assert rel_max(mag.cpu(), g["mag"]) < 2e-5
+    back = istft((re * 0.5 - im * 0.25, im * 0.5 + re * 0.25), 960, 480, 960, length=12000, input_type="real_imag")
+    n_ok = 480 * (mag.shape[-1] - 1)
+    assert np.abs(back.cpu().numpy() - g["back"])[:, :n_ok].max() < 2e-5 * max(1.0, float(np.abs(g["back"]).max()))
+
+
+def test_improved_fullsubnet_960_matches_reference(golden, dev):
+    from fullsubnet_b200.improved_fullsubnet.model import Model
+    from oracle import improved_fullsubnet_oracle as IO
+    g = golden("improved_960")
+    m = Model(**IO.ARGS_48K_960)
+    m.load_state_dict(IO.make_improved_state_dict(seed=5, args=IO.ARGS_48K_960), strict=True)
+    m = m.to(dev).eval()
+    with torch.no_grad():
+        wav = m(T(g["y"], dev))
+    err = np.abs(wav.cpu().numpy() - g["wav"]).max()
+    print(f"improved_fullsubnet n_fft=960: waveform max-abs {err:.2e} (scale {np.abs(g['wav']).max():.2e})")
+    assert err < WAV_TOL

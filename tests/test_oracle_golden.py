@@ -214,3 +214,15 @@ def test_cumulative_laplace_norm_oracle_matches_reference(golden):
     wav, crm = O.enhance(T(g["full_y"]), sdf, full, return_crm=True)
     assert rel_max(crm, g["full_crm"]) < 5e-5
     assert np.abs(wav.numpy() - g["full_wav"]).max() < 1e-5
+
+
+def test_improved_fullsubnet_960_oracle_matches_reference(golden):
+    """The reference's own 48 kHz example (model.py:603-620): n_fft = 960, 12.18 M parameters."""
+    from oracle import improved_fullsubnet_oracle as IO
+    g = golden("improved_960")
+    sd = IO.make_improved_state_dict(seed=5, args=IO.ARGS_48K_960)
+    assert sum(v.numel() for v in sd.values()) == 12_180_874  # "12.18 M" (SURVEY A14)
+    wav = IO.improved_forward(T(g["y"]), sd, IO.ARGS_48K_960)
+    assert np.abs(wav.numpy() - g["wav"]).max() < 2e-6 * max(1.0, np.abs(g["wav"]).max())
+    mag, _, re, im = O.stft(T(g["y"]), 960, 480, 960)
+    assert rel_max(re, g["real"]) < 5e-6 and rel_max(im, g["imag"]) < 5e-6 and rel_max(mag, g["mag"]) < 5e-6
