@@ -58,6 +58,11 @@ class ParamList(C.Structure):
                 ("numel", C.c_int64 * MAX_PARAM_TENSORS)]
 
 
+class FullbandDesc(C.Structure):
+    _fields_ = [("num_freqs", C.c_int32), ("hidden", C.c_int32), ("num_layers", C.c_int32), ("look_ahead", C.c_int32),
+                ("activation", C.c_int32), ("norm_type", C.c_int32)]
+
+
 IMP_MAX_SECTIONS = 8
 
 
@@ -109,6 +114,9 @@ _SIGNATURES = {
     "fsn_mse_loss": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _P, _S, _P]),
     "fsn_clip_adam_scratch_bytes": (_S, []),
     "fsn_clip_adam": (C.c_int, [C.POINTER(ParamList), _F, _F, _F, _F, _F, _F, _I, _P, _P, _S, _P]),
+    "fsn_fullband_workspace_bytes": (_S, [C.POINTER(FullbandDesc), _I, _I]),
+    "fsn_fullband_forward": (C.c_int, [C.POINTER(FullbandDesc), _P, _P, _P, _P, _I, _I, _P, _P, _S, _P]),
+    "fsn_peak_normalize_int16": (C.c_int, [_P, _I, _I, _F, _P, _P]),
     "fsn_debug_tgemm": (C.c_int, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _P, _L, _P]),
     "fsn_last_error_code": (C.c_int, []),
     "fsn_last_launch_count": (C.c_int64, []),

@@ -263,6 +263,24 @@ __global__ void drop_band_kernel(const float* __restrict__ in, float* __restrict
   }
 }
 
+// base_inferencer.py:181-182: int16(0.8 * 32767 * y / max|y|) per clip; one CTA per clip (max reduce, then scale)
+__global__ void peak_normalize_int16_kernel(const float* __restrict__ wav, int L, float gain, int16_t* __restrict__ out) {
+  __shared__ float sh[256];
+  const float* x = wav + (size_t)blockIdx.x * L;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) m = fmaxf(m, fabsf(x[i]));
+  sh[threadIdx.x] = m;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] = fmaxf(sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  m = sh[0];
+  int16_t* o = out + (size_t)blockIdx.x * L;
+  for (int i = threadIdx.x; i < L; i += blockDim.x)
+    o[i] = (m > 0.f) ? (int16_t)__fdiv_rn(__fmul_rn(gain, x[i]), m) : (int16_t)0;  // float32 mul, div, truncation like numpy
+}
+
 static int ew_grid(int64_t n) {
   int64_t g = (n + 255) / 256;
   return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -353,6 +371,13 @@ extern "C" int fsn_stft(const float* wav, int B, int L, int n_fft, int hop, int 
 extern "C" int fsn_istft(const float* real, const float* imag, int cstride, const float* crm, int B, int T,
                          int n_fft, int hop, int win_length, int length, float* wav, fsn_stream_t stream) {
   return istft_launch(real, imag, cstride, crm, B, T, n_fft, hop, win_length, length, wav, (cudaStream_t)stream, 1);
+}
+
+extern "C" int fsn_peak_normalize_int16(const float* wav, int B, int L, float gain, int16_t* out, fsn_stream_t stream) {
+  FSN_REQUIRE(B > 0 && L > 0, FSN_ERR_SHAPE, "peak_normalize: empty input");
+  peak_normalize_int16_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(wav, L, gain, out);
+  FSN_CHECK_LAUNCH("peak_normalize_int16_kernel");
+  return FSN_OK;
 }
 
 extern "C" int fsn_decompress_cirm(const float* in, float* out, int64_t n, float K, float limit,

@@ -85,6 +85,30 @@ class Inferencer:
         return out
 
     @torch.no_grad()
+    def enhance_to_pcm(self, noisy: torch.Tensor) -> torch.Tensor:
+        """enhance_batch + the int16 scaling of base_inferencer.py:181-182 on the device: noisy [B,L] -> int16 [B,L]
+        (what the reference hands to ``sf.write``); only B*L*2 bytes come back to the host."""
+        from . import _lib
+        enhanced = self.enhance_batch(noisy)
+        B, L = enhanced.shape
+        pcm = torch.empty(B, L, dtype=torch.int16, device=enhanced.device)
+        with torch.cuda.device(enhanced.device):
+            _lib.check(_lib.load().fsn_peak_normalize_int16(enhanced.data_ptr(), B, L, 0.8 * float(np.iinfo(np.int16).max),
+                                                          pcm.data_ptr(), _lib.stream_ptr(enhanced.device)))
+        return pcm
+
+    @staticmethod
+    def write_wav(path, pcm, sr: int = 16000) -> None:
+        """16-bit mono PCM file with the standard library (the reference uses soundfile, base_inferencer.py:183-187)."""
+        import wave
+        data = pcm.cpu().numpy() if isinstance(pcm, torch.Tensor) else np.asarray(pcm)
+        with wave.open(str(path), "wb") as f:
+            f.setnchannels(1)
+            f.setsampwidth(2)
+            f.setframerate(int(sr))
+            f.writeframes(np.ascontiguousarray(data, dtype="<i2").tobytes())
+
+    @torch.no_grad()
     def __call__(self, clips):
         """Host loop of base_inferencer.py:163-195 without the wav I/O: yields (enhanced float32, int16 PCM
         scaled as base_inferencer.py:181-182) per clip."""

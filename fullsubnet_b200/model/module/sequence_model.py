@@ -24,8 +24,8 @@ class SequenceModel(nn.Module):
         else:
             # sequence_model.py:59-79: GRU exists upstream; this build covers the LSTM configs only
             raise NotImplementedError(f"Not implemented {sequence_model}")
-        if bidirectional or num_layers not in (1, 2):
-            raise NotImplementedError("libfsn_b200 builds uni-directional 1- or 2-layer LSTM stacks")
+        if bidirectional or not 1 <= num_layers <= 8:
+            raise NotImplementedError("libfsn_b200 builds uni-directional LSTM stacks of 1..8 layers")
         if int(output_size):  # sequence_model.py:82-84 (no Linear layer when output_size == 0)
             self.fc_output_layer = nn.Linear(hidden_size, output_size)
         self.num_layers = num_layers

@@ -286,6 +286,28 @@ size_t fsn_clip_adam_scratch_bytes(void);
 int fsn_clip_adam(const fsn_param_list* L, float max_norm, float grad_scale, float lr, float beta1, float beta2,
                   float eps, int step, float* norm_out, void* scratch, size_t scratch_bytes, fsn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * recipes/dns_interspeech_2020/fullband_baseline/model.py:8-68  Model
+ *   look-ahead pad -> norm -> num_layers x LSTM(F -> H) -> Linear(H -> 2F) [+ activation] -> [B,2,F,T]; fp32 kernels.
+ *   layers: num_layers entries (PyTorch parameter layout); fc_w [2F,H], fc_b [2F]. */
+typedef struct fsn_fullband_desc {
+  int32_t num_freqs;
+  int32_t hidden;
+  int32_t num_layers; /* the reference builds 3 */
+  int32_t look_ahead;
+  int32_t activation; /* FSN_ACT_* */
+  int32_t norm_type;  /* FSN_NORM_* */
+} fsn_fullband_desc;
+
+size_t fsn_fullband_workspace_bytes(const fsn_fullband_desc* d, int B, int T);
+int fsn_fullband_forward(const fsn_fullband_desc* d, const fsn_lstm_layer* layers, const float* fc_w, const float* fc_b,
+                         const float* noisy_mag, int B, int T, float* out, void* workspace, size_t workspace_bytes,
+                         fsn_stream_t stream);
+
+/* audio_zen/inferencer/base_inferencer.py:181-182: out = int16(gain * wav / max|wav|) per clip,
+ * gain = 0.8 * 32767 in the reference; float32 multiply, divide, truncation toward zero like numpy; all-zero clip -> 0 */
+int fsn_peak_normalize_int16(const float* wav, int B, int L, float gain, int16_t* out, fsn_stream_t stream);
+
 /* unit-test hook for the tf32 tcgen05 GEMM of the training path: C[M,N] (+)= A[M,K] B[N,K]^T, fp32 row-major
  * operands with 16-byte aligned rows; scratch (optional) enables split-K */
 int fsn_debug_tgemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,

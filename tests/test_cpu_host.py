@@ -4,6 +4,7 @@ import os
 import re
 import shutil
 
+import numpy as np
 import pytest
 import torch
 
@@ -154,3 +155,47 @@ def test_training_host_objects_without_gpu():
     m.train_precision = "bf16"
     with pytest.raises(ValueError):
         m._resolve_train_precision()
+
+
+def test_fullband_baseline_state_dict_contract():
+    from fullsubnet_b200.fullband_baseline.model import Model
+    from oracle import fullband_baseline_oracle as BO
+    m = Model(**BO.DEFAULT_FBB_ARGS)
+    want = BO.fbb_state_dict_shapes()  # validated against the reference by oracle/make_golden_fbb.py
+    sd = m.state_dict()
+    assert list(sd.keys()) == [k for k, _ in want] and [tuple(v.shape) for v in sd.values()] == [s for _, s in want]
+    m.load_state_dict(BO.make_fbb_state_dict(11), strict=True)
+    with pytest.raises(RuntimeError), torch.no_grad():
+        m.eval()(torch.zeros(1, 1, 257, 4))  # no CPU path
+
+
+def test_workspace_queries_report_error_class_without_gpu():
+    """*_workspace_bytes() run no CUDA code: they can be exercised on the CPU box (sizes, error classes)."""
+    import ctypes as C
+    from fullsubnet_b200 import _lib
+    lib = _lib.load()
+    d = _lib.ModelDesc(num_freqs=257, look_ahead=2, fb_num_neighbors=0, sb_num_neighbors=15, fb_hidden=512, sb_hidden=384,
+                       fb_activation=1, sb_activation=0, norm_type=0, num_groups_in_drop_band=2, precision=2, reserved=0)
+    n = lib.fsn_train_workspace_bytes(C.byref(d), 64, 188)
+    assert 40e9 < n < 50e9  # config 3: 28.7 GB of saved activations + transposed copies and scratch
+    assert lib.fsn_train_workspace_bytes(C.byref(d), 2, 188) == 0  # B == G (feature.py:317-319)
+    assert lib.fsn_last_error_code() == _lib.FSN_ERR_SHAPE and b"Batch size" in lib.fsn_last_error()
+    d.norm_type = 1
+    assert lib.fsn_train_workspace_bytes(C.byref(d), 64, 188) == 0  # cumulative norm + tensor-core precision
+    assert lib.fsn_last_error_code() == _lib.FSN_ERR_UNSUPPORTED
+    with pytest.raises(NotImplementedError):
+        _lib.check_workspace(0)
+    f = _lib.FullbandDesc(num_freqs=257, hidden=512, num_layers=3, look_ahead=2, activation=0, norm_type=0)
+    assert lib.fsn_fullband_workspace_bytes(C.byref(f), 4, 100) > 0
+    f.num_layers = 9
+    assert lib.fsn_fullband_workspace_bytes(C.byref(f), 4, 100) == 0 and lib.fsn_last_error_code() == _lib.FSN_ERR_UNSUPPORTED
+
+
+def test_write_wav_roundtrip(tmp_path):
+    import wave
+    from fullsubnet_b200.inferencer import Inferencer
+    pcm = (np.arange(-500, 500) * 30).astype(np.int16)
+    Inferencer.write_wav(tmp_path / "x.wav", pcm, 48000)
+    with wave.open(str(tmp_path / "x.wav")) as f:
+        assert (f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()) == (1, 2, 48000, 1000)
+        assert np.array_equal(np.frombuffer(f.readframes(1000), dtype="<i2"), pcm)

@@ -332,3 +332,42 @@ def test_improved_fullsubnet_960_matches_reference(golden, dev):
     err = np.abs(wav.cpu().numpy() - g["wav"]).max()
     print(f"improved_fullsubnet n_fft=960: waveform max-abs {err:.2e} (scale {np.abs(g['wav']).max():.2e})")
     assert err < WAV_TOL
+
+
+# ------------------------------------------------------------------ fullband_baseline
+def test_fullband_baseline_matches_reference(golden, dev):
+    from fullsubnet_b200.fullband_baseline.model import Model
+    from oracle import fullband_baseline_oracle as BO
+    g = golden("fullband_baseline")
+    small = dict(BO.DEFAULT_FBB_ARGS, num_freqs=33, hidden_size=32, output_activate_function="ReLU",
+                 norm_type="cumulative_laplace_norm")
+    for tag, a in (("small", small), ("full", dict(BO.DEFAULT_FBB_ARGS))):
+        m = Model(**a)
+        m.load_state_dict(BO.make_fbb_state_dict(seed=11, args=a), strict=True)
+        m = m.to(dev).eval()
+        with torch.no_grad():
+            out = m(T(g[tag + "_mag"], dev))
+            one = m(T(g[tag + "_mag"], dev)[1:2])
+        assert out.shape == g[tag + "_out"].shape
+        assert rel_max(out.cpu(), g[tag + "_out"]) < 2e-5, tag
+        assert rel_max(one.cpu(), g[tag + "_out"][1:2]) < 2e-5, tag
+
+
+# ------------------------------------------------------------------ host loop: int16 scaling
+def test_peak_normalize_int16_matches_numpy(dev, tmp_path):
+    from fullsubnet_b200.inferencer import Inferencer
+    from oracle import fullsubnet_oracle as O
+    m = _full_model(dev, 1.0, "auto")
+    inf = Inferencer(model=m, device=dev)
+    y = O.make_noisy(3, 6000, seed=5, speechlike=True)
+    pcm = inf.enhance_to_pcm(y).cpu().numpy()
+    enhanced = inf.enhance_batch(y).cpu().numpy()
+    amp = np.iinfo(np.int16).max
+    for i in range(3):  # base_inferencer.py:181-182 per clip
+        ref = np.int16(0.8 * amp * enhanced[i] / np.max(np.abs(enhanced[i])))
+        assert np.array_equal(pcm[i], ref), int(np.abs(pcm[i].astype(np.int32) - ref).max())
+    assert np.abs(pcm).max(axis=1).tolist() == [26213] * 3
+    inf.write_wav(tmp_path / "a.wav", pcm[0], 16000)
+    import wave
+    with wave.open(str(tmp_path / "a.wav")) as f:
+        assert f.getframerate() == 16000 and f.getnframes() == 6000 and f.getsampwidth() == 2

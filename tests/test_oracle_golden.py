@@ -226,3 +226,14 @@ def test_improved_fullsubnet_960_oracle_matches_reference(golden):
     assert np.abs(wav.numpy() - g["wav"]).max() < 2e-6 * max(1.0, np.abs(g["wav"]).max())
     mag, _, re, im = O.stft(T(g["y"]), 960, 480, 960)
     assert rel_max(re, g["real"]) < 5e-6 and rel_max(im, g["imag"]) < 5e-6 and rel_max(mag, g["mag"]) < 5e-6
+
+
+def test_fullband_baseline_oracle_matches_reference(golden):
+    """3 x LSTM + Linear(2F) (fullband_baseline/model.py:8-68), both norms."""
+    from oracle import fullband_baseline_oracle as BO
+    g = golden("fullband_baseline")
+    small = dict(BO.DEFAULT_FBB_ARGS, num_freqs=33, hidden_size=32, output_activate_function="ReLU",
+                 norm_type="cumulative_laplace_norm")
+    for tag, a in (("small", small), ("full", dict(BO.DEFAULT_FBB_ARGS))):
+        out = BO.fbb_forward(T(g[tag + "_mag"]), BO.make_fbb_state_dict(seed=11, args=a), a)
+        assert out.shape == g[tag + "_out"].shape and rel_max(out, g[tag + "_out"]) < 2e-5, tag
