@@ -72,7 +72,7 @@ class ImprovedDesc(C.Structure):
                 ("sb_num_center", C.c_int32 * IMP_MAX_SECTIONS), ("sb_num_neighbor", C.c_int32 * IMP_MAX_SECTIONS),
                 ("fb_num_center", C.c_int32 * IMP_MAX_SECTIONS), ("fb_num_neighbor", C.c_int32 * IMP_MAX_SECTIONS),
                 ("fb_hidden", C.c_int32), ("sb_hidden", C.c_int32), ("fb_activation", C.c_int32),
-                ("sb_activation", C.c_int32)]
+                ("sb_activation", C.c_int32), ("precision", C.c_int32)]
 
 
 class ImprovedWeights(C.Structure):

@@ -83,6 +83,15 @@ __global__ void imp_fc_step_kernel(const float* __restrict__ h, int R, int H, co
   }
 }
 
+// X[t][r][w] *= inv[b(r)] with r = b*N + n: element i of the [T, R*W] tensor belongs to clip (i % (R*W)) / (N*W)
+__global__ void imp_scale_rows_kernel(float* __restrict__ X, const float* __restrict__ inv, size_t n, size_t per_t,
+                                      size_t per_clip, int B) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = (i % per_t) / per_clip;
+    X[i] *= inv[b < (size_t)B ? b : 0];
+  }
+}
+
 struct ImpDims { int B, L, T, F, Fu, S; SecGeom sec[FSN_IMP_MAX_SECTIONS]; int maxRW, maxR; };
 
 struct ImpWs {
@@ -92,6 +101,8 @@ struct ImpWs {
   unsigned int* barrier;
   float *h0[2], *h1[2], *c0, *c1;
   float *fbs_h0[2], *fbs_c0, *fbs_c1;  // per-step full-band fallback
+  LayerSave tc;                        // FSN_PREC_TF32_TC: gates / cell / hidden of every step of one layer
+  float *tc_h1, *tc_rec;
   size_t bytes;
 };
 
@@ -114,6 +125,8 @@ static int imp_dims(const fsn_improved_desc* d, int B, int L, ImpDims& m) {
               d->n_fft);
   FSN_REQUIRE(d->num_freqs == d->n_fft / 2 + 1, FSN_ERR_SHAPE, "improved model: num_freqs != n_fft/2+1");
   FSN_REQUIRE(d->num_sections >= 1 && d->num_sections <= FSN_IMP_MAX_SECTIONS, FSN_ERR_SHAPE, "improved model: sections");
+  FSN_REQUIRE(d->precision == FSN_PREC_FP32 || (d->precision == FSN_PREC_TF32_TC && (d->sb_hidden & 3) == 0),
+              FSN_ERR_UNSUPPORTED, "improved model: precision must be FSN_PREC_FP32 or FSN_PREC_TF32_TC (sb_hidden %% 4 == 0)");
   m.B = B; m.L = L; m.T = 1 + L / d->hop_length; m.F = d->num_freqs; m.Fu = m.F - 1; m.S = d->num_sections;
   m.maxRW = 0; m.maxR = 0;
   for (int s = 0; s < m.S; ++s) {
@@ -152,6 +165,15 @@ static void imp_carve(const fsn_improved_desc* d, const ImpDims& m, void* base, 
   const size_t BH = (size_t)m.B * d->fb_hidden;
   w.fbs_h0[0] = c.take<float>(BH); w.fbs_h0[1] = c.take<float>(BH);
   w.fbs_c0 = c.take<float>(BH); w.fbs_c1 = c.take<float>(BH);
+  w.tc.G = w.tc.C = w.tc.H = w.tc_h1 = w.tc_rec = nullptr;
+  if (d->precision == FSN_PREC_TF32_TC) {
+    const size_t TR = (size_t)m.T * m.B * m.maxR;
+    w.tc.G = c.take<float>(TR * 4 * d->sb_hidden);
+    w.tc.C = c.take<float>(TR * d->sb_hidden);
+    w.tc.H = c.take<float>(TR * d->sb_hidden);
+    w.tc_h1 = c.take<float>(TR * d->sb_hidden);
+    w.tc_rec = c.take<float>(4 * RH);
+  }
   w.bytes = c.off;
 }
 
@@ -234,6 +256,26 @@ extern "C" int fsn_improved_forward(const fsn_improved_desc* d, const fsn_improv
     if ((rc = clip_reduce_only_launch(w.fs, B, T, w.sums, st))) return rc;
     if ((rc = norm_scales_launch(w.sums, w.sums, B, (float)g.N * g.W * T, 1.f, w.invs, nullptr, st, eps))) return rc;
     const fsn_seq_weights& sw = wt->sb[s];
+    if (d->precision == FSN_PREC_TF32_TC) {
+      // layer by layer over all steps: hoisted input projection + per-step recurrent GEMM on tcgen05 (tf32), fused cell
+      LayerSave l1{w.tc.G, w.tc.C, w.tc_h1};
+      {  // scale X by the section norm in place (the tensor-core GEMM reads plain fp32 rows)
+        const size_t n = (size_t)T * R * g.W;
+        int blocks = (int)((n + 255) / 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        imp_scale_rows_kernel<<<blocks, 256, 0, st>>>(w.X, w.invs, n, (size_t)R * g.W, (size_t)g.N * g.W, B);
+        FSN_CHECK_LAUNCH("imp_scale_rows_kernel");
+      }
+      if ((rc = layer_forward_save_tc(&sw, 0, w.X, R, g.W, Hs, T, w.tc, w.tc_rec, st))) return rc;
+      if ((rc = layer_forward_save_tc(&sw, 1, w.tc.H, R, Hs, Hs, T, l1, w.tc_rec, st))) return rc;
+      for (int t = 0; t < T; ++t) {
+        const size_t warps = (size_t)R * 2 * g.cs;
+        imp_fc_step_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(w.tc_h1 + (size_t)t * R * Hs, R, Hs, sw.fc_w, sw.fc_b,
+                                                                    g.cs, g.N, g.lo, d->sb_activation, crm, F, T, t);
+        FSN_CHECK_LAUNCH("imp_fc_step_kernel");
+      }
+      continue;
+    }
     for (int t = 0; t < T; ++t) {
       StepParams p;
       memset(&p, 0, sizeof(p));

@@ -58,6 +58,13 @@ bool tgemm_supported(const float* A, size_t lda, const float* Bm, size_t ldb, in
 int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float* C, size_t ldc, int M, int N, int K,
                  bool accumulate, float* scratch, size_t scratch_floats, cudaStream_t st);
 
+// one LSTM layer over all steps on the tf32 tensor-core path (fsn_train.cu): input projection of all steps hoisted
+// into one GEMM, then per step the recurrent GEMM into `rec` [R,4H] and the fused cell kernel.  G [Tp,R,4H]
+// (post-activation gates), C, H [Tp,R,H] receive every step.  X [Tp,R,K0] contiguous.
+struct LayerSave { float *G, *C, *H; };
+int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R, int K0, int H, int Tp,
+                          const LayerSave& s, float* rec, cudaStream_t st);
+
 // shapes of one Model.forward call (fsn_model.cu)
 struct Dims {
   int B, T, Tp, F, Fsub, G, R, Ksb;

@@ -406,7 +406,6 @@ __global__ void train_dfbz_kernel(const float* __restrict__ dX, const float* __r
 }
 
 // ------------------------------------------------------------------------------------------ workspace
-struct LayerSave { float *G, *C, *H; };
 
 struct TrainWs {
   float *raw, *xfb, *fbz, *inv1, *inv2;
@@ -497,7 +496,7 @@ static int layer_forward_save(const fsn_seq_weights* w, int l, const float* X, i
 
 // tensor-core variant: input projection of ALL steps as one GEMM into the gate buffer, then per step
 // G_t += h_{t-1} W_hh^T (tcgen05 tf32) and the fused cell kernel
-static int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R, int K0, int H, int Tp,
+int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R, int K0, int H, int Tp,
                                  const LayerSave& s, float* rec, cudaStream_t st) {
   int rc;
   const int rows = Tp * R;

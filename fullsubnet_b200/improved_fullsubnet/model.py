@@ -6,6 +6,7 @@ Same constructor kwargs and ``state_dict`` keys (``fb_model.*``, ``sb_model.sb_m
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -56,6 +57,17 @@ class Model(BaseModel):
             # model.py:226-236 also offers cumulative_laplace_norm / offline_gaussian_norm
             raise NotImplementedError("libfsn_b200 builds offline_laplace_norm for improved_fullsubnet")
         self.norm_type = norm_type
+        # arithmetic of the sub-band sections (98 % of the FLOPs): "fp32" (FMA kernels), "tf32_tc" (tcgen05 kind::tf32
+        # GEMMs, fp32 accumulate; waveform within 1e-4 of the reference) or "auto" (= tf32_tc when sb_hidden % 4 == 0)
+        self.precision = os.environ.get("FSN_IMPROVED_PRECISION", "auto")
+
+    def _resolve_precision(self) -> str:
+        ok = self.sb_model.sb_models[0].hidden_size % 4 == 0
+        if self.precision == "auto":
+            return "tf32_tc" if ok else "fp32"
+        if self.precision not in ("fp32", "tf32_tc"):
+            raise ValueError("precision must be 'fp32', 'tf32_tc' or 'auto'")
+        return self.precision
 
     def _structs(self):
         sb = self.sb_model
@@ -63,7 +75,8 @@ class Model(BaseModel):
                               num_freqs=self.num_freqs, fdrc=float(self.fdrc), num_sections=len(sb.sb_models),
                               fb_hidden=self.fb_model.hidden_size, sb_hidden=sb.sb_models[0].hidden_size,
                               fb_activation=_lib.ACT[self.fb_model.output_activate_function],
-                              sb_activation=_lib.ACT[sb.sb_models[0].output_activate_function])
+                              sb_activation=_lib.ACT[sb.sb_models[0].output_activate_function],
+                              precision=_lib.PREC[self._resolve_precision()])
         for s in range(len(sb.sb_models)):
             if s < len(sb.freq_cutoffs):
                 d.freq_cutoffs[s] = sb.freq_cutoffs[s]

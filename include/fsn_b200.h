@@ -211,6 +211,7 @@ typedef struct fsn_improved_desc {
   int32_t sb_num_center[FSN_IMP_MAX_SECTIONS], sb_num_neighbor[FSN_IMP_MAX_SECTIONS];
   int32_t fb_num_center[FSN_IMP_MAX_SECTIONS], fb_num_neighbor[FSN_IMP_MAX_SECTIONS];
   int32_t fb_hidden, sb_hidden, fb_activation, sb_activation;
+  int32_t precision; /* FSN_PREC_FP32, or FSN_PREC_TF32_TC: the sub-band sections' GEMMs on tcgen05 kind::tf32 */
 } fsn_improved_desc;
 
 typedef struct fsn_improved_weights {

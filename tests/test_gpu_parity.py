@@ -252,14 +252,16 @@ def test_fast_fullsubnet_matches_reference(golden, dev, precision, tol):
 
 
 # ------------------------------------------------------------------ improved_fullsubnet (config 5, A14)
+@pytest.mark.parametrize("prec", ["fp32", "tf32_tc"])
 @pytest.mark.parametrize("tag", ["k16", "k48"])
-def test_improved_fullsubnet_matches_reference(golden, dev, tag):
+def test_improved_fullsubnet_matches_reference(golden, dev, tag, prec):
     from fullsubnet_b200.improved_fullsubnet.model import Model
     from oracle import improved_fullsubnet_oracle as IO
     g = golden("improved")
     args = IO.DEFAULT_IMPROVED_ARGS if tag == "k16" else IO.ARGS_48K_1024
     m = Model(**args)
     m.load_state_dict(IO.make_improved_state_dict(seed=5, args=args), strict=True)
+    m.precision = prec
     m = m.to(dev).eval()
     y = T(g[tag + "_y"], dev)
     with torch.no_grad():
@@ -267,7 +269,9 @@ def test_improved_fullsubnet_matches_reference(golden, dev, tag):
         wav3 = m(y.unsqueeze(1)[:1])
     assert wav.shape == g[tag + "_wav"].shape
     err = np.abs(wav.cpu().numpy() - g[tag + "_wav"]).max()
-    print(f"improved_fullsubnet {tag}: waveform max-abs {err:.2e} (scale {np.abs(g[tag + '_wav']).max():.2e})")
+    print(f"improved_fullsubnet {tag} {prec}: waveform max-abs {err:.2e} (scale {np.abs(g[tag + '_wav']).max():.2e})")
+    if prec == "fp32":
+        assert err < 1e-6
     assert err < WAV_TOL
     assert np.abs(wav3.cpu().numpy() - g[tag + "_wav"][:1]).max() < WAV_TOL
     # bad section geometry: ValueError like the reference (model.py:341-345)
