@@ -199,3 +199,30 @@ def test_write_wav_roundtrip(tmp_path):
     with wave.open(str(tmp_path / "x.wav")) as f:
         assert (f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()) == (1, 2, 48000, 1000)
         assert np.array_equal(np.frombuffer(f.readframes(1000), dtype="<i2"), pcm)
+
+
+def test_c_abi_argument_validation_without_gpu():
+    """Every entry point validates its arguments before touching CUDA: the error classes of the reference's asserts can
+    be checked on the CPU box (no kernel is launched by these calls)."""
+    import ctypes as C
+    from fullsubnet_b200 import _lib
+    lib = _lib.load()
+    assert lib.fsn_stft(None, 1, 1000, 511, 256, 511, None, None, None, None, None, 0, None) == _lib.FSN_ERR_UNSUPPORTED
+    assert b"n_fft=511" in lib.fsn_last_error()
+    assert lib.fsn_stft(None, 1, 1000, 512, 0, 512, None, None, None, None, None, 0, None) == _lib.FSN_ERR_SHAPE
+    assert lib.fsn_stft(None, 1, 100, 512, 256, 512, None, None, None, None, None, 0, None) == _lib.FSN_ERR_SHAPE  # pad >= L
+    assert lib.fsn_stft(None, 0, 1000, 960, 480, 960, None, None, None, None, None, 0, None) == _lib.FSN_ERR_SHAPE
+    assert lib.fsn_istft(None, None, 3, None, 1, 4, 512, 256, 512, 0, None, None) == _lib.FSN_ERR_SHAPE  # cstride
+    assert lib.fsn_mse_loss(None, None, 0, 4, 4, None, None, None, 0, None) == _lib.FSN_ERR_SHAPE
+    L = _lib.ParamList()
+    L.n = 1
+    assert lib.fsn_clip_adam(C.byref(L), 10.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, 0, None, None, 0, None) == _lib.FSN_ERR_SHAPE
+    L.n = _lib.MAX_PARAM_TENSORS + 1
+    assert lib.fsn_clip_adam(C.byref(L), 10.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, 1, None, None, 0, None) == _lib.FSN_ERR_SHAPE
+    assert lib.fsn_peak_normalize_int16(None, 0, 10, 1.0, None, None) == _lib.FSN_ERR_SHAPE
+    with pytest.raises(AssertionError):
+        _lib.check(_lib.FSN_ERR_SHAPE)
+    with pytest.raises(NotImplementedError):
+        _lib.check(_lib.FSN_ERR_UNSUPPORTED)
+    with pytest.raises(RuntimeError):
+        _lib.check(_lib.FSN_ERR_CUDA)
