@@ -50,7 +50,7 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 }
 
 // c[r] = #{(f,k): reflect(f+k) = r, |k| <= N}: multiplicity of row r in the unfolded tensor
-__device__ __forceinline__ int reflect_count(int r, int F, int N) {
+__host__ __device__ __forceinline__ int reflect_count(int r, int F, int N) {
   int c = 0;
   for (int k = -N; k <= N; ++k) {
     int f = r - k;                       // f + k = r

@@ -230,6 +230,21 @@ extern "C" float fsn_last_stage_ms(int stage) {
   if (cudaEventElapsedTime(&ms, g_ev[stage], g_ev[stage + 1]) != cudaSuccess) return -1.0f;
   return ms;
 }
+// host-side views of the index helpers the kernels share (tests/test_cpu_host.py checks them against the oracle)
+extern "C" int fsn_debug_row_to_unit(int B, int F, int G, int r, int* b, int* f) {
+  const int g = (B > 1 && G > 1) ? G : 1;
+  RowMap m{B, F, g > 1 ? F / g : F, g};
+  if (r < 0 || r >= B * m.Fsub) return FSN_ERR_SHAPE;
+  row_to_unit(m, r, *b, *f);
+  return FSN_OK;
+}
+extern "C" int fsn_debug_unit_to_row(int B, int F, int G, int b, int f) {
+  const int g = (B > 1 && G > 1) ? G : 1;
+  RowMap m{B, F, g > 1 ? F / g : F, g};
+  return unit_to_row(m, b, f);
+}
+extern "C" int fsn_debug_reflect_count(int r, int F, int N) { return reflect_count(r, F, N); }
+
 extern "C" int fsn_built_arch(void) {
 #ifdef FSN_BUILT_ARCH
   return FSN_BUILT_ARCH;

@@ -309,6 +309,12 @@ int fsn_fullband_forward(const fsn_fullband_desc* d, const fsn_lstm_layer* layer
  * gain = 0.8 * 32767 in the reference; float32 multiply, divide, truncation toward zero like numpy; all-zero clip -> 0 */
 int fsn_peak_normalize_int16(const float* wav, int B, int L, float gain, int16_t* out, fsn_stream_t stream);
 
+/* unit-test hooks (host code only): the drop_band row map of Model.forward and its inverse (-1 = unit dropped), and
+ * the reflect-padding multiplicity c[r] of the closed-form second norm */
+int fsn_debug_row_to_unit(int B, int F, int G, int r, int* b, int* f);
+int fsn_debug_unit_to_row(int B, int F, int G, int b, int f);
+int fsn_debug_reflect_count(int r, int F, int N);
+
 /* unit-test hook for the tf32 tcgen05 GEMM of the training path: C[M,N] (+)= A[M,K] B[N,K]^T, fp32 row-major
  * operands with 16-byte aligned rows; scratch (optional) enables split-K */
 int fsn_debug_tgemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,

@@ -226,3 +226,49 @@ def test_c_abi_argument_validation_without_gpu():
         _lib.check(_lib.FSN_ERR_UNSUPPORTED)
     with pytest.raises(RuntimeError):
         _lib.check(_lib.FSN_ERR_CUDA)
+
+
+def test_row_map_and_reflect_count_match_oracle():
+    """The drop_band row map (feature.py:332-345) and its inverse as compiled into the library vs the oracle's index
+    form; reflect multiplicity c[r] of the closed-form second norm vs the oracle and its closed values."""
+    import ctypes as C
+    from hypothesis import given, settings, strategies as st
+    from fullsubnet_b200 import _lib
+    from oracle import fullsubnet_oracle as O
+    lib = _lib.load()
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 9), st.integers(2, 40), st.integers(1, 4))
+    def check(B, F, G):
+        if B > 1 and G > 1 and B <= G:
+            return  # rejected by Model.forward (feature.py:317-319)
+        if B > 1 and G > 1:
+            sb_, sf_ = O.drop_band_index_map(B, F, G)
+            want = [(int(sb_[i]), int(f)) for i in range(len(sb_)) for f in sf_[i]]
+        else:
+            want = [(b, f) for b in range(B) for f in range(F)]
+        b, f = C.c_int(), C.c_int()
+        seen = set()
+        for r, (wb, wf) in enumerate(want):
+            assert lib.fsn_debug_row_to_unit(B, F, G, r, C.byref(b), C.byref(f)) == 0
+            assert (b.value, f.value) == (wb, wf)
+            assert lib.fsn_debug_unit_to_row(B, F, G, wb, wf) == r  # inverse
+            seen.add((wb, wf))
+        assert lib.fsn_debug_row_to_unit(B, F, G, len(want), C.byref(b), C.byref(f)) == _lib.FSN_ERR_SHAPE
+        for bb in range(B):
+            for ff in range(F):
+                if (bb, ff) not in seen:
+                    assert lib.fsn_debug_unit_to_row(B, F, G, bb, ff) == -1  # dropped unit
+    check()
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(2, 300), st.integers(0, 20))
+    def check_count(F, N):
+        if N >= F:
+            return
+        want = O.reflect_count(F, N)
+        got = [lib.fsn_debug_reflect_count(r, F, N) for r in range(F)]
+        assert got == list(want) and sum(got) == F * (2 * N + 1)
+    check_count()
+    c = [lib.fsn_debug_reflect_count(r, 257, 15) for r in range(257)]
+    assert c[0] == c[256] == 16 and set(c[1:16]) == {32} and set(c[16:241]) == {31}  # SURVEY A6
