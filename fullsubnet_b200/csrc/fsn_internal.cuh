@@ -65,6 +65,11 @@ struct LayerSave { float *G, *C, *H; };
 int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R, int K0, int H, int Tp,
                           const LayerSave& s, float* rec, cudaStream_t st);
 
+// EXPERIMENTAL, off unless FSN_TGEMM_MN=1 (not yet run on hardware): C[M,N] (+)= A^T B with A [K,M], B [K,N] (MN-major)
+bool tgemm_mn_enabled();
+int tgemm_mn_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float* C, size_t ldc, int M, int N, int K,
+                    bool accumulate, float* scratch, size_t scratch_floats, cudaStream_t st);
+
 // shapes of one Model.forward call (fsn_model.cu)
 struct Dims {
   int B, T, Tp, F, Fsub, G, R, Ksb;

@@ -319,6 +319,10 @@ int fsn_debug_reflect_count(int r, int F, int N);
  * operands with 16-byte aligned rows; scratch (optional) enables split-K */
 int fsn_debug_tgemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
                     int K, int accumulate, float* scratch, int64_t scratch_floats, fsn_stream_t stream);
+/* EXPERIMENTAL (not yet run on hardware; nothing calls it unless FSN_TGEMM_MN=1): the MN-major variant,
+ * C[M,N] (+)= A^T B with A stored [K,M] and B stored [K,N] */
+int fsn_debug_tgemm_mn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
+                       int K, int accumulate, float* scratch, int64_t scratch_floats, fsn_stream_t stream);
 
 #ifdef __cplusplus
 }
