@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libfsn_b200.so")
 
 FSN_OK, FSN_ERR_SHAPE, FSN_ERR_UNSUPPORTED, FSN_ERR_CUDA, FSN_ERR_WORKSPACE = 0, 1, 2, 3, 4
 ACT = {None: 0, False: 0, "": 0, "ReLU": 1, "Tanh": 2, "ReLU6": 3}
-PREC = {"fp32": 0, "f16_tc": 1, "tf32_tc": 2}
+PREC = {"fp32": 0, "f16_tc": 1, "tf32_tc": 2, "f16x3_tc": 3}
 
 
 class ModelDesc(C.Structure):

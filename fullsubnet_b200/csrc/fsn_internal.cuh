@@ -119,6 +119,7 @@ struct SbTcArgs {
   int B, F, Tp, la, Ns, Nf, H, act;
   int steps, shrink;      // pair kernel only: LSTM steps (0 = Tp) and time down-sampling of the gathered input (0/1 = none)
   bool pair;              // packed for / run by the CTA-pair kernel
+  bool x3;                // pair kernel only: error-compensated variant (FSN_PREC_F16X3_TC image)
   RowMap map;
 };
 size_t sb_tc_packed_bytes(const fsn_model_desc* d);
@@ -128,10 +129,10 @@ bool sb_tc_supported(const fsn_model_desc* d);
 
 // CTA-pair (cta_group::2) variant (fsn_subband_tc2.cu); preferred when the shape allows (H = 384)
 bool sb_tc2_supported(const fsn_model_desc* d);
-size_t sb_tc2_packed_bytes();
+size_t sb_tc2_packed_bytes(bool x3 = false);
 int sb_tc2_pack(const fsn_model_desc* d, const fsn_seq_weights* sb, void* packed, cudaStream_t st);
 int sb_tc2_forward(const SbTcArgs& a, cudaStream_t st);
-int sb_tc2_pack_raw(const fsn_seq_weights* sb, int Ksb, int fc_out, void* packed, cudaStream_t st);
+int sb_tc2_pack_raw(const fsn_seq_weights* sb, int Ksb, int fc_out, void* packed, cudaStream_t st, bool x3 = false);
 bool sb_tc2_enabled();  // H = 384 stacks may use the pair kernel (FSN_TC_PAIR != 0)
 
 }  // namespace fsn

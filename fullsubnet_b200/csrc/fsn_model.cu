@@ -172,13 +172,13 @@ static int model_core(const fsn_model_desc* d, const fsn_seq_weights* fb, const 
   if (cum && (rc = cum_unit_scale_launch(w.magT, w.fbT, map, m.R, Tp, d->sb_num_neighbors, d->fb_num_neighbors, cum_eps,
                                          w.cum2, st)))
     return rc;
-  if (d->precision == FSN_PREC_F16_TC) {
-    FSN_REQUIRE(sb_packed, FSN_ERR_SHAPE, "model: FSN_PREC_F16_TC needs packed sub-band weights");
+  if (d->precision == FSN_PREC_F16_TC || d->precision == FSN_PREC_F16X3_TC) {
+    FSN_REQUIRE(sb_packed, FSN_ERR_SHAPE, "model: the tensor-core precisions need packed sub-band weights");
     SbTcArgs a;
     memset(&a, 0, sizeof(a));
     a.packed = sb_packed; a.magT = w.magT; a.fbT = w.fbT; a.inv2 = w.inv2; a.crm = crm;
     a.B = B; a.F = F; a.Tp = Tp; a.la = d->look_ahead; a.Ns = d->sb_num_neighbors; a.Nf = d->fb_num_neighbors;
-    a.H = Hs; a.act = d->sb_activation; a.map = map; a.pair = sb_tc2_supported(d);
+    a.H = Hs; a.act = d->sb_activation; a.map = map; a.pair = sb_tc2_supported(d); a.x3 = d->precision == FSN_PREC_F16X3_TC;
     rc = sb_tc_forward(a, st);
     prof_mark(3, st);
     return rc;
@@ -276,7 +276,7 @@ extern "C" int fsn_model_forward(const fsn_model_desc* d, const fsn_seq_weights*
   int rc = make_dims(d, B, T, m);
   if (rc) return rc;
   FSN_REQUIRE(d->precision == FSN_PREC_FP32 || sb_tc_supported(d), FSN_ERR_UNSUPPORTED,
-              "FSN_PREC_F16_TC needs sb_hidden %% 128 == 0 and sub-band input width <= 32");
+              "FSN_PREC_F16_TC needs sb_hidden %% 128 == 0 (FSN_PREC_F16X3_TC: sb_hidden = 384) and sub-band input width <= 32");
   ModelWs w;
   carve_model(d, m, workspace, w);
   FSN_REQUIRE(workspace && workspace_bytes >= w.bytes, FSN_ERR_WORKSPACE, "workspace too small: %zu < %zu",
@@ -338,7 +338,7 @@ extern "C" int fsn_enhance(const fsn_model_desc* d, const fsn_seq_weights* fb, c
   int rc = carve_enhance(&dd, B, L, n_fft, hop, workspace, e, m);
   if (rc) return rc;
   FSN_REQUIRE(dd.precision == FSN_PREC_FP32 || sb_tc_supported(&dd), FSN_ERR_UNSUPPORTED,
-              "FSN_PREC_F16_TC needs sb_hidden %% 128 == 0 and sub-band input width <= 32");
+              "FSN_PREC_F16_TC needs sb_hidden %% 128 == 0 (FSN_PREC_F16X3_TC: sb_hidden = 384) and sub-band input width <= 32");
   FSN_REQUIRE(workspace && workspace_bytes >= e.bytes, FSN_ERR_WORKSPACE, "workspace too small: %zu < %zu",
               workspace_bytes, e.bytes);
   ModelWs w;

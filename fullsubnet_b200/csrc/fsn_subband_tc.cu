@@ -676,12 +676,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
 
 bool sb_tc_supported(const fsn_model_desc* d) {
   const int Ksb = (2 * d->sb_num_neighbors + 1) + (2 * d->fb_num_neighbors + 1);
+  if (d->precision == FSN_PREC_F16X3_TC) return sb_tc2_supported(d);  // compensated variant: pair kernel only
   return d->sb_hidden % 128 == 0 && d->sb_hidden / 128 <= tc::MAX_MT && d->sb_hidden >= 128 && Ksb <= tc::KS;
 }
 
 size_t sb_tc_packed_bytes(const fsn_model_desc* d) {
   if (!sb_tc_supported(d)) return 0;
-  if (sb_tc2_supported(d)) return sb_tc2_packed_bytes();
+  if (sb_tc2_supported(d)) return sb_tc2_packed_bytes(d->precision == FSN_PREC_F16X3_TC);
   const int Ksb = (2 * d->sb_num_neighbors + 1) + (2 * d->fb_num_neighbors + 1);
   return tc::packed_layout(d->sb_hidden, Ksb).bytes;
 }

@@ -95,7 +95,12 @@ class Model(BaseModel):
         self.norm_type = norm_type
         self.norm = self.norm_wrapper(norm_type)
         self.num_groups_in_drop_band = num_groups_in_drop_band
-        # arithmetic of the sub-band stack: "fp32" or "f16_tc" (tcgen05, fp16 operands / fp32 accumulate)
+        # arithmetic of the sub-band stack (99 % of the FLOPs):
+        #   "fp32"     fp32 FMA kernels
+        #   "f16x3_tc" tcgen05, fp16 hi+lo split of weights and state, 3 MMAs per product: the fp32 error class
+        #              (cRM ~1e-6 rel, waveform <= 1e-4 abs even where decompress_cIRM amplifies x100)
+        #   "f16_tc"   tcgen05, single fp16 pass: 3x faster, cRM within 1e-3 rel; opt-in
+        #   "auto"     f16x3_tc when the shape allows, else fp32 -- the default never trades the reference's accuracy
         self.precision = precision or os.environ.get("FSN_PRECISION", "auto")
         # arithmetic of the training step's GEMMs: "fp32" (FMA) or "tf32_tc" (tcgen05 kind::tf32); the reference
         # trains under fp16 autocast (trainer.py:56), so both are at least its precision
@@ -108,13 +113,13 @@ class Model(BaseModel):
     # ---------------------------------------------------------------- C-ABI plumbing
     def _resolve_precision(self) -> str:
         if self.precision != "auto":
-            if self.precision not in ("fp32", "f16_tc"):
-                raise ValueError("precision must be 'fp32', 'f16_tc' or 'auto'")
+            if self.precision not in ("fp32", "f16_tc", "f16x3_tc"):
+                raise ValueError("precision must be 'fp32', 'f16x3_tc', 'f16_tc' or 'auto'")
             return self.precision
         if self.norm_type == "cumulative_laplace_norm":  # per-step scales: built for the fp32 kernels
             return "fp32"
-        d = self._desc("f16_tc", 1)
-        return "f16_tc" if _lib.load().fsn_sb_packed_bytes(C.byref(d)) > 0 else "fp32"
+        d = self._desc("f16x3_tc", 1)
+        return "f16x3_tc" if _lib.load().fsn_sb_packed_bytes(C.byref(d)) > 0 else "fp32"
 
     def _resolve_train_precision(self) -> str:
         if self.train_precision == "auto":
@@ -134,7 +139,7 @@ class Model(BaseModel):
 
     def _packed_sb(self, desc, sb_w, device):
         """Tile-ordered fp16 image of the sub-band weights, rebuilt when any parameter changes."""
-        key = (self.sb_model.version_key(), str(device))
+        key = (self.sb_model.version_key(), str(device), int(desc.precision))
         if self._packed is None or self._packed_key != key:
             lib = _lib.load()
             n = lib.fsn_sb_packed_bytes(C.byref(desc))
@@ -147,7 +152,7 @@ class Model(BaseModel):
         prec = self._resolve_precision()
         desc = self._desc(prec, num_groups)
         fb_w, sb_w = self.fb_model.weight_struct(), self.sb_model.weight_struct()
-        packed = self._packed_sb(desc, sb_w, device) if prec == "f16_tc" else None
+        packed = self._packed_sb(desc, sb_w, device) if prec in ("f16_tc", "f16x3_tc") else None
         return desc, fb_w, sb_w, packed
 
     # ---------------------------------------------------------------- reference API

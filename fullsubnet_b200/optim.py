@@ -17,11 +17,28 @@ class FusedClipAdam(torch.optim.Optimizer):
         self.last_norm = None  # device tensor [2]: total gradient norm, applied coefficient
         self._scratch = None
 
+    def _merged_groups(self):
+        """clip_grad_norm_(model.parameters()) clips by the GLOBAL norm over every parameter (trainer.py:65-67), and
+        one fsn_clip_adam call computes one norm: groups that share their hyper-parameters are merged into one call;
+        groups that differ cannot share a launch."""
+        groups = [g for g in self.param_groups if any(p.grad is not None for p in g["params"])]
+        if len(groups) <= 1:
+            return groups
+        keys = {(g["lr"], tuple(g["betas"]), g["eps"]) for g in groups}
+        if len(keys) > 1 and self.max_norm:
+            raise NotImplementedError("FusedClipAdam: param groups with different lr/betas/eps cannot share the global "
+                                      "gradient norm of one fsn_clip_adam call; use one group or max_norm=None")
+        if len(keys) > 1:
+            return groups
+        merged = dict(groups[0])
+        merged["params"] = [p for g in groups for p in g["params"]]
+        return [merged]
+
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
         assert closure is None
         lib = _lib.load()
-        for group in self.param_groups:
+        for group in self._merged_groups():
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
                 continue
@@ -54,4 +71,7 @@ class FusedClipAdam(torch.optim.Optimizer):
                 _lib.check(lib.fsn_clip_adam(C.byref(L), float(self.max_norm or 0.0), float(grad_scale), group["lr"],
                                              b1, b2, group["eps"], step, self.last_norm.data_ptr(),
                                              self._scratch.data_ptr(), self._scratch.numel(), _lib.stream_ptr(device)))
+            # the kernel wrote through raw pointers: tell autograd / the packed-weight caches (keyed on
+            # (data_ptr, _version), fullsubnet/model.py:_packed_sb) that the parameters changed
+            torch._C._increment_version(ps)
         return None

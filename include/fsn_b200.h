@@ -47,8 +47,12 @@ enum { FSN_NORM_OFFLINE_LAPLACE = 0, FSN_NORM_CUMULATIVE_LAPLACE = 1 };
  *                       time and of the weight gradients on tcgen05 kind::tf32 (fp32 data read as tf32, fp32
  *                       accumulate in TMEM); gate / cell arithmetic and all reductions stay fp32
  *   FSN_PREC_F16_TC   - fp16 operands (11-bit significand, like TF32) x fp32 accumulate on the
- *                       tcgen05 tensor cores, fp32 cell state; cRM within 1e-3 rel (tests) */
-enum { FSN_PREC_FP32 = 0, FSN_PREC_F16_TC = 1, FSN_PREC_TF32_TC = 2 };
+ *                       tcgen05 tensor cores, fp32 cell state; cRM within 1e-3 rel (tests)
+ *   FSN_PREC_F16X3_TC - error-compensated tensor-core path: weights and state split into fp16 hi + lo terms, every
+ *                       product issued as W_hi.S_hi + W_hi.S_lo + W_lo.S_hi into one fp32 TMEM accumulator (22
+ *                       significand bits per operand), libm-class gate functions; the fp32 error class (cRM ~1e-6
+ *                       rel), needed where decompress_cIRM amplifies mask errors x100 (|cRM| near the 9.9 clip) */
+enum { FSN_PREC_FP32 = 0, FSN_PREC_F16_TC = 1, FSN_PREC_TF32_TC = 2, FSN_PREC_F16X3_TC = 3 };
 
 int fsn_version(void);
 const char* fsn_last_error(void);
@@ -127,8 +131,9 @@ typedef struct fsn_seq_weights {
 /* bytes of caller-provided scratch for fsn_model_forward / fsn_enhance at batch B, T frames */
 size_t fsn_model_workspace_bytes(const fsn_model_desc* d, int B, int T);
 
-/* FSN_PREC_F16_TC only: bytes of, and packer for, the tile-ordered fp16 image of the sub-band
- * weights that the tcgen05 kernel streams (cache it keyed on the parameters' version). */
+/* FSN_PREC_F16_TC / FSN_PREC_F16X3_TC only: bytes of, and packer for, the tile-ordered fp16 image of the sub-band
+ * weights that the tcgen05 kernel streams (cache it keyed on the parameters' version AND the precision: the
+ * compensated image carries a hi and a lo stage per k range). */
 size_t fsn_sb_packed_bytes(const fsn_model_desc* d);
 int fsn_pack_sb_weights(const fsn_model_desc* d, const fsn_seq_weights* sb, void* packed, fsn_stream_t stream);
 

@@ -134,13 +134,18 @@ def _full_model(dev, gain, precision):
     return make_model(dict(O.DEFAULT_MODEL_ARGS), O.make_state_dict(seed=0, sb_fc_gain=gain), dev, precision)
 
 
-@pytest.mark.parametrize("precision,crm_tol", [("fp32", 5e-5), ("f16_tc", CRM_TOL)])
+@pytest.mark.parametrize("precision,crm_tol", [("fp32", 5e-5), ("f16x3_tc", 5e-5), ("auto", 5e-5)])
 @pytest.mark.parametrize("tag,gain", [("wa", 1.0), ("wb", WB_GAIN)])
 def test_full_model_and_inferencer_match_reference(golden, dev, tag, gain, precision, crm_tol):
+    """Both north-star gates (cRM <= 1e-3 rel -- held to 5e-5 here -- and waveform <= 1e-4 abs) on BOTH weight
+    sets, W-b being the set whose cRM reaches the +-9.9 clip where decompress_cIRM has gain ~100
+    (mask.py:58-63).  `auto` (the default precision) resolves to the error-compensated tensor-core path."""
     from fullsubnet_b200.acoustics.feature import stft
     from fullsubnet_b200.inferencer import Inferencer
     g = golden("model_full")
     m = _full_model(dev, gain, precision)
+    if precision == "auto":
+        assert m._resolve_precision() == "f16x3_tc"
     y = T(g["y"], dev)
     ref_crm, ref_wav = g[f"{tag}_crm"], g[f"{tag}_wav"]
     with torch.no_grad():
@@ -151,18 +156,25 @@ def test_full_model_and_inferencer_match_reference(golden, dev, tag, gain, preci
     wav = np.stack([inf.full_band_crm_mask(y[i:i + 1], {}) for i in range(2)])  # op-by-op reference flow
     fused, crm2 = m.enhance(y, return_crm=True)  # one fsn_enhance call, batched
     assert rel_max(crm2.cpu(), ref_crm) < crm_tol
-    scale = max(1.0, float(np.abs(ref_wav).max()))
-    if precision == "f16_tc" and tag == "wb":
-        # adversarial weight set: |cRM| reaches the +-9.9 clip where decompress_cIRM has gain 2K^2/(K^2-m^2) ~ 100,
-        # so the 11-bit-significand operand rounding (cRM still within 1e-3) is amplified in the waveform.
-        # The fp32 path meets 1e-4 here; the tensor-core path is held to 1 % of the waveform's L2 norm.
-        assert rel_l2(wav, ref_wav) < 1e-2 and rel_l2(fused.cpu(), ref_wav) < 1e-2
-    else:
-        assert np.abs(wav - ref_wav).max() < WAV_TOL * scale
-        assert np.abs(fused.cpu().numpy() - ref_wav).max() < WAV_TOL * scale
+    assert np.abs(wav - ref_wav).max() < WAV_TOL
+    assert np.abs(fused.cpu().numpy() - ref_wav).max() < WAV_TOL
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("f16_tc", WAV_TOL)])
+def test_single_pass_f16_is_opt_in_and_meets_the_mask_gate(golden, dev):
+    """precision="f16_tc" (one fp16 MMA pass, 3x the speed) is never chosen by `auto`.  It meets the cRM gate on both
+    weight sets and the waveform gate on W-a; on W-b its 11-bit operand rounding is amplified x100 by
+    decompress_cIRM near the clip, which is exactly why the default is the compensated path."""
+    g = golden("model_full")
+    y = T(g["y"], dev)
+    for tag, gain in (("wa", 1.0), ("wb", WB_GAIN)):
+        m = _full_model(dev, gain, "f16_tc")
+        fused, crm = m.enhance(y, return_crm=True)
+        assert rel_max(crm.cpu(), g[f"{tag}_crm"]) < CRM_TOL and rel_l2(crm.cpu(), g[f"{tag}_crm"]) < CRM_TOL
+        if tag == "wa":
+            assert np.abs(fused.cpu().numpy() - g["wa_wav"]).max() < WAV_TOL
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("f16x3_tc", 2e-5), ("f16_tc", WAV_TOL)])
 def test_batched_equals_loop_of_single_clips(dev, precision, tol):
     """batched inference == loop of B=1 calls (drop_band off)."""
     from oracle import fullsubnet_oracle as O
