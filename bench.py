@@ -1,7 +1,7 @@
 """bench.py - FullSubNet inference throughput on B200 (BASELINE.json metric: frames/s and x real-time,
 16 kHz, n_fft=512, hop=256) for the workload `configs[1]`: batch = 256 x 4 s synthetic clips per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--precision auto|fp32|f16_tc]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--precision auto|fp32|f16x3_tc|f16_tc] [--no-extras]
   python bench.py --impl reference      # the CPU arm (oracle port of the reference path, all host threads)
 
 One "step" = one pass of the hot path (stft -> model -> decompress/mask -> istft) over one batch.
@@ -74,43 +74,63 @@ class ClockSampler:
 
 
 _CPU_THREADS = None
+_CPU_SWEEP = {}
+
+
+def _cpu_model():
+    from oracle import fullsubnet_oracle as O
+    from oracle import libcall_port as P
+    return P.LibcallModel(O.make_state_dict(seed=0))
 
 
 def pick_cpu_threads() -> int:
-    """The LSTM steps are small matmuls: more threads than ~16-32 only add OpenMP barrier cost (128 threads
-    measured 500x slower than 8).  Calibrate once on a 0.25 s clip and keep the fastest count."""
+    """Thread count of the CPU arm.  The per-step LSTM matmuls are small, so more threads are not always faster;
+    every candidate count enhances one warm-up clip and then three full 4 s clips (>= 1 s of work each) and the count
+    with the best MEDIAN clip time is kept - long enough that the choice does not flap between runs."""
     global _CPU_THREADS
     if _CPU_THREADS is None:
         from oracle import fullsubnet_oracle as O
+        from oracle import libcall_port as P
         cores = os.cpu_count() or 1
-        sd = O.make_state_dict(seed=0)
-        y = O.make_noisy(1, 4000, seed=0)
+        model = _cpu_model()
+        y = O.make_noisy(1, SR * CLIP_SECONDS, seed=0)
         best = (1e30, 1)
-        for n in sorted({c for c in (4, 8, 16, 32, 64) if c <= cores} | {min(cores, 8)}):
+        for n in sorted({c for c in (8, 16, 32, 64) if c <= cores} | {min(cores, 8)}):
             torch.set_num_threads(n)
-            with torch.no_grad():
+            P.enhance(y, model)
+            ts = []
+            for _ in range(3):
                 t0 = time.perf_counter()
-                O.enhance(y, sd, batched=False)
-                dt = time.perf_counter() - t0
-            best = min(best, (dt, n))
-            if dt > 20:
+                P.enhance(y, model)
+                ts.append(time.perf_counter() - t0)
+            med = sorted(ts)[1]
+            _CPU_SWEEP[n] = round((1 + (SR * CLIP_SECONDS) // HOP) / med, 1)
+            best = min(best, (med, n))
+            if med > 20:
                 break
         _CPU_THREADS = best[1]
     return _CPU_THREADS
 
 
 def cpu_oracle_time(n_clips: int, threads: int):
-    """Times the oracle port of Inferencer.full_band_crm_mask (B=1 loop, the reference's only batch)."""
+    """Times the CPU arm: Inferencer.full_band_crm_mask restated with the reference's own PyTorch library calls
+    (oracle/libcall_port.py: torch.stft / nn.LSTM / F.unfold / torch.istft, bit-identical to the reference's output
+    on the goldens), B=1 loop - the reference's only inference batch."""
     from oracle import fullsubnet_oracle as O
+    from oracle import libcall_port as P
     torch.set_num_threads(threads)
-    sd = O.make_state_dict(seed=0)
+    model = _cpu_model()
     y = O.make_noisy(n_clips, SR * CLIP_SECONDS, seed=0)
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        O.enhance(y, sd, batched=False)
-        dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    P.enhance(y, model)
+    dt = time.perf_counter() - t0
     frames = n_clips * (1 + (SR * CLIP_SECONDS) // HOP)
     return frames / dt, dt
+
+
+CPU_KIND_NOTE = ("port = the reference path written with the reference's own torch library calls (torch.stft, nn.LSTM, "
+                 "F.unfold, torch.istft), output bit-identical to the unmodified reference on tests/golden; the reference "
+                 "is pure Python without setup.py and with uninstalled deps, so it cannot be installed or travel")
 
 
 def run_reference(args):
@@ -118,7 +138,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = pick_cpu_threads()
-    n_clips = 2
+    n_clips = 4
     vals = []
     for _ in range(1 if args.warmup > 0 else 0):
         cpu_oracle_time(1, cores)
@@ -134,11 +154,15 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "rtf_x": v / (SR / HOP),
-        "config": {"workload": "fullsubnet inference, 4 s 16 kHz clips, n_fft=512 hop=256 N=15 (CPU: B=1 loop)",
-                   "clip_seconds": CLIP_SECONDS, "frames_per_clip": T},
+        "config": {"workload": "fullsubnet inference, 4 s 16 kHz synthetic clips, n_fft=512 hop=256 N=15, 2xLSTM-512 fb + "
+                               "2xLSTM-384 sb (CPU: B=1 loop over 4 clips per step; per-frame throughput is batch-"
+                               "independent on this arm, the GPU arm runs 256 clips per step)",
+                   "clip_seconds": CLIP_SECONDS, "frames_per_clip": T, "clips_per_step": n_clips},
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_clips} x 4 s clips per step, B=1 loop, torch CPU fp32, {cores} threads "
-                                   f"(fastest of a calibration sweep; host has {os.cpu_count()} logical cores)"},
+                         "sample": f"{n_clips} x 4 s clips per step, B=1 loop, torch CPU fp32 library calls, {cores} "
+                                   f"threads (best median of a sweep {_CPU_SWEEP} frames/s; host has "
+                                   f"{os.cpu_count()} logical cores)",
+                         "note": CPU_KIND_NOTE},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -157,6 +181,8 @@ def main():
                          "fullsubnet_train = configs[2], the training step (bench_train.py)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `precisions`, `latency_b1` and `train_dp` objects")
+    ap.add_argument("--no-train", action="store_true", help="skip the `train_dp` object")
     args = ap.parse_args()
     if args.model == "fullsubnet_train":
         import bench_train
@@ -258,47 +284,127 @@ def main():
     value = frames / (ms_step * 1e-3)
     e2e_value = frames / (ms_e2e * 1e-3)
     peaks, peak_kind = load_peaks()
-    sb_ms = stage_ms[2]
-    sb_flops = B * (T + 2) * FLOP_PER_FRAME_STEP_SB
-    achieved = sb_flops / (sb_ms * 1e-3) / 1e12 if sb_ms > 0 else None
-    # tensor roofline: fp16 operands on tcgen05 (same dense rate as the measured bf16 cuBLAS peak);
-    # the fp32 path is FMA-bound and reported against the same denominator for comparability
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
-    traffic = None
+    sb_flops = B * (T + 2) * FLOP_PER_FRAME_STEP_SB
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if precision == "f16_tc" and B == 256 and os.path.exists(tpath):  # ncu capture of this exact workload
-        tj = json.load(open(tpath))
-        key = "sb_lstm_tc_kernel" if os.environ.get("FSN_TC_PAIR", "1") == "0" else "sb_lstm_tc2_kernel"
-        traffic = tj.get(key, {}).get("dram_bytes_per_launch")
+    tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
+
+    def sb_roofline(prec, sb_ms):
+        """Tensor roofline of the sub-band stack: ALGORITHMIC FLOPs (one product per MAC, whatever the
+        number of MMA passes the precision needs) over the CUDA-event time of the stage."""
+        achieved = sb_flops / (sb_ms * 1e-3) / 1e12 if sb_ms > 0 else None
+        passes = {"f16x3_tc": 3, "f16_tc": 1}.get(prec)
+        key = {"f16x3_tc": "sb_lstm_tc2_kernel<x3>", "f16_tc": "sb_lstm_tc2_kernel"}.get(prec)
+        if prec == "f16_tc" and os.environ.get("FSN_TC_PAIR", "1") == "0":
+            key = "sb_lstm_tc_kernel"
+        r = {"kernel": f"sub-band LSTM stack ({prec})", "bound": "tensor" if passes else "fma", "achieved": achieved,
+             "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
+             "traffic": tj.get(key, {}).get("dram_bytes_per_launch") if (key and B == 256) else None,
+             "peak_source": f"{peak_kind} bf16_tflops_sustained (fp16 and bf16 share the dense tensor rate)",
+             "flops_per_launch": sb_flops, "ms_per_launch": sb_ms}
+        if passes:
+            r["mma_passes"] = passes
+            r["executed_frac"] = (passes * achieved / peak_tf) if achieved else None
+        return r
+
     line = {
         "metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f16xf32acc" if precision == "f16_tc" else "f32", "data": "synthetic",
-        "rtf_x": value / (SR / HOP),
+        "vs_baseline": None,
+        "dtype": {"f16_tc": "f16xf32acc", "f16x3_tc": "f16x3(hi+lo split, fp32-class)xf32acc"}.get(precision, "f32"),
+        "data": "synthetic", "rtf_x": value / (SR / HOP),
         "config": {"workload": (f"fullsubnet inference, batch={B} x 4 s 16 kHz synthetic clips per GPU, "
                                 "n_fft=512 hop=256 N=15, 2xLSTM-512 fb + 2xLSTM-384 sb (BASELINE configs[1])"
                                 if args.model == "fullsubnet" else
                                 f"fast_fullsubnet inference, batch={B} x 4 s 16 kHz synthetic clips per GPU "
                                 "(BASELINE configs[3])"),
                    "clips_per_gpu": B, "frames_per_clip": T, "precision": precision,
+                   "precision_note": "headline = the fastest arithmetic that meets BOTH parity gates (cRM 1e-3 rel, "
+                                     "waveform 1e-4 abs) on BOTH weight sets W-a and W-b (tests/test_gpu_parity.py); "
+                                     "single-pass f16_tc and fp32 are under `precisions`",
                    "l2": "256 MiB flush write between timed iterations", "parallelism": f"clips sharded x{world}"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * L * 4, "rtf_x": e2e_value / (SR / HOP)},
         "gpu_launches": launches,
         "clocks": clocks,
         "stage_ms": {"stft": stage_ms[0], "fullband": stage_ms[1], "subband": stage_ms[2], "mask_istft": stage_ms[3]},
-        "roofline": {"kernel": "sub-band LSTM stack", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
-                     "peak_source": f"{peak_kind} bf16_tflops_sustained",
-                     "flops_per_launch": sb_flops, "ms_per_launch": sb_ms},
+        "roofline": sb_roofline(precision, stage_ms[2]),
     }
+
+    extras = args.model == "fullsubnet" and not args.no_extras
+    if extras and args.precision == "auto":
+        # the other arithmetic modes on the same workload (fewer iterations; same timing rules)
+        line["precisions"] = {}
+        for p in ("f16_tc", "fp32"):
+            model.precision = p
+            ms_p, _ = timed(step_resident, 2, 1)
+            _, st_p = timed(step_resident, 2, 0, prof=True)
+            line["precisions"][p] = {"ms_per_step": ms_p, "value": frames / (ms_p * 1e-3), "unit": "frames/s",
+                                     "rtf_x": frames / (ms_p * 1e-3) / (SR / HOP),
+                                     "stage_ms": {"fullband": st_p[1], "subband": st_p[2]},
+                                     "roofline": sb_roofline(p, st_p[2]),
+                                     "parity": {"f16_tc": "cRM gate on W-a and W-b, waveform gate on W-a only",
+                                                "fp32": "both gates, both weight sets"}[p]}
+        model.precision = args.precision
+    if extras:
+        # regime (ii) of SURVEY 8d: ONE 4 s clip (BASELINE configs[0] shape) - latency, not throughput
+        x1 = x_dev[:1].contiguous()
+        lat = {}
+        for p in ([args.precision] if args.precision != "auto" else ["auto", "f16_tc", "fp32"]):
+            model.precision = p
+            for _ in range(3):
+                model.enhance(x1, N_FFT, HOP, WIN)
+            torch.cuda.synchronize()
+            ts = []
+            lib.fsn_set_profiling(1)
+            st = [0.0] * 4
+            for _ in range(10):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                model.enhance(x1, N_FFT, HOP, WIN)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+                for k in range(4):
+                    st[k] += max(0.0, lib.fsn_last_stage_ms(k)) / 10
+            lib.fsn_set_profiling(0)
+            ms1 = sorted(ts)[len(ts) // 2]
+            fb_bytes = 15.21e6  # SURVEY 8d: fp32 weights of the full-band stack one LSTM step touches
+            lat[model._resolve_precision()] = {
+                "ms_per_clip": ms1, "rtf_x": CLIP_SECONDS * 1e3 / ms1, "frames_per_sec": T / (ms1 * 1e-3),
+                "stage_ms": {"stft": st[0], "fullband": st[1], "subband": st[2], "mask_istft": st[3]},
+                "fullband_us_per_lstm_step": 1e3 * st[1] / (T + 2),
+                "fullband_weight_stream": {
+                    "bytes_per_step": fb_bytes, "achieved_gbs": fb_bytes / (1e-3 * st[1] / (T + 2)) / 1e9,
+                    "hbm_peak_gbs": peaks.get("hbm_gbs"),
+                    "frac_of_hbm_peak": fb_bytes / (1e-3 * st[1] / (T + 2)) / 1e9 / peaks.get("hbm_gbs", 6582.5),
+                    "note": "the persistent kernel keeps the weights in shared memory for all 253 steps (HBM is read "
+                            "once, 15.2 MB per launch); the figure is the SMEM-resident weight bytes one step consumes "
+                            "over the step time, i.e. what an HBM-streaming GEMV would have to sustain to keep up; "
+                            "the step is bound by the grid barrier + the h exchange through L2"}}
+        model.precision = args.precision
+        line["latency_b1"] = {"workload": "1 x 4 s clip (BASELINE configs[0] shape), inputs resident, median of 10",
+                              "by_precision": lat}
+
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         cores = pick_cpu_threads()
         v, dt = cpu_oracle_time(4, cores)
         line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-                                "sample": f"4 x 4 s clips, B=1 loop of the oracle port, torch CPU fp32, "
-                                          f"{cores} threads (fastest of a calibration sweep; host has "
-                                          f"{os.cpu_count()} logical cores), {dt:.1f} s"}
+                                "sample": f"4 x 4 s clips, B=1 loop, torch CPU fp32 library calls "
+                                          f"(oracle/libcall_port.py), {cores} threads (best median of a sweep "
+                                          f"{_CPU_SWEEP} frames/s; host has {os.cpu_count()} logical cores), {dt:.1f} s",
+                                "note": CPU_KIND_NOTE}
+    if extras and not args.no_train:
+        # BASELINE configs[2]: the training step with its gradient all-reduce - the one collective on the path
+        del x_dev, flush
+        torch.cuda.empty_cache()
+        import bench_train
+        targs = argparse.Namespace(**vars(args))
+        targs.batch, targs.steps, targs.warmup = 64, max(2, min(args.steps, 5)), 3
+        tl = bench_train.measure(targs, dist, dev, rank, world, local, cpu_leg=False)
+        line["train_dp"] = {k: tl[k] for k in ("value", "unit", "ms_per_step", "n_gpus", "dtype", "gpu_launches")}
+        line["train_dp"].update({"workload": tl["config"]["workload"], "parallelism": tl["config"]["parallelism"],
+                                 "allreduce": tl.get("allreduce"), "e2e": tl["e2e"], "roofline": tl["roofline"]})
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

@@ -64,14 +64,6 @@ def run_reference(args):
 def main(args):
     if args.impl == "reference":
         return run_reference(args)
-    from bench import ClockSampler, load_peaks, pick_cpu_threads
-    from fullsubnet_b200 import _lib
-    from fullsubnet_b200.fullsubnet.model import Model
-    from fullsubnet_b200.loss import mse_loss
-    from fullsubnet_b200.optim import FusedClipAdam
-    from fullsubnet_b200.trainer import Trainer
-    from oracle import fullsubnet_oracle as O  # weights / inputs generator only (+ cpu_baseline leg)
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -83,6 +75,24 @@ def main(args):
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=dev)
         dist = dist_mod
+    line = measure(args, dist, dev, rank, world, local, cpu_leg=not args.no_cpu_baseline)
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def measure(args, dist, dev, rank, world, local, cpu_leg=True):
+    """One measurement of the training step on an initialised process group (``dist`` = torch.distributed or None);
+    returns the JSON line as a dict.  bench.py embeds it as `train_dp` next to the inference numbers."""
+    from bench import ClockSampler, load_peaks, pick_cpu_threads
+    from fullsubnet_b200 import _lib
+    from fullsubnet_b200.fullsubnet.model import Model
+    from fullsubnet_b200.loss import mse_loss
+    from fullsubnet_b200.optim import FusedClipAdam
+    from fullsubnet_b200.trainer import Trainer
+    from oracle import fullsubnet_oracle as O  # weights / inputs generator only (+ cpu_baseline leg)
+
     lib = _lib.load()
     B = args.batch if args.batch != 256 else 64  # bench.py's default batch belongs to the inference config
     L = SR * CLIP_SECONDS
@@ -142,6 +152,25 @@ def main(args):
     torch.cuda.synchronize()
     launches = int(lib.fsn_total_launch_count() - n0)
     ms_e2e = timed(step_e2e, args.steps, 1)
+    allreduce = None
+    if dist is not None:  # the collective alone: K all-reduces of the flat gradient buffer, device-timed, max over ranks
+        flat = model.flat_grad()
+        for _ in range(3):
+            dist.all_reduce(flat)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(20):
+            dist.all_reduce(flat)
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1) / 20], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ar_ms = float(t.item())
+        nbytes = flat.numel() * 4
+        allreduce = {"ms": ar_ms, "bytes": nbytes, "ranks": world, "backend": "nccl",
+                     "busbw_gbs": 2 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9,
+                     "share_of_step": ar_ms / ms_step}
 
     frames = B * T * world
     value, e2e_value = frames / (ms_step * 1e-3), frames / (ms_e2e * 1e-3)
@@ -177,16 +206,16 @@ def main(args):
                      "note": "achieved = algorithmic FLOPs of the whole step (3 x forward) / step time; traffic = DRAM "
                              "bytes of one BPTT-step GEMM launch (profiles/traffic.json)"},
     }
-    if rank == 0 and not args.no_cpu_baseline and world == 1:
+    line["allreduce"] = allreduce
+    if rank == 0 and cpu_leg and world == 1:
         cores = pick_cpu_threads()
         v, dt = cpu_train_time(3, cores)
         line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                                 "sample": f"one step on 3 x 3 s clips, oracle port of trainer.py:41-68 (torch CPU "
                                           f"autograd fp32), {cores} threads, {dt:.1f} s"}
-    if rank == 0:
-        print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    del trainer, model, dev_noisy, dev_clean, flush
+    torch.cuda.empty_cache()
+    return line
 
 
 if __name__ == "__main__":

@@ -281,6 +281,38 @@ __global__ void peak_normalize_int16_kernel(const float* __restrict__ wav, int L
     o[i] = (m > 0.f) ? (int16_t)__fdiv_rn(__fmul_rn(gain, x[i]), m) : (int16_t)0;  // float32 mul, div, truncation like numpy
 }
 
+// audio_zen/metrics.py:6-31 SI_SDR(reference, estimation) per clip: alpha = <ref,est>/<ref,ref>;
+// 10 log10(|alpha ref|^2 / |est - alpha ref|^2).  One CTA per clip, two passes, fixed-order tree reductions in
+// double (the reference sums in float32 pairwise; both agree to ~1e-5 dB on 4 s clips).
+__global__ void si_sdr_kernel(const float* __restrict__ ref, const float* __restrict__ est, int L, float* __restrict__ out) {
+  __shared__ double sa[256], sb[256];
+  const float* r = ref + (size_t)blockIdx.x * L;
+  const float* e = est + (size_t)blockIdx.x * L;
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) { a += (double)r[i] * r[i]; b += (double)r[i] * e[i]; }
+  sa[threadIdx.x] = a; sb[threadIdx.x] = b;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { sa[threadIdx.x] += sa[threadIdx.x + s]; sb[threadIdx.x] += sb[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  const float alpha = (float)sb[0] / (float)sa[0];  // float32 like the reference's optimal_scaling
+  __syncthreads();
+  a = 0.0; b = 0.0;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const float p = alpha * r[i];
+    const float n = e[i] - p;
+    a += (double)p * p; b += (double)n * n;
+  }
+  sa[threadIdx.x] = a; sb[threadIdx.x] = b;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { sa[threadIdx.x] += sa[threadIdx.x + s]; sb[threadIdx.x] += sb[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = (float)(10.0 * log10(sa[0] / sb[0]));
+}
+
 static int ew_grid(int64_t n) {
   int64_t g = (n + 255) / 256;
   return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -377,6 +409,13 @@ extern "C" int fsn_peak_normalize_int16(const float* wav, int B, int L, float ga
   FSN_REQUIRE(B > 0 && L > 0, FSN_ERR_SHAPE, "peak_normalize: empty input");
   peak_normalize_int16_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(wav, L, gain, out);
   FSN_CHECK_LAUNCH("peak_normalize_int16_kernel");
+  return FSN_OK;
+}
+
+extern "C" int fsn_si_sdr(const float* reference, const float* estimation, int B, int L, float* out, fsn_stream_t stream) {
+  FSN_REQUIRE(B > 0 && L > 0, FSN_ERR_SHAPE, "si_sdr: empty input");
+  si_sdr_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(reference, estimation, L, out);
+  FSN_CHECK_LAUNCH("si_sdr_kernel");
   return FSN_OK;
 }
 

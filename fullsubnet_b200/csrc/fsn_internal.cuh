@@ -65,11 +65,6 @@ struct LayerSave { float *G, *C, *H; };
 int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R, int K0, int H, int Tp,
                           const LayerSave& s, float* rec, cudaStream_t st);
 
-// EXPERIMENTAL, off unless FSN_TGEMM_MN=1 (not yet run on hardware): C[M,N] (+)= A^T B with A [K,M], B [K,N] (MN-major)
-bool tgemm_mn_enabled();
-int tgemm_mn_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float* C, size_t ldc, int M, int N, int K,
-                    bool accumulate, float* scratch, size_t scratch_floats, cudaStream_t st);
-
 // shapes of one Model.forward call (fsn_model.cu)
 struct Dims {
   int B, T, Tp, F, Fsub, G, R, Ksb;
@@ -109,6 +104,20 @@ bool fb_persistent_supported(int F, int H0, int H1);
 int fb_persistent_launch(const fsn_seq_weights* w, const float* x_chunk, const float* inv1_chunk, float* h0buf,
                          float* h1all_chunk, unsigned int* barrier, int nb, int F, int H0, int H1, int Tp,
                          cudaStream_t st);
+
+// tensor-core LSTM layer for a small batch of sequences (fsn_lstm_rec_tc.cu): hoisted input projection on the tf32
+// GEMM (x3: three passes on tf32 hi/lo splits) + persistent cooperative tcgen05 recurrence (x3: fp16 hi/lo splits)
+bool lstm_rec_tc_supported(int H, bool x3);
+int lstm_rec_tc_rows_per_launch(int H);
+size_t lstm_rec_tc_scratch_bytes(int H, bool x3);
+int lstm_rec_tc_launch(const float* w_hh, const float* b_ih, const float* b_hh, const float* P, size_t p_row, size_t p_t,
+                       float* hall, size_t h_row, size_t h_t, int R, int T, int H, bool x3, void* scratch,
+                       cudaStream_t st);
+int split_tf32_launch(const float* in, size_t rows, int K, size_t ldi, const float* row_scale, int rows_per_scale,
+                      float* out_hi, float* out_lo, int ldo, cudaStream_t st, int scale_B = 0);
+int bias_act_launch(float* x, size_t rows, int N, size_t ld, const float* bias, int act, cudaStream_t st);
+int gemm_tc_split_launch(const float* A_hi, const float* A_lo, size_t lda, const float* W, int N, int K, float* w_hi,
+                         float* w_lo, float* C, size_t ldc, size_t M, bool x3, cudaStream_t st);
 
 // tcgen05 sub-band stack (fsn_subband_tc.cu)
 struct SbTcArgs {

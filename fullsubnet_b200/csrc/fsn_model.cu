@@ -53,8 +53,19 @@ struct ModelWs {
   float *cum1, *cum2;  // cumulative norm: per-(step, clip) and per-(step, unit) scales
   unsigned int* fb_barrier;
   float *sb_h0[2], *sb_h1[2], *sb_c0, *sb_c1;
+  // tensor-core full-band path (fb_tc_forward): split operands, hoisted projection, layer-0 output, scratch
+  float *tc_a_hi, *tc_a_lo, *tc_w_hi, *tc_w_lo, *tc_P, *tc_h0all;
+  void* tc_rec;
   size_t bytes;
 };
+
+// full-band stack on the tensor cores?  (tensor-core precisions, offline norm, enough clips to fill an MMA tile)
+static bool fb_tc_enabled(const fsn_model_desc* d, int B) {
+  static const int min_b = getenv("FSN_FB_TC_MIN_B") ? atoi(getenv("FSN_FB_TC_MIN_B")) : 16;
+  if (d->precision != FSN_PREC_F16_TC && d->precision != FSN_PREC_F16X3_TC) return false;
+  if (B < min_b) return false;
+  return lstm_rec_tc_supported(d->fb_hidden, d->precision == FSN_PREC_F16X3_TC);
+}
 
 int make_dims(const fsn_model_desc* d, int B, int T, Dims& m) {
   FSN_REQUIRE(d && d->num_freqs > 1 && d->fb_hidden > 0 && d->sb_hidden > 0 && d->look_ahead >= 0, FSN_ERR_SHAPE,
@@ -62,8 +73,8 @@ int make_dims(const fsn_model_desc* d, int B, int T, Dims& m) {
   FSN_REQUIRE(B > 0 && T > 0, FSN_ERR_SHAPE, "model: empty input (B=%d, T=%d)", B, T);
   FSN_REQUIRE(d->norm_type == FSN_NORM_OFFLINE_LAPLACE || d->norm_type == FSN_NORM_CUMULATIVE_LAPLACE,
               FSN_ERR_UNSUPPORTED, "You must set up a type of Norm. (offline_laplace_norm / cumulative_laplace_norm are built)");
-  FSN_REQUIRE(d->norm_type == FSN_NORM_OFFLINE_LAPLACE || d->precision == FSN_PREC_FP32, FSN_ERR_UNSUPPORTED,
-              "cumulative_laplace_norm is built for the fp32 path only");
+  FSN_REQUIRE(d->norm_type == FSN_NORM_OFFLINE_LAPLACE || d->precision != FSN_PREC_TF32_TC, FSN_ERR_UNSUPPORTED,
+              "cumulative_laplace_norm is built for inference (the training step keeps the offline norm)");
   FSN_REQUIRE(d->sb_num_neighbors >= 0 && d->fb_num_neighbors >= 0 && d->sb_num_neighbors < d->num_freqs &&
                   d->fb_num_neighbors < d->num_freqs,
               FSN_ERR_SHAPE, "model: reflect padding needs num_neighbors < num_freqs");
@@ -104,12 +115,68 @@ static void carve_model(const fsn_model_desc* d, const Dims& m, void* base, Mode
     w.sb_c0 = c.take<float>(RH);
     w.sb_c1 = c.take<float>(RH);
   }
+  w.tc_a_hi = w.tc_a_lo = w.tc_w_hi = w.tc_w_lo = w.tc_P = w.tc_h0all = nullptr;
+  w.tc_rec = nullptr;
+  if (fb_tc_enabled(d, m.B)) {
+    const int Hf = d->fb_hidden, Fp = (m.F + 3) & ~3;
+    const size_t rows = (size_t)m.B * m.Tp, wa = (size_t)(Fp > Hf ? Fp : Hf);
+    const bool x3 = d->precision == FSN_PREC_F16X3_TC;
+    w.tc_a_hi = c.take<float>(rows * wa);
+    w.tc_a_lo = x3 ? c.take<float>(rows * wa) : nullptr;
+    w.tc_w_hi = c.take<float>((size_t)4 * Hf * wa);
+    w.tc_w_lo = x3 ? c.take<float>((size_t)4 * Hf * wa) : nullptr;
+    w.tc_P = c.take<float>(rows * 4 * Hf);
+    w.tc_h0all = c.take<float>(rows * Hf);
+    w.tc_rec = c.take<char>(lstm_rec_tc_scratch_bytes(Hf, x3));
+  }
   w.cum1 = w.cum2 = nullptr;
   if (d->norm_type == FSN_NORM_CUMULATIVE_LAPLACE) {
     w.cum1 = c.take<float>((size_t)m.Tp * m.B);
     w.cum2 = c.take<float>((size_t)m.Tp * m.R);
   }
   w.bytes = c.off;
+}
+
+// Full-band stack on the tensor cores (model.py:92-95; sequence_model.py:106-125): per layer the input projection of
+// all steps as one tf32 GEMM (three passes on hi/lo splits when x3) and the recurrence in the persistent tcgen05
+// kernel; Linear(Hf -> F) + activation as the same GEMM + a bias/activation pass.  x3 keeps the fp32 error class.
+static int fb_tc_forward(const fsn_model_desc* d, const fsn_seq_weights* fb, const Dims& m, const ModelWs& w, cudaStream_t st) {
+  const int F = m.F, Tp = m.Tp, B = m.B, Hf = d->fb_hidden, Fp = (F + 3) & ~3;
+  const bool x3 = d->precision == FSN_PREC_F16X3_TC;
+  const size_t rows = (size_t)B * Tp;
+  int rc;
+  // layer 0: x = magT * inv1[clip] (model.py:92), P = x W_ih0^T
+  // (cumulative norm: the scale of (clip, step) from the time-major table cum1[t*B + b], base_model.py:220-251)
+  const bool cum = d->norm_type == FSN_NORM_CUMULATIVE_LAPLACE;
+  if ((rc = split_tf32_launch(w.magT, rows, F, (size_t)F, cum ? w.cum1 : w.inv1, Tp, w.tc_a_hi, w.tc_a_lo, Fp, st, cum ? B : 0)))
+    return rc;
+  if ((rc = gemm_tc_split_launch(w.tc_a_hi, w.tc_a_lo, Fp, fb->w_ih[0], 4 * Hf, F, w.tc_w_hi, w.tc_w_lo, w.tc_P,
+                                 (size_t)4 * Hf, rows, x3, st)))
+    return rc;
+  if ((rc = lstm_rec_tc_launch(fb->w_hh[0], fb->b_ih[0], fb->b_hh[0], w.tc_P, (size_t)Tp * 4 * Hf, (size_t)4 * Hf, w.tc_h0all,
+                               (size_t)Tp * Hf, (size_t)Hf, B, Tp, Hf, x3, w.tc_rec, st)))
+    return rc;
+  // layer 1: P = h0 W_ih1^T
+  const float *a_hi = w.tc_h0all, *a_lo = nullptr;
+  if (x3) {
+    if ((rc = split_tf32_launch(w.tc_h0all, rows, Hf, (size_t)Hf, nullptr, 1, w.tc_a_hi, w.tc_a_lo, Hf, st))) return rc;
+    a_hi = w.tc_a_hi; a_lo = w.tc_a_lo;
+  }
+  if ((rc = gemm_tc_split_launch(a_hi, a_lo, Hf, fb->w_ih[1], 4 * Hf, Hf, w.tc_w_hi, w.tc_w_lo, w.tc_P, (size_t)4 * Hf, rows,
+                                 x3, st)))
+    return rc;
+  if ((rc = lstm_rec_tc_launch(fb->w_hh[1], fb->b_ih[1], fb->b_hh[1], w.tc_P, (size_t)Tp * 4 * Hf, (size_t)4 * Hf, w.fb_h1all,
+                               (size_t)Tp * Hf, (size_t)Hf, B, Tp, Hf, x3, w.tc_rec, st)))
+    return rc;
+  // Linear(Hf -> F) + activation (sequence_model.py:119-123) -> fbT [B, Tp, F]
+  a_hi = w.fb_h1all; a_lo = nullptr;
+  if (x3) {
+    if ((rc = split_tf32_launch(w.fb_h1all, rows, Hf, (size_t)Hf, nullptr, 1, w.tc_a_hi, w.tc_a_lo, Hf, st))) return rc;
+    a_hi = w.tc_a_hi; a_lo = w.tc_a_lo;
+  }
+  if ((rc = gemm_tc_split_launch(a_hi, a_lo, Hf, fb->fc_w, F, Hf, w.tc_w_hi, w.tc_w_lo, w.fbT, (size_t)F, rows, x3, st)))
+    return rc;
+  return bias_act_launch(w.fbT, rows, F, (size_t)F, fb->fc_b, d->fb_activation, st);
 }
 
 // everything after the time-major magnitude exists: norms, full-band stack, sub-band stack
@@ -126,7 +193,10 @@ static int model_core(const fsn_model_desc* d, const fsn_seq_weights* fb, const 
 
   // ---- full-band stack (model.py:92-95): 2-layer LSTM(F -> Hf -> Hf), rows = clips
   static const bool fb_stepwise = getenv("FSN_FB_STEPWISE") != nullptr;  // debug: force the per-step kernels
-  if (!fb_stepwise && !cum && fb_persistent_supported(F, Hf, Hf)) {
+  const bool fb_tc = !fb_stepwise && fb_tc_enabled(d, B);
+  if (fb_tc) {
+    if ((rc = fb_tc_forward(d, fb, m, w, st))) return rc;
+  } else if (!fb_stepwise && !cum && fb_persistent_supported(F, Hf, Hf)) {
     // one persistent cooperative kernel per chunk of <= 256 clips: weights resident in shared memory,
     // layer wavefront, one grid barrier per time step
     for (int b0 = 0; b0 < B; b0 += 256) {
@@ -160,7 +230,7 @@ static int model_core(const fsn_model_desc* d, const fsn_seq_weights* fb, const 
   }
   }
   // Linear(Hf -> F) + activation over all (b,t): fbT[b,t,f]  (sequence_model.py:119-123)
-  if ((rc = fc_gemm_launch(w.fb_h1all, fb->fc_w, fb->fc_b, w.fbT, B * Tp, Hf, F, d->fb_activation, st))) return rc;
+  if (!fb_tc && (rc = fc_gemm_launch(w.fb_h1all, fb->fc_w, fb->fc_b, w.fbT, B * Tp, Hf, F, d->fb_activation, st))) return rc;
 
   // ---- second norm (model.py:110-111) in closed form: never materialise [B,F,Ksb,T']
   if ((rc = clip_stats_launch(w.fbT, B, Tp, F, d->fb_num_neighbors, w.fs, w.sums_fb, st))) return rc;
@@ -179,6 +249,7 @@ static int model_core(const fsn_model_desc* d, const fsn_seq_weights* fb, const 
     a.packed = sb_packed; a.magT = w.magT; a.fbT = w.fbT; a.inv2 = w.inv2; a.crm = crm;
     a.B = B; a.F = F; a.Tp = Tp; a.la = d->look_ahead; a.Ns = d->sb_num_neighbors; a.Nf = d->fb_num_neighbors;
     a.H = Hs; a.act = d->sb_activation; a.map = map; a.pair = sb_tc2_supported(d); a.x3 = d->precision == FSN_PREC_F16X3_TC;
+    a.unit_scale = cum ? w.cum2 : nullptr;
     rc = sb_tc_forward(a, st);
     prof_mark(3, st);
     return rc;

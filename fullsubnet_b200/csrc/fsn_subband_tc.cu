@@ -308,6 +308,7 @@ __device__ __forceinline__ void trace_ev(long long* tr, int it, int ev) {
 struct KArgs {
   const uint8_t* packed;
   const float* magT; const float* fbT; const float* inv2;
+  const float* unit_scale;  // nullable: cumulative norm, scale of (step t, row r) at [t*R + r] instead of inv2[clip]
   float* crm;
   int R, F, Tp, la, T, Ns, Nf, H, Ksb, act, Fsub, stages, cluster;
   long long* trace;  // debug: clock64 event trace of CTA 0 (FSN_TC_TRACE), else nullptr
@@ -507,6 +508,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
 #pragma unroll 4
       for (int n = 0; n < NB; ++n) {
         const RowInfo ri = rows[n];
+        const float scale = (a.unit_scale && ri.src_b >= 0) ? a.unit_scale[(size_t)t * a.R + row0 + n] : ri.scale;
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
           const int k = lane + 32 * kk;
@@ -515,7 +517,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
             const size_t base = ((size_t)ri.src_b * Tp + t) * a.F;
             if (k < nmag) v = a.magT[base + reflect_idx(ri.src_f + k - a.Ns, a.F)];
             else          v = a.fbT[base + reflect_idx(ri.src_f + (k - nmag) - a.Nf, a.F)];
-            v *= ri.scale;
+            v *= scale;
           }
           *reinterpret_cast<__half*>(xb + swz_off(n, k)) = __float2half_rn(v);
         }
@@ -703,7 +705,7 @@ int sb_tc_forward(const SbTcArgs& s, cudaStream_t st) {
   if (s.pair) return sb_tc2_forward(s, st);
   tc::KArgs a;
   a.packed = (const uint8_t*)s.packed;
-  a.magT = s.magT; a.fbT = s.fbT; a.inv2 = s.inv2; a.crm = s.crm;
+  a.magT = s.magT; a.fbT = s.fbT; a.inv2 = s.inv2; a.unit_scale = s.unit_scale; a.crm = s.crm;
   a.R = s.map.B * s.map.Fsub; a.F = s.F; a.Tp = s.Tp; a.la = s.la; a.T = s.Tp - s.la;
   a.Ns = s.Ns; a.Nf = s.Nf; a.H = s.H; a.Ksb = (2 * s.Ns + 1) + (2 * s.Nf + 1); a.act = s.act;
   a.Fsub = s.map.Fsub; a.map = s.map;

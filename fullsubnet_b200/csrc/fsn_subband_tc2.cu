@@ -183,6 +183,7 @@ struct RowInfo {
 struct KArgs {
   const uint8_t* packed;
   const float* magT; const float* fbT; const float* inv2;
+  const float* unit_scale;  // nullable: cumulative norm, scale of (step t, row r) at [t*R + r] instead of inv2[clip]
   float* crm;
   int R, F, Tp, la, T, Ns, Nf, Ksb, act, Fsub;
   int src_T, shrink;  // frames in magT/fbT; x_t = mean of `shrink` source frames (fast_fullsubnet down-sampling), 1 = none
@@ -510,7 +511,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) sb_lstm
               const size_t base = ((size_t)ri.src_b * a.src_T + t) * a.F;
               if (lane < nmag) v = a.magT[base + reflect_idx(ri.src_f + lane - a.Ns, a.F)];
               else             v = a.fbT[base + reflect_idx(ri.src_f + (lane - nmag) - a.Nf, a.F)];
-              v *= ri.scale;
+              v *= a.unit_scale ? a.unit_scale[(size_t)t * a.R + row0 + n] : ri.scale;
             }
             put(n, v);
           }
@@ -765,7 +766,7 @@ static int tc2_launch(const tc2::KArgs& a, cudaStream_t st) {
 int sb_tc2_forward(const SbTcArgs& s, cudaStream_t st) {
   tc2::KArgs a;
   a.packed = (const uint8_t*)s.packed;
-  a.magT = s.magT; a.fbT = s.fbT; a.inv2 = s.inv2; a.crm = s.crm;
+  a.magT = s.magT; a.fbT = s.fbT; a.inv2 = s.inv2; a.unit_scale = s.shrink > 1 ? nullptr : s.unit_scale; a.crm = s.crm;
   a.R = s.map.B * s.map.Fsub; a.F = s.F; a.Tp = s.steps > 0 ? s.steps : s.Tp; a.la = s.la; a.T = a.Tp - s.la;
   a.src_T = s.Tp; a.shrink = s.shrink > 1 ? s.shrink : 1;
   a.Ns = s.Ns; a.Nf = s.Nf; a.Ksb = (2 * s.Ns + 1) + (2 * s.Nf + 1); a.act = s.act;

@@ -249,101 +249,6 @@ tgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// EXPERIMENTAL - NOT YET RUN ON HARDWARE (off unless FSN_TGEMM_MN=1): MN-major operands, for the weight gradients
-// dW[M,N] = A^T B with A stored [K,M] (= dG [T'R,4H]) and B stored [K,N] (= X / H), i.e. no transposed copies.
-// Canonical MN-major 128B-swizzle layout (16-byte units): Swizzle<3,4,3> o ((8,n),(8,k)) : ((1,LBO),(8,SBO)) -
-// 128 contiguous bytes along M (32 tf32), eight k-rows per 1 024-byte atom.  A stage holds BM/32 (+ BN/32) TMA
-// boxes {32 floats of m, 32 rows of k} of 4 096 B each: LBO = 4 096 B (next m chunk), SBO = 1 024 B (next 8 k-rows),
-// one K = 8 MMA per atom row group (descriptor start += 1 024 B), a_major = b_major = 1 in the instruction descriptor.
-__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-         (2ull << 61);
-}
-
-template <int BN>
-__global__ void __launch_bounds__(160, Cfg<BN>::MIN_CTAS)
-tgemm_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
-                size_t ldc, int M, int N, int K, int k_per_split, int accumulate, size_t split_stride) {
-  using CF = Cfg<BN>;
-  constexpr int STAGES = CF::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  Bars& bars = *reinterpret_cast<Bars*>(smem + STAGES * CF::STAGE_BYTES);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int kb = blockIdx.z * k_per_split;
-  const int ke = (kb + k_per_split < K) ? kb + k_per_split : K;
-  const int nk = (ke - kb + BK - 1) / BK;
-  if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
-    mbar_init(&bars.acc_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
-                 "n"(CF::TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = bars.tmem_base;
-  if (warp < 4) {
-    if (warp == 0) {
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % STAGES;
-        if (i >= STAGES) mbar_wait<false>(&bars.empty[s], (uint32_t)(((i / STAGES) - 1) & 1));
-        if (elect_one()) {
-          uint8_t* sa = smem + s * CF::STAGE_BYTES;
-          mbar_expect_tx(&bars.full[s], CF::STAGE_BYTES);
-#pragma unroll
-          for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * 4096, &tmA, m0 + c * 32, kb + i * BK, &bars.full[s]);
-#pragma unroll
-          for (int c = 0; c < BN / 32; ++c)
-            tma_load_2d(sa + A_BYTES + c * 4096, &tmB, n0 + c * 32, kb + i * BK, &bars.full[s]);
-        }
-        __syncwarp();
-      }
-    }
-    epilogue<BN>(smem, bars, tmem_base, C, ldc, M, N, m0, n0, accumulate, split_stride);
-  } else {
-    constexpr int N0 = BN > 256 ? 256 : BN, N1 = BN - N0;
-    const uint32_t major = (1u << 15) | (1u << 16);  // A and B MN-major
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | major | ((uint32_t)(N0 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | major | ((uint32_t)((N1 > 0 ? N1 : 8) >> 3) << 17) |
-                            ((uint32_t)(BM >> 4) << 24);
-    const uint32_t smem_base = smem_u32(smem);
-    for (int i = 0; i < nk; ++i) {
-      const int s = i % STAGES;
-      mbar_wait<false>(&bars.full[s], (uint32_t)((i / STAGES) & 1));
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_base + s * CF::STAGE_BYTES;
-        const uint32_t sb = sa + A_BYTES;
-#pragma unroll
-        for (int kk = 0; kk < BK / 8; ++kk) {
-          tc_mma1_tf32(tmem_base, desc_mn_sw128(sa + kk * 1024), desc_mn_sw128(sb + kk * 1024), idesc,
-                       (i > 0 || kk > 0) ? 1u : 0u);
-          if (N1 > 0)  // columns 256..: n chunks 8.. start 8 * 4 096 bytes further
-            tc_mma1_tf32(tmem_base + 256, desc_mn_sw128(sa + kk * 1024), desc_mn_sw128(sb + 8 * 4096 + kk * 1024), idesc1,
-                         (i > 0 || kk > 0) ? 1u : 0u);
-        }
-        tc_commit1(&bars.empty[s]);
-      }
-      __syncwarp();
-    }
-    if (elect_one()) tc_commit1(&bars.acc_full);
-    __syncwarp();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(CF::TMEM_COLS));
-  }
-}
-
 }  // namespace tg
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
@@ -425,7 +330,8 @@ int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float*
   CUtensorMap tmB2;
   if (make_tmap(&tmA, A, K, M, lda, tg::BM) && make_tmap(&tmB, Bm, K, N, ldb, BN > 256 ? 256 : BN) &&
       make_tmap(&tmB2, Bm, K, N, ldb, BN > 256 ? BN - 256 : 128)) {
-    static bool attr = false;
+    static bool attr_by_dev[64] = {};  // the opt-in is per device
+    int cur_dev_ = 0; cudaGetDevice(&cur_dev_); bool& attr = attr_by_dev[cur_dev_ & 63];
     if (!attr) {
       if ((rc = check_cuda(cudaFuncSetAttribute(tg::tgemm_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 tg::Cfg<256>::SMEM), "tgemm smem attr")))
@@ -453,7 +359,8 @@ int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float*
   }
   FSN_REQUIRE(BN != 384, FSN_ERR_CUDA, "tgemm: tensor-map encoding failed for the 128x384 tile");
   if (BN == 256) {
-    static bool attr = false;
+    static bool attr_by_dev[64] = {};  // the opt-in is per device
+    int cur_dev_ = 0; cudaGetDevice(&cur_dev_); bool& attr = attr_by_dev[cur_dev_ & 63];
     if (!attr) {
       if ((rc = check_cuda(cudaFuncSetAttribute(tg::tgemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 tg::Cfg<256>::SMEM), "tgemm smem attr")))
@@ -463,7 +370,8 @@ int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float*
     tg::tgemm_kernel<256><<<grid, 160, tg::Cfg<256>::SMEM, st>>>(A, lda, Bm, ldb, dst, ldd, M, N, K, kps, acc,
                                                                  (size_t)M * N);
   } else {
-    static bool attr = false;
+    static bool attr_by_dev[64] = {};  // the opt-in is per device
+    int cur_dev_ = 0; cudaGetDevice(&cur_dev_); bool& attr = attr_by_dev[cur_dev_ & 63];
     if (!attr) {
       if ((rc = check_cuda(cudaFuncSetAttribute(tg::tgemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 tg::Cfg<128>::SMEM), "tgemm smem attr")))
@@ -478,77 +386,6 @@ int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float*
   return FSN_OK;
 }
 
-// EXPERIMENTAL (see tgemm_mn_kernel): C[M,N] (+)= A^T B, A stored [K,M] (lda), B stored [K,N] (ldb), both fp32 with
-// 16-byte aligned rows.  Tensor maps: inner dimension = M (N), boxes of 32 floats x 32 k-rows.
-static bool make_tmap_mn(CUtensorMap* m, const float* base, int inner, int K, size_t ld) {
-  PFN_cuTensorMapEncodeTiled_v12000 fn = tmap_encoder();
-  if (!fn) return false;
-  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)K};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {32, (cuuint32_t)tg::BK};
-  cuuint32_t estr[2] = {1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
-         CUDA_SUCCESS;
-}
-
-bool tgemm_mn_enabled() {
-  static const bool on = getenv("FSN_TGEMM_MN") != nullptr && atoi(getenv("FSN_TGEMM_MN")) != 0;
-  return on && tmap_encoder() != nullptr;
-}
-
-int tgemm_mn_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float* C, size_t ldc, int M, int N, int K,
-                    bool accumulate, float* scratch, size_t scratch_floats, cudaStream_t st) {
-  if (M <= 0 || N <= 0 || K <= 0) return FSN_OK;
-  FSN_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(Bm) & 15) == 0,
-              FSN_ERR_UNSUPPORTED, "tgemm_mn: operands must have 16-byte aligned rows");
-  const int BN = (N > 256 && N <= 384 && scratch && K >= 65536) ? 384 : ((N >= 256 && N % 256 == 0) ? 256 : 128);
-  const int tiles = cdiv(M, tg::BM) * cdiv(N, BN);
-  int S = 1;
-  if (scratch && K >= 8192 && tiles < 296) {
-    const int slots = 148 * (BN == 128 ? 2 : 1);
-    double best = 1e30;
-    for (int s = 1; s <= 64 && s <= cdiv(K, 2048); ++s) {
-      if ((size_t)s * M * N > scratch_floats) break;
-      const double cost = (double)cdiv(tiles * s, slots) / s + 1e-4 * s;
-      if (cost < best) { best = cost; S = s; }
-    }
-  }
-  const int kps = cdiv(cdiv(K, S), tg::BK) * tg::BK;
-  S = cdiv(K, kps);
-  dim3 grid(cdiv(M, tg::BM), cdiv(N, BN), S);
-  float* dst = S > 1 ? scratch : C;
-  const size_t ldd = S > 1 ? (size_t)N : ldc;
-  const int acc = (S > 1) ? 0 : (accumulate ? 1 : 0);
-  CUtensorMap tmA, tmB;
-  FSN_REQUIRE(make_tmap_mn(&tmA, A, M, K, lda) && make_tmap_mn(&tmB, Bm, N, K, ldb), FSN_ERR_CUDA,
-              "tgemm_mn: tensor-map encoding failed");
-  int rc;
-  static bool attr = false;
-  if (!attr) {
-    if ((rc = check_cuda(cudaFuncSetAttribute(tg::tgemm_mn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              tg::Cfg<128>::SMEM), "tgemm smem attr")))
-      return rc;
-    if ((rc = check_cuda(cudaFuncSetAttribute(tg::tgemm_mn_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              tg::Cfg<256>::SMEM), "tgemm smem attr")))
-      return rc;
-    if ((rc = check_cuda(cudaFuncSetAttribute(tg::tgemm_mn_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              tg::Cfg<384>::SMEM), "tgemm smem attr")))
-      return rc;
-    attr = true;
-  }
-  if (BN == 384)
-    tg::tgemm_mn_kernel<384><<<grid, 160, tg::Cfg<384>::SMEM, st>>>(tmA, tmB, dst, ldd, M, N, K, kps, acc, (size_t)M * N);
-  else if (BN == 256)
-    tg::tgemm_mn_kernel<256><<<grid, 160, tg::Cfg<256>::SMEM, st>>>(tmA, tmB, dst, ldd, M, N, K, kps, acc, (size_t)M * N);
-  else
-    tg::tgemm_mn_kernel<128><<<grid, 160, tg::Cfg<128>::SMEM, st>>>(tmA, tmB, dst, ldd, M, N, K, kps, acc, (size_t)M * N);
-  FSN_CHECK_LAUNCH("tgemm_mn_kernel");
-  if (S > 1) return splitk_reduce_launch(scratch, S, M, N, C, ldc, accumulate, st);
-  return FSN_OK;
-}
-
 }  // namespace fsn
 
 // debug / unit-test entry point (tests/test_gpu_train.py): C[M,N] (+)= A[M,K] B[N,K]^T on the tcgen05 path
@@ -557,12 +394,4 @@ extern "C" int fsn_debug_tgemm(const float* A, int64_t lda, const float* B, int6
                                fsn_stream_t stream) {
   return fsn::tgemm_launch(A, (size_t)lda, B, (size_t)ldb, C, (size_t)ldc, M, N, K, accumulate != 0, scratch,
                            (size_t)scratch_floats, (cudaStream_t)stream);
-}
-
-// EXPERIMENTAL (tgemm_mn_kernel): C[M,N] (+)= A^T B with A [K,M], B [K,N]
-extern "C" int fsn_debug_tgemm_mn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M,
-                                  int N, int K, int accumulate, float* scratch, int64_t scratch_floats,
-                                  fsn_stream_t stream) {
-  return fsn::tgemm_mn_launch(A, (size_t)lda, B, (size_t)ldb, C, (size_t)ldc, M, N, K, accumulate != 0, scratch,
-                              (size_t)scratch_floats, (cudaStream_t)stream);
 }

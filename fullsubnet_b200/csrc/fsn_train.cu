@@ -569,19 +569,6 @@ static int layer_weight_grads(const LayerBwd& L, int Tp, const float* X, float* 
   const int H4 = 4 * L.H;
   const int rows = Tp * L.R;
   int rc;
-  if (L.w_hhT && tgemm_mn_enabled() && (L.K0 & 3) == 0) {
-    // EXPERIMENTAL (FSN_TGEMM_MN=1): MN-major operands straight from dG [rows,4H] and X / H [rows, K0 / H] - no transposes
-    if ((rc = tgemm_mn_launch(L.s.G, H4, X, L.K0, g_w_ih, L.K0, H4, L.K0, rows, false, w.splitk, SPLITK_SCRATCH_FLOATS, st)))
-      return rc;
-    if (Tp > 1) {
-      if ((rc = tgemm_mn_launch(L.s.G + (size_t)L.R * H4, H4, L.s.H, L.H, g_w_hh, L.H, H4, L.H, rows - L.R, false, w.splitk,
-                                SPLITK_SCRATCH_FLOATS, st)))
-        return rc;
-    } else if ((rc = check_cuda(cudaMemsetAsync(g_w_hh, 0, (size_t)H4 * L.H * sizeof(float), st), "memset"))) {
-      return rc;
-    }
-    return colsum_launch(L.s.G, (size_t)rows, H4, H4, g_b_ih, g_b_hh, w.colsum, st);
-  }
   if (L.w_hhT && (L.R & 3) == 0) {
     // tensor-core path: K-major operands = transposed copies dG^T [4H, rows], X^T [K0, rows], H^T [H, rows]
     if ((rc = transpose_launch(L.s.G, (size_t)rows, H4, w.gT, st))) return rc;

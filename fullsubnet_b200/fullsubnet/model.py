@@ -116,8 +116,6 @@ class Model(BaseModel):
             if self.precision not in ("fp32", "f16_tc", "f16x3_tc"):
                 raise ValueError("precision must be 'fp32', 'f16x3_tc', 'f16_tc' or 'auto'")
             return self.precision
-        if self.norm_type == "cumulative_laplace_norm":  # per-step scales: built for the fp32 kernels
-            return "fp32"
         d = self._desc("f16x3_tc", 1)
         return "f16x3_tc" if _lib.load().fsn_sb_packed_bytes(C.byref(d)) > 0 else "fp32"
 

@@ -10,7 +10,11 @@
  * Conventions
  *   - every pointer is a DEVICE pointer to contiguous fp32 unless noted; the caller allocates
  *     all buffers including the workspace; the library never allocates, frees or retains
- *     pointers across calls and keeps no mutable global state (re-entrant across streams);
+ *     DATA pointers across calls, so compute calls are re-entrant across streams and threads.  The
+ *     only mutable state it keeps is diagnostic and host-side: the thread-local last-error string /
+ *     code, the thread-local profiling switch with its per-stage CUDA events (fsn_set_profiling,
+ *     fsn_last_stage_ms), a thread-local launch counter (fsn_last_launch_count) and one process-wide
+ *     launch total (fsn_total_launch_count, a relaxed counter); none of it influences results;
  *   - `stream` is a cudaStream_t; nothing synchronises the host;
  *   - return value 0 = ok, non-zero = error; fsn_last_error() gives a thread-local message.
  *     Shape-contract violations that are AssertionError / NotImplementedError in the reference
@@ -314,6 +318,11 @@ int fsn_fullband_forward(const fsn_fullband_desc* d, const fsn_lstm_layer* layer
  * gain = 0.8 * 32767 in the reference; float32 multiply, divide, truncation toward zero like numpy; all-zero clip -> 0 */
 int fsn_peak_normalize_int16(const float* wav, int B, int L, float gain, int16_t* out, fsn_stream_t stream);
 
+/* audio_zen/metrics.py:6-31  SI_SDR(reference, estimation) (the validation metric of
+ * fullsubnet/trainer.py:78-181 that is pure arithmetic; STOI / PESQ are third-party CPU packages and stay out).
+ * reference, estimation [B,L] -> out[B] in dB; fixed-order reductions. */
+int fsn_si_sdr(const float* reference, const float* estimation, int B, int L, float* out, fsn_stream_t stream);
+
 /* unit-test hooks (host code only): the drop_band row map of Model.forward and its inverse (-1 = unit dropped), and
  * the reflect-padding multiplicity c[r] of the closed-form second norm */
 int fsn_debug_row_to_unit(int B, int F, int G, int r, int* b, int* f);
@@ -324,10 +333,7 @@ int fsn_debug_reflect_count(int r, int F, int N);
  * operands with 16-byte aligned rows; scratch (optional) enables split-K */
 int fsn_debug_tgemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
                     int K, int accumulate, float* scratch, int64_t scratch_floats, fsn_stream_t stream);
-/* EXPERIMENTAL (not yet run on hardware; nothing calls it unless FSN_TGEMM_MN=1): the MN-major variant,
- * C[M,N] (+)= A^T B with A stored [K,M] and B stored [K,N] */
-int fsn_debug_tgemm_mn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
-                       int K, int accumulate, float* scratch, int64_t scratch_floats, fsn_stream_t stream);
+
 
 #ifdef __cplusplus
 }

@@ -66,3 +66,34 @@ def _grad_worker(rank, world, port):
 def test_two_rank_gloo_flat_gradient_allreduce():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_grad_worker, args=(2, port), nprocs=2, join=True)
+
+
+# ------------------------------------------------------------------ trainer start-up: every rank starts from rank 0's weights
+def _bcast_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fullsubnet_b200.fullsubnet.model import Model
+    from fullsubnet_b200.trainer import broadcast_parameters, unwrap
+    torch.manual_seed(100 + rank)  # DIFFERENT initial weights per rank: without the broadcast the replicas diverge
+    m = Model(num_freqs=9, look_ahead=1, sequence_model="LSTM", fb_num_neighbors=0, sb_num_neighbors=2,
+              fb_output_activate_function="ReLU", sb_output_activate_function=False, fb_model_hidden_size=8,
+              sb_model_hidden_size=4, weight_init=True)
+    before = [p.detach().clone() for p in m.parameters()]
+    broadcast_parameters(m, dist, src=0)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, [p.detach().clone() for p in m.parameters()])
+    for a, b in zip(gathered[0], gathered[1]):
+        assert torch.equal(a, b)
+    if rank == 0:
+        assert all(torch.equal(a, b) for a, b in zip(before, m.parameters()))  # rank 0 keeps its own
+    else:
+        assert any(not torch.equal(a, b) for a, b in zip(before, m.parameters()))
+    ddp = torch.nn.parallel.DistributedDataParallel(torch.nn.Linear(2, 2))
+    assert unwrap(ddp) is ddp.module and unwrap(m) is m
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_parameter_broadcast():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_bcast_worker, args=(2, port), nprocs=2, join=True)

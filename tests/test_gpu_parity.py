@@ -299,24 +299,33 @@ def test_cumulative_laplace_norm_matches_reference(golden, dev):
     g = golden("model_cum")
     args = dict(small_args(), norm_type="cumulative_laplace_norm")
     m = make_model(args, O.make_state_dict(seed=7, args=args), dev, "auto")
-    assert m._resolve_precision() == "fp32"
+    assert m._resolve_precision() == "fp32"  # hidden 24: the tensor-core kernels do not cover it
     mag = T(g["small_mag"], dev).unsqueeze(1)
     with torch.no_grad():
         assert rel_max(m(mag[:1]).cpu(), g["small_b1"]) < 2e-5
         assert rel_max(m(mag).cpu(), g["small_g2"]) < 2e-5  # B=3: drop_band + per-unit running means
     full = dict(O.DEFAULT_MODEL_ARGS, norm_type="cumulative_laplace_norm")
-    mf = make_model(full, O.make_state_dict(seed=0, args=full, sb_fc_gain=60.0), dev, "auto")
-    wav, crm = mf.enhance(T(g["full_y"], dev), return_crm=True)
-    assert rel_max(crm.cpu(), g["full_crm"]) < 5e-5
-    assert np.abs(wav.cpu().numpy() - g["full_wav"]).max() < WAV_TOL
+    for prec, tol in (("fp32", 5e-5), ("auto", 5e-5), ("f16_tc", CRM_TOL)):
+        # auto = the compensated tensor-core path: per-step unit scales inside the tcgen05 gather warp
+        mf = make_model(full, O.make_state_dict(seed=0, args=full, sb_fc_gain=60.0), dev, prec)
+        if prec == "auto":
+            assert mf._resolve_precision() == "f16x3_tc"
+        wav, crm = mf.enhance(T(g["full_y"], dev), return_crm=True)
+        assert rel_max(crm.cpu(), g["full_crm"]) < tol, prec
+        if prec != "f16_tc":
+            assert np.abs(wav.cpu().numpy() - g["full_wav"]).max() < WAV_TOL, prec
+        # a batch large enough for the tensor-core full-band path (time-major per-(step, clip) scales): every copy of
+        # the clip gives the single-clip result
+        y = T(g["full_y"], dev)
+        wav_b = mf.enhance(y.repeat(10, 1))  # 20 clips: c0, c1, c0, c1, ...
+        assert np.abs(wav_b.cpu().numpy() - np.tile(g["full_wav"], (10, 1))).max() < (
+            WAV_TOL if prec != "f16_tc" else 1e-2), prec
 
 
 def test_cumulative_laplace_norm_unsupported_combinations(dev):
     from oracle import fullsubnet_oracle as O
     full = dict(O.DEFAULT_MODEL_ARGS, norm_type="cumulative_laplace_norm")
     sd = O.make_state_dict(seed=0, args=full)
-    with pytest.raises(NotImplementedError), torch.no_grad():
-        make_model(full, sd, dev, "f16_tc")(torch.rand(1, 1, 257, 4, device=dev))  # tensor-core path: offline norm only
     with pytest.raises(NotImplementedError):
         make_model(full, sd, dev, "auto").train()(torch.rand(3, 1, 257, 5, device=dev))  # training: offline norm only
 

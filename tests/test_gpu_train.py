@@ -210,3 +210,122 @@ def test_tf32_tensor_core_gemm_matches_truncated_reference(dev):
         err = ((Cc[:, :N].double() - ref).abs().max() / ref.abs().max()).item()
         assert err < 1e-4, (M, N, K, err)
         assert torch.equal(Cc[:, N:], C0[:, N:])
+
+
+def test_reference_trainer_flow_ddp_autocast_gradscaler(golden, dev):
+    """The reference's own optimisation flow (fullsubnet/trainer.py:56-69, base_trainer.py:32,46) on the drop-in Model:
+    DistributedDataParallel (NCCL, world 1) + autocast + GradScaler + unscale_ + clip_grad_norm_ + torch.optim.Adam,
+    two steps, equal to the golden steps of the unmodified reference."""
+    import os
+    import torch.distributed as dist
+    from torch.cuda.amp import GradScaler, autocast
+    from torch.nn.parallel import DistributedDataParallel
+    from fullsubnet_b200.acoustics.feature import drop_band, stft
+    from fullsubnet_b200.acoustics.mask import build_complex_ideal_ratio_mask
+    from oracle import fullsubnet_oracle as O
+    g = golden("train_small")
+    args = small_args()
+    core = build(args, O.make_state_dict(seed=7, args=args, sb_fc_gain=8.0), dev, "fp32")
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29541")
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+    try:
+        model = DistributedDataParallel(core, device_ids=[0])
+        optimizer = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.999))
+        loss_function = torch.nn.MSELoss()
+        scaler = GradScaler(enabled=True)
+        noisy, clean = T(g["noisy"], dev), T(g["clean"], dev)
+        for it in range(2):
+            optimizer.zero_grad()
+            noisy_mag, _, nr, ni = stft(noisy, 64, 32, 64)
+            _, _, cr, ci = stft(clean, 64, 32, 64)
+            cIRM = build_complex_ideal_ratio_mask(nr, ni, cr, ci)
+            cIRM = drop_band(cIRM.permute(0, 3, 1, 2), model.module.num_groups_in_drop_band).permute(0, 2, 3, 1)
+            with autocast(enabled=True):
+                cRM = model(noisy_mag.unsqueeze(1)).permute(0, 2, 3, 1)
+                loss = loss_function(cIRM, cRM)
+            scaler.scale(loss).backward()
+            scaler.unscale_(optimizer)
+            gn = torch.nn.utils.clip_grad_norm_(model.parameters(), 10)
+            scaler.step(optimizer)
+            scaler.update()
+            assert abs(float(loss) - g["loss"][it]) <= 1e-5 * abs(g["loss"][it]), (float(loss), g["loss"][it])
+            assert abs(float(gn) - g["gnorm"][it]) < 1e-4 * g["gnorm"][it]
+            if it == 0:
+                for k, p in model.module.named_parameters():
+                    assert rel_l2(p.grad.cpu(), g["grad." + k]) < GRAD_TOL["fp32"], k
+            for k, v in model.module.state_dict().items():
+                assert np.abs(v.cpu().numpy() - g[f"p{it}." + k]).max() < 2e-5, (it, k)
+        # the Trainer accepts the DDP-wrapped model (no second all-reduce, checkpoints without the `module.` prefix)
+        from fullsubnet_b200.trainer import Trainer
+        cfg = {"meta": {"use_amp": True, "save_dir": "/tmp/fsn_t", "experiment_name": "ddp"},
+               "acoustics": {"n_fft": 64, "hop_length": 32, "win_length": 64},
+               "trainer": {"train": {"epochs": 1, "save_checkpoint_interval": 1, "clip_grad_norm_value": 10}}}
+        tr = Trainer(dist, 0, cfg, False, False, model, loss_function, optimizer, [(g["noisy"], g["clean"])], None)
+        assert tr.is_ddp and tr.core is core
+        l3 = tr.train_step(torch.from_numpy(g["noisy"]), torch.from_numpy(g["clean"]))
+        assert torch.isfinite(l3)
+        tr._save_checkpoint(1)
+        ck = torch.load("/tmp/fsn_t/ddp/checkpoints/latest_model.tar", map_location="cpu")
+        assert all(not k.startswith("module.") for k in ck["model"])
+    finally:
+        if created:
+            dist.destroy_process_group()
+
+
+def test_si_sdr_kernel_matches_reference_formula(dev):
+    """audio_zen/metrics.py:6-31 restated in numpy float32 vs fsn_si_sdr."""
+    from fullsubnet_b200.trainer import si_sdr
+    rng = np.random.default_rng(3)
+    ref = rng.standard_normal((5, 64000)).astype(np.float32) * 0.1
+    est = (0.7 * ref + 0.05 * rng.standard_normal((5, 64000))).astype(np.float32)
+    est[4] = ref[4] * 1.5 + 1e-4 * rng.standard_normal(64000).astype(np.float32)  # high SI-SDR
+
+    def SI_SDR(reference, estimation):
+        estimation, reference = np.broadcast_arrays(estimation, reference)
+        reference_energy = np.sum(reference ** 2, axis=-1, keepdims=True)
+        optimal_scaling = np.sum(reference * estimation, axis=-1, keepdims=True) / reference_energy
+        projection = optimal_scaling * reference
+        noise = estimation - projection
+        return 10 * np.log10(np.sum(projection ** 2, axis=-1) / np.sum(noise ** 2, axis=-1))
+    got = si_sdr(torch.from_numpy(ref).to(dev), torch.from_numpy(est).to(dev)).cpu().numpy()
+    want = SI_SDR(ref.astype(np.float64), est.astype(np.float64))
+    assert np.abs(got - want).max() < 2e-3, (got, want)
+    assert np.abs(got - SI_SDR(ref, est)).max() < 5e-3
+
+
+def test_trainer_with_validation_loader(golden, dev, tmp_path):
+    """train.py:65-80 always passes a validation dataloader: the B=1 validation loop (trainer.py:78-181) runs on the
+    device (loss + enhance + SI-SDR) and its numbers equal the op-by-op evaluation of the same items."""
+    from fullsubnet_b200.inferencer import Inferencer
+    from fullsubnet_b200.loss import mse_loss
+    from fullsubnet_b200.optim import FusedClipAdam
+    from fullsubnet_b200.trainer import Trainer, si_sdr
+    from oracle import fullsubnet_oracle as O
+    g = golden("train_small")
+    args = small_args()
+    sd = O.make_state_dict(seed=7, args=args, sb_fc_gain=8.0)
+    cfg = {"meta": {"use_amp": False, "save_dir": str(tmp_path), "experiment_name": "v"},
+           "acoustics": {"n_fft": 64, "hop_length": 32, "win_length": 64},
+           "trainer": {"train": {"epochs": 1, "save_checkpoint_interval": 1, "clip_grad_norm_value": 10},
+                       "validation": {"validation_interval": 1, "save_max_metric_score": True}}}
+    noisy, clean = torch.from_numpy(g["noisy"]), torch.from_numpy(g["clean"])
+    valid = [(noisy[i:i + 1], clean[i:i + 1], [f"clip{i}"], ["With_reverb" if i % 2 == 0 else "No_reverb"])
+             for i in range(4)]
+    m = build(args, sd, dev)
+    tr = Trainer(None, 0, cfg, False, False, m, mse_loss(), FusedClipAdam(m.parameters(), lr=1e-3),
+                 [(noisy, clean)], valid)
+    tr.train()
+    v = tr.last_validation
+    assert v["items"] == {"With_reverb": 2, "No_reverb": 2} and np.isfinite(v["loss_total"])
+    assert (tmp_path / "v" / "checkpoints" / "best_model.tar").exists() and tr.best_score == v["si_sdr"]["With_reverb"]
+    assert m.training  # validation restores the training mode
+    # same items through the Inferencer + SI-SDR, one by one
+    inf = Inferencer(config={"acoustics": cfg["acoustics"]}, model=m, device=dev)
+    scores = []
+    for i in (0, 2):
+        enh = torch.from_numpy(inf.full_band_crm_mask(noisy[i:i + 1].to(dev), {}))[None].to(dev)
+        scores.append(float(si_sdr(clean[i:i + 1].to(dev), enh)[0]))
+    assert abs(np.mean(scores) - v["si_sdr"]["With_reverb"]) < 1e-3

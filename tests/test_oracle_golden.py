@@ -237,3 +237,34 @@ def test_fullband_baseline_oracle_matches_reference(golden):
     for tag, a in (("small", small), ("full", dict(BO.DEFAULT_FBB_ARGS))):
         out = BO.fbb_forward(T(g[tag + "_mag"]), BO.make_fbb_state_dict(seed=11, args=a), a)
         assert out.shape == g[tag + "_out"].shape and rel_max(out, g[tag + "_out"]) < 2e-5, tag
+
+
+# ------------------------------------------------------------------ the timed CPU arm and the config-length fixtures
+def test_libcall_port_is_the_reference_computation(golden):
+    """bench.py's CPU arm (oracle/libcall_port.py: the path written with the reference's own torch library calls)
+    reproduces the outputs of the unmodified reference - so what is TIMED on the host is the reference's computation."""
+    from oracle import libcall_port as P
+    g = golden("model_full")
+    y = T(g["y"])
+    for tag, gain in (("wa", 1.0), ("wb", WB_GAIN)):
+        wav, crm = P.enhance(y, P.LibcallModel(O.make_state_dict(seed=0, sb_fc_gain=gain)), return_crm=True)
+        assert rel_max(crm, g[f"{tag}_crm"]) < 1e-6
+        assert np.abs(wav.numpy() - g[f"{tag}_wav"]).max() < 1e-6
+
+
+def _fingerprint(y):
+    a = y.numpy().astype(np.float64)
+    return np.concatenate([a.reshape(-1)[:8], [a.sum(), np.abs(a).sum()]])
+
+
+def test_oracle_at_config_length_4s(golden):
+    """T = 251 (BASELINE configs 0/1 clip length), both weight sets: oracle vs the unmodified reference."""
+    g = golden("model_full_4s")
+    y = O.make_noisy(1, 64000, seed=40, speechlike=True)
+    assert np.allclose(_fingerprint(y), g["y_fp"], rtol=0, atol=1e-9)
+    torch.set_num_threads(8)
+    for tag, gain in (("wa", 1.0), ("wb", WB_GAIN)):
+        with torch.no_grad():
+            wav, crm = O.enhance(y, O.make_state_dict(seed=0, sb_fc_gain=gain), return_crm=True)
+        assert rel_max(crm, g[f"{tag}_crm"]) < 5e-5 and rel_l2(crm, g[f"{tag}_crm"]) < 5e-5
+        assert np.abs(wav.numpy() - g[f"{tag}_wav"]).max() < 1e-4

@@ -53,45 +53,6 @@ def run(M, N, K, lda=None, ldb=None, ldc=None, acc=False, split=False, check=Tru
     print(msg, flush=True)
 
 
-def run_mn(M, N, K, lda=None, ldb=None, split=False, reps=0):
-    """EXPERIMENTAL MN-major variant (fsn_debug_tgemm_mn): C = A^T B with A [K,M], B [K,N].  FSN_TGEMM_MN=1 not needed here."""
-    lda, ldb = lda or M, ldb or N
-    g = torch.Generator(device="cpu").manual_seed(M + N + K)
-    A = torch.randn(K, lda, generator=g).to(dev)
-    B = torch.randn(K, ldb, generator=g).to(dev)
-    Cc = torch.zeros(M, N, device=dev)
-    scratch = torch.empty(16 << 20, device=dev) if split else None
-    st = torch.cuda.current_stream().cuda_stream
-
-    def call():
-        _lib.check(lib.fsn_debug_tgemm_mn(A.data_ptr(), lda, B.data_ptr(), ldb, Cc.data_ptr(), N, M, N, K, 0,
-                                          scratch.data_ptr() if split else None, scratch.numel() if split else 0, st))
-    call()
-    torch.cuda.synchronize()
-    ref = trunc_tf32(A[:, :M]).double().T @ trunc_tf32(B[:, :N]).double()
-    err = (Cc.double() - ref).abs().max().item() / ref.abs().max().item()
-    msg = f"MN-major M={M} N={N} K={K} lda={lda} ldb={ldb} split={split}: err vs tf32-trunc {err:.2e}"
-    if reps:
-        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-        e0.record()
-        for _ in range(reps):
-            call()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        msg += f"  {ms * 1e3:.1f} us  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s"
-    print(msg, flush=True)
-
-
-if len(sys.argv) > 1 and sys.argv[1] == "--mn":
-    run_mn(128, 128, 32)
-    run_mn(128, 128, 256)
-    run_mn(200, 72, 100, lda=200, ldb=72)
-    run_mn(1536, 32, 70000, split=True)
-    run_mn(1536, 384, 70000, split=True)
-    run_mn(1536, 384, 1556480 // 4, split=True, reps=2)
-    sys.exit(0)
-
 run(128, 128, 32)
 run(128, 128, 64)
 run(128, 256, 256)
