@@ -121,6 +121,9 @@ _SIGNATURES = {
     "fsn_debug_row_to_unit": (C.c_int, [_I, _I, _I, _I, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "fsn_debug_unit_to_row": (C.c_int, [_I, _I, _I, _I, _I]),
     "fsn_debug_reflect_count": (C.c_int, [_I, _I, _I]),
+    "fsn_debug_lstm_tc_workspace_bytes": (_S, [_I, _I, _I, _I, _I]),
+    "fsn_debug_lstm_layer_tc": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _S, _P]),
+    "fsn_debug_linear_tc": (C.c_int, [_P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _S, _P]),
     "fsn_debug_tgemm": (C.c_int, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _P, _L, _P]),
     "fsn_last_error_code": (C.c_int, []),
     "fsn_last_launch_count": (C.c_int64, []),

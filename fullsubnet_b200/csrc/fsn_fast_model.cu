@@ -86,6 +86,7 @@ static bool fast_tc_ok(const fsn_fast_desc* d) {
   const int K = (2 * d->noisy_num_neighbors + 1) + (2 * d->enc_num_neighbors + 1);
   return sb_tc2_enabled() && d->bn_hidden == 384 && d->bn_layers == 2 && K <= 32;
 }
+static bool fast_x3(const fsn_fast_desc* d) { return d->precision == FSN_PREC_F16X3_TC; }
 
 struct FastWs {
   float *magT, *melT, *encT, *bn, *bn_out, *dec_in, *dec_out, *inv1, *inv2;
@@ -95,8 +96,18 @@ struct FastWs {
   float *d1_h[2], *d1_c, *d2_hall, *d2_c;
   float* pp;               // h0 ping-pong of the persistent LSTM kernel [2][256][max H0]
   unsigned int* barrier;
+  LstmTcWs tc;             // tensor-core LSTM layers of the encoder / decoder (fsn_lstm_rec_tc.cu)
+  float* tc_mid;           // first layer's output for every step [B*Tp, max(He1, Hd)]
   size_t bytes;
 };
+
+static bool fast_is_tc(const fsn_fast_desc* d) { return d->precision == FSN_PREC_F16_TC || d->precision == FSN_PREC_F16X3_TC; }
+// encoder / decoder LSTM pairs on the tensor cores?
+static bool fast_lstm_tc(const fsn_fast_desc* d) {
+  const bool x3 = d->precision == FSN_PREC_F16X3_TC;
+  return fast_is_tc(d) && lstm_rec_tc_supported(d->enc1_hidden, x3) && lstm_rec_tc_supported(d->enc2_hidden, x3) &&
+         lstm_rec_tc_supported(d->dec_hidden, x3);
+}
 
 struct FCarver {
   char* base; size_t off;
@@ -140,7 +151,7 @@ static void fast_carve(const fsn_fast_desc* d, const FastDims& m, void* base, Fa
   w.e1_c = c.take<float>((size_t)m.B * d->enc1_hidden);
   w.e2_hall = c.take<float>(BT * d->enc2_hidden);
   w.e2_c = c.take<float>((size_t)m.B * d->enc2_hidden);
-  if (d->precision == FSN_PREC_FP32) {
+  if (!fast_is_tc(d)) {
     for (int i = 0; i < 2; ++i) { w.bn_h0[i] = c.take<float>(R * d->bn_hidden); w.bn_h1[i] = c.take<float>(R * d->bn_hidden); }
     w.bn_c0 = c.take<float>(R * d->bn_hidden);
     w.bn_c1 = c.take<float>(R * d->bn_hidden);
@@ -151,6 +162,15 @@ static void fast_carve(const fsn_fast_desc* d, const FastDims& m, void* base, Fa
   w.d2_c = c.take<float>((size_t)m.B * d->dec_hidden);
   w.pp = c.take<float>((size_t)2 * 256 * (d->dec_hidden > d->enc1_hidden ? d->dec_hidden : d->enc1_hidden));
   w.barrier = c.take<unsigned int>(64);
+  memset(&w.tc, 0, sizeof(w.tc));
+  w.tc_mid = nullptr;
+  if (fast_lstm_tc(d)) {
+    int Hm = d->enc1_hidden > d->enc2_hidden ? d->enc1_hidden : d->enc2_hidden;
+    if (d->dec_hidden > Hm) Hm = d->dec_hidden;
+    int Km = Hm > 2 * m.M ? Hm : 2 * m.M;
+    lstm_tc_carve(c.base, c.off, BT, Km, Hm, d->precision == FSN_PREC_F16X3_TC, w.tc);
+    w.tc_mid = c.take<float>(BT * (d->enc1_hidden > d->dec_hidden ? d->enc1_hidden : d->dec_hidden));
+  }
   w.bytes = c.off;
 }
 
@@ -159,9 +179,14 @@ static void fast_carve(const fsn_fast_desc* d, const FastDims& m, void* base, Fa
 static int run_lstm_pair(const fsn_lstm_layer& la, int Ka, int Ha, const fsn_lstm_layer& lb, int Hb, int R, int steps,
                          const float* x, size_t x_row_stride, size_t x_step_stride, const float* row_scale,
                          float* ha[2], float* ca, float* hb_all, float* cb, float* pp, unsigned int* barrier,
-                         cudaStream_t st) {
+                         cudaStream_t st, const LstmTcWs* tc = nullptr, float* tc_mid = nullptr, bool x3 = false) {
   int rc;
   static const bool stepwise = getenv("FSN_FB_STEPWISE") != nullptr;
+  if (!stepwise && tc && tc_mid && x_step_stride == (size_t)Ka && x_row_stride == (size_t)steps * Ka) {
+    // tensor cores: per layer one hoisted input-projection GEMM + the persistent tcgen05 recurrence
+    if ((rc = lstm_layer_tc(la, x, (size_t)Ka, Ka, row_scale, steps, 0, R, steps, Ha, x3, *tc, tc_mid, st))) return rc;
+    return lstm_layer_tc(lb, tc_mid, (size_t)Ha, Ha, nullptr, 1, 0, R, steps, Hb, x3, *tc, hb_all, st);
+  }
   if (!stepwise && x_step_stride == (size_t)Ka && x_row_stride == (size_t)steps * Ka && fb_persistent_supported(Ka, Ha, Hb)) {
     // persistent cooperative wavefront kernel (fsn_fullband.cu), chunks of <= 256 rows
     fsn_seq_weights w2;
@@ -210,7 +235,7 @@ extern "C" size_t fsn_fast_workspace_bytes(const fsn_fast_desc* d, int B, int T)
   return w.bytes;
 }
 
-extern "C" size_t fsn_fast_packed_bytes(const fsn_fast_desc* d) { return fast_tc_ok(d) ? sb_tc2_packed_bytes() : 0; }
+extern "C" size_t fsn_fast_packed_bytes(const fsn_fast_desc* d) { return fast_tc_ok(d) ? sb_tc2_packed_bytes(fast_x3(d)) : 0; }
 
 extern "C" int fsn_fast_pack_bn_weights(const fsn_fast_desc* d, const fsn_fast_weights* wt, void* packed,
                                         fsn_stream_t stream) {
@@ -219,7 +244,7 @@ extern "C" int fsn_fast_pack_bn_weights(const fsn_fast_desc* d, const fsn_fast_w
   for (int l = 0; l < 2; ++l) { s.w_ih[l] = wt->bn[l].w_ih; s.w_hh[l] = wt->bn[l].w_hh; s.b_ih[l] = wt->bn[l].b_ih; s.b_hh[l] = wt->bn[l].b_hh; }
   s.fc_w = wt->bn_fc_w; s.fc_b = wt->bn_fc_b;
   const int K = (2 * d->noisy_num_neighbors + 1) + (2 * d->enc_num_neighbors + 1);
-  return sb_tc2_pack_raw(&s, K, /*fc_out=*/1, packed, (cudaStream_t)stream);
+  return sb_tc2_pack_raw(&s, K, /*fc_out=*/1, packed, (cudaStream_t)stream, fast_x3(d));
 }
 
 extern "C" int fsn_fast_model_forward(const fsn_fast_desc* d, const fsn_fast_weights* wt, const float* mix_mag, int B,
@@ -234,6 +259,8 @@ extern "C" int fsn_fast_model_forward(const fsn_fast_desc* d, const fsn_fast_wei
               workspace_bytes, w.bytes);
   cudaStream_t st = (cudaStream_t)stream;
   const int Tp = m.Tp, M = m.M, F = m.F, R = B * M;
+  const bool lstm_tc = fast_lstm_tc(d);
+  static const int tc_mask = getenv("FSN_FAST_TC_MASK") ? atoi(getenv("FSN_FAST_TC_MASK")) : 15;  // debug: 1 enc LSTMs, 2 enc fc, 4 dec LSTMs, 8 dec fc
   // look-ahead pad + time-major layout, Mel filtering (model.py:161-166)
   if ((rc = transpose_mag_launch(mix_mag, w.magT, B, F, T, Tp, st))) return rc;
   if ((rc = fc_gemm_launch(w.magT, wt->mel_fb, nullptr, w.melT, B * Tp, F, M, FSN_ACT_NONE, st, /*w_kmajor=*/true)))
@@ -243,10 +270,16 @@ extern "C" int fsn_fast_model_forward(const fsn_fast_desc* d, const fsn_fast_wei
   if ((rc = norm_scales_launch(w.sums, w.sums, B, (float)M * Tp, 1.f, w.inv1, nullptr, st))) return rc;
   // F_l2m: LSTM(M->He1), LSTM(He1->He2) + Linear(M) + ReLU (model.py:35-54,171)
   if ((rc = run_lstm_pair(wt->enc1, M, d->enc1_hidden, wt->enc2, d->enc2_hidden, B, Tp, w.melT, (size_t)Tp * M, M,
-                          w.inv1, w.e1_h, w.e1_c, w.e2_hall, w.e2_c, w.pp, w.barrier, st)))
+                          w.inv1, w.e1_h, w.e1_c, w.e2_hall, w.e2_c, w.pp, w.barrier, st, (lstm_tc && (tc_mask & 1)) ? &w.tc : nullptr, w.tc_mid,
+                          fast_x3(d))))
     return rc;
-  if ((rc = fc_gemm_launch(w.e2_hall, wt->enc_fc_w, wt->enc_fc_b, w.encT, B * Tp, d->enc2_hidden, M, FSN_ACT_RELU, st)))
+  if (lstm_tc && (tc_mask & 2)) {
+    if ((rc = linear_tc(w.e2_hall, (size_t)d->enc2_hidden, d->enc2_hidden, wt->enc_fc_w, wt->enc_fc_b, M, FSN_ACT_RELU, w.encT,
+                        (size_t)M, (size_t)B * Tp, fast_x3(d), w.tc, st)))
+      return rc;
+  } else if ((rc = fc_gemm_launch(w.e2_hall, wt->enc_fc_w, wt->enc_fc_b, w.encT, B * Tp, d->enc2_hidden, M, FSN_ACT_RELU, st))) {
     return rc;
+  }
   // bottleneck input: unfold + concat + real-time down-sampling, then its norm (model.py:174-187)
   fast_bn_input_kernel<<<B * m.Ts, 256, 0, st>>>(w.melT, w.encT, B, Tp, M, d->noisy_num_neighbors,
                                                  d->enc_num_neighbors, m.S, m.Ts, w.bn, w.fs);
@@ -257,16 +290,16 @@ extern "C" int fsn_fast_model_forward(const fsn_fast_desc* d, const fsn_fast_wei
   // S: 2xLSTM(K->Hb->Hb) + Linear(1) + ReLU on B*M rows over Ts steps (model.py:188-189)
   const int Hb = d->bn_hidden;
   int bn_bstride = M;
-  if (d->precision == FSN_PREC_F16_TC) {
+  if (fast_is_tc(d)) {
     // tcgen05 CTA-pair kernel of the fullsubnet sub-band stack: same stack shape (K<=32 -> 384 -> 384), the gather
     // does the unfold AND the time down-sampling on the fly from melT / encT, Linear output 1 of 2 is zero-padded
     FSN_REQUIRE(wt->bn_packed && fast_tc_ok(d), FSN_ERR_UNSUPPORTED,
-                "fast model: FSN_PREC_F16_TC needs packed bottleneck weights, bn_hidden = 384 and input width <= 32");
+                "fast model: the tensor-core precisions need packed bottleneck weights, bn_hidden = 384 and input width <= 32");
     SbTcArgs a;
     memset(&a, 0, sizeof(a));
     a.packed = wt->bn_packed; a.magT = w.melT; a.fbT = w.encT; a.inv2 = w.inv2; a.crm = w.bn_out;
     a.B = B; a.F = M; a.Tp = Tp; a.la = 0; a.Ns = d->noisy_num_neighbors; a.Nf = d->enc_num_neighbors;
-    a.H = Hb; a.act = FSN_ACT_RELU; a.steps = m.Ts; a.shrink = m.S; a.pair = true;
+    a.H = Hb; a.act = FSN_ACT_RELU; a.steps = m.Ts; a.shrink = m.S; a.pair = true; a.x3 = fast_x3(d);
     a.map = RowMap{B, M, M, 1};
     if ((rc = sb_tc2_forward(a, st))) return rc;
     bn_bstride = 2 * M;
@@ -304,11 +337,17 @@ extern "C" int fsn_fast_model_forward(const fsn_fast_desc* d, const fsn_fast_wei
   }
   // F_m2l: LSTM(2M->Hd), LSTM(Hd->Hd) + Linear(2F) (model.py:77-96,196)
   if ((rc = run_lstm_pair(wt->dec1, 2 * M, d->dec_hidden, wt->dec2, d->dec_hidden, B, Tp, w.dec_in, (size_t)Tp * 2 * M,
-                          2 * M, nullptr, w.d1_h, w.d1_c, w.d2_hall, w.d2_c, w.pp, w.barrier, st)))
+                          2 * M, nullptr, w.d1_h, w.d1_c, w.d2_hall, w.d2_c, w.pp, w.barrier, st, (lstm_tc && (tc_mask & 4)) ? &w.tc : nullptr,
+                          w.tc_mid, fast_x3(d))))
     return rc;
-  if ((rc = fc_gemm_launch(w.d2_hall, wt->dec_fc_w, wt->dec_fc_b, w.dec_out, B * Tp, d->dec_hidden, 2 * F, FSN_ACT_NONE,
-                           st)))
+  if (lstm_tc && (tc_mask & 8)) {
+    if ((rc = linear_tc(w.d2_hall, (size_t)d->dec_hidden, d->dec_hidden, wt->dec_fc_w, wt->dec_fc_b, 2 * F, FSN_ACT_NONE,
+                        w.dec_out, (size_t)2 * F, (size_t)B * Tp, fast_x3(d), w.tc, st)))
+      return rc;
+  } else if ((rc = fc_gemm_launch(w.d2_hall, wt->dec_fc_w, wt->dec_fc_b, w.dec_out, B * Tp, d->dec_hidden, 2 * F, FSN_ACT_NONE,
+                                  st))) {
     return rc;
+  }
   dim3 grid(cdiv(T, 32), cdiv(F, 32), B * 2);
   fast_output_kernel<<<grid, dim3(32, 8), 0, st>>>(w.dec_out, B, Tp, F, d->look_ahead, out);
   FSN_CHECK_LAUNCH("fast_output_kernel");

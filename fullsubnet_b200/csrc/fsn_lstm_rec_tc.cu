@@ -268,7 +268,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_tc_kernel(const __grid_c
         }
       }
       if (p + 1 < T) {
-        __threadfence();  // this thread's h_p before its arrival at the named barrier / the release below
+        // publish h_p: every writer orders its own stores at gpu scope (and towards the async proxy, which is what
+        // reads them - the other CTAs' TMA loads), then the CTA-scope barrier, then one release by the arriving thread.
+        // (A single fence by the arriving thread after the barrier is NOT enough for the TMA readers: measured as
+        // stale-state errors of ~3e-4 on long sequences.)
+        __threadfence();
+        fence_proxy_async();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (threadIdx.x == 64) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
       }
@@ -359,7 +364,7 @@ static int rec_sm_count() {
 // tensor-core recurrence available for hidden size H on this device?
 bool lstm_rec_tc_supported(int H, bool x3) {
   static const bool off = getenv("FSN_NO_REC_TC") != nullptr;
-  if (off || H < rec::U || !rec::encoder()) return false;
+  if (off || H < 64 || !rec::encoder()) return false;  // H >= 64: see lstm_rec_tc_scratch_bytes
   int dev = 0, coop = 0, max_smem = 0, major = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
@@ -377,11 +382,13 @@ int lstm_rec_tc_rows_per_launch(int H) {
   return G * rec::MR;
 }
 
-// scratch of one launch: fp16 state ping-pong [2][parts][Rpad][Kp] + the group counters
+// scratch of one launch: fp16 state ping-pong [2][parts][rows][Kp] + the group counters.  The same scratch serves
+// layers of DIFFERENT hidden sizes (fast_fullsubnet: 384 / 257 / 512), so its size must not depend on H:
+// rows_per_launch * Kp <= (SMs * 8 / H) * 128 * (H + 63) < 2 * SMs * 8 * 128 elements for H >= 64.
+static size_t rec_state_capacity_bytes() { return align_up((size_t)2 * 2 * 2 * rec_sm_count() * 8 * 128 * sizeof(__half), 256); }
 size_t lstm_rec_tc_scratch_bytes(int H, bool x3) {
-  const int Kp = (H + rec::KB - 1) / rec::KB * rec::KB;
-  const size_t rows = (size_t)lstm_rec_tc_rows_per_launch(H);
-  return align_up(2 * (x3 ? 2 : 1) * rows * Kp * sizeof(__half), 256) + 64 * 32 * sizeof(unsigned int);
+  (void)H; (void)x3;
+  return rec_state_capacity_bytes() + 64 * 32 * sizeof(unsigned int);
 }
 
 // h_t for every step of one layer, given the hoisted input projection P (see Args for the strides); R rows (any
@@ -402,7 +409,8 @@ int lstm_rec_tc_launch(const float* w_hh, const float* b_ih, const float* b_hh, 
   const size_t smem = rec::smem_bytes(Kp, x3, stages);
   __half* state = (__half*)scratch;
   const size_t state_bytes = align_up((size_t)2 * parts * rows_max * Kp * sizeof(__half), 256);
-  unsigned int* barrier = (unsigned int*)((uint8_t*)scratch + state_bytes);
+  FSN_REQUIRE(state_bytes <= rec_state_capacity_bytes(), FSN_ERR_UNSUPPORTED, "lstm_rec_tc: state of H=%d exceeds the scratch", H);
+  unsigned int* barrier = (unsigned int*)((uint8_t*)scratch + rec_state_capacity_bytes());  // fixed place, whatever H
   int rc;
   const void* kern = x3 ? (const void*)rec::lstm_rec_tc_kernel<true> : (const void*)rec::lstm_rec_tc_kernel<false>;
   if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "lstm_rec_tc smem attr")))
@@ -412,8 +420,8 @@ int lstm_rec_tc_launch(const float* w_hh, const float* b_ih, const float* b_hh, 
     const int G = cdiv(nr, rec::MR);
     const int Rpad = G * rec::MR;
     // state of padded rows / padded k stays zero for the whole launch; counters start at zero
-    if ((rc = check_cuda(cudaMemsetAsync(scratch, 0, state_bytes + 64 * 32 * sizeof(unsigned int), st), "lstm_rec_tc memset")))
-      return rc;
+    if ((rc = check_cuda(cudaMemsetAsync(scratch, 0, state_bytes, st), "lstm_rec_tc memset"))) return rc;
+    if ((rc = check_cuda(cudaMemsetAsync(barrier, 0, 64 * 32 * sizeof(unsigned int), st), "lstm_rec_tc memset"))) return rc;
     CUtensorMap tm;
     cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)(2 * parts * Rpad)};
     cuuint64_t gstr[1] = {(cuuint64_t)Kp * sizeof(__half)};
@@ -476,4 +484,83 @@ int gemm_tc_split_launch(const float* A_hi, const float* A_lo, size_t lda, const
   return FSN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// One full LSTM layer and one Linear layer on top of the pieces above (what the model files call).
+void lstm_tc_carve(char* base, size_t& off, size_t rows_T, int Kmax, int Hmax, bool x3, LstmTcWs& ws) {
+  auto take = [&](size_t bytes) { char* r = base ? base + off : nullptr; off = align_up(off + bytes, 256); return r; };
+  const size_t wa = (size_t)((Kmax + 3) & ~3);
+  ws.a_hi = (float*)take(rows_T * wa * sizeof(float));
+  ws.a_lo = x3 ? (float*)take(rows_T * wa * sizeof(float)) : nullptr;
+  ws.w_hi = (float*)take((size_t)4 * Hmax * wa * sizeof(float));
+  ws.w_lo = x3 ? (float*)take((size_t)4 * Hmax * wa * sizeof(float)) : nullptr;
+  ws.P = (float*)take(rows_T * 4 * Hmax * sizeof(float));
+  ws.rec = take(lstm_rec_tc_scratch_bytes(Hmax, x3));
+}
+
+// operand A of a GEMM: x [rows, K] (row stride ldx) -> 16-byte aligned rows, scaled, split when x3
+static int prep_operand(const float* x, size_t ldx, int K, size_t rows, const float* row_scale, int rows_per_scale, int scale_B,
+                        bool x3, const LstmTcWs& ws, const float*& a_hi, const float*& a_lo, size_t& lda, cudaStream_t st) {
+  if (!x3 && !row_scale && (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    a_hi = x; a_lo = nullptr; lda = ldx;
+    return FSN_OK;
+  }
+  const int Kp = (K + 3) & ~3;
+  a_hi = ws.a_hi; a_lo = x3 ? ws.a_lo : nullptr; lda = (size_t)Kp;
+  return split_tf32_launch(x, rows, K, ldx, row_scale, rows_per_scale, ws.a_hi, x3 ? ws.a_lo : nullptr, Kp, st, scale_B);
+}
+
+// hall[r, t, :] (row stride T*H) of one LSTM layer over x[(r*T + t), :K] * scale
+int lstm_layer_tc(const fsn_lstm_layer& L, const float* x, size_t ldx, int K, const float* row_scale, int rows_per_scale,
+                  int scale_B, int R, int T, int H, bool x3, const LstmTcWs& ws, float* hall, cudaStream_t st) {
+  const size_t rows = (size_t)R * T;
+  const float *a_hi, *a_lo;
+  size_t lda;
+  int rc;
+  if ((rc = prep_operand(x, ldx, K, rows, row_scale, rows_per_scale, scale_B, x3, ws, a_hi, a_lo, lda, st))) return rc;
+  if ((rc = gemm_tc_split_launch(a_hi, a_lo, lda, L.w_ih, 4 * H, K, ws.w_hi, ws.w_lo, ws.P, (size_t)4 * H, rows, x3, st)))
+    return rc;
+  return lstm_rec_tc_launch(L.w_hh, L.b_ih, L.b_hh, ws.P, (size_t)T * 4 * H, (size_t)4 * H, hall, (size_t)T * H, (size_t)H, R, T,
+                            H, x3, ws.rec, st);
+}
+
+// out[rows, :N] (row stride ldo) = act(x[rows, :K] W[N,K]^T + bias)
+int linear_tc(const float* x, size_t ldx, int K, const float* W, const float* bias, int N, int act, float* out, size_t ldo,
+              size_t rows, bool x3, const LstmTcWs& ws, cudaStream_t st) {
+  const float *a_hi, *a_lo;
+  size_t lda;
+  int rc;
+  if ((rc = prep_operand(x, ldx, K, rows, nullptr, 1, 0, x3, ws, a_hi, a_lo, lda, st))) return rc;
+  if ((rc = gemm_tc_split_launch(a_hi, a_lo, lda, W, N, K, ws.w_hi, ws.w_lo, out, ldo, rows, x3, st))) return rc;
+  if (!bias && act == FSN_ACT_NONE) return FSN_OK;
+  return bias_act_launch(out, rows, N, ldo, bias, act, st);
+}
+
 }  // namespace fsn
+
+// unit-test hooks (tests/test_gpu_rec_tc.py): one LSTM layer / one Linear layer on the tensor-core path
+extern "C" size_t fsn_debug_lstm_tc_workspace_bytes(int R, int T, int K, int H, int x3) {
+  size_t off = 0;
+  fsn::LstmTcWs ws;
+  fsn::lstm_tc_carve(nullptr, off, (size_t)R * T, K > H ? K : H, H, x3 != 0, ws);
+  return off;
+}
+extern "C" int fsn_debug_lstm_layer_tc(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                       const float* x, int R, int T, int K, int H, int x3, float* hall, void* workspace,
+                                       size_t workspace_bytes, fsn_stream_t stream) {
+  FSN_REQUIRE(fsn::lstm_rec_tc_supported(H, x3 != 0), FSN_ERR_UNSUPPORTED, "lstm_layer_tc: hidden size %d not supported", H);
+  size_t off = 0;
+  fsn::LstmTcWs ws;
+  fsn::lstm_tc_carve((char*)workspace, off, (size_t)R * T, K > H ? K : H, H, x3 != 0, ws);
+  FSN_REQUIRE(workspace && workspace_bytes >= off, FSN_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, off);
+  fsn_lstm_layer L{w_ih, w_hh, b_ih, b_hh};
+  return fsn::lstm_layer_tc(L, x, (size_t)K, K, nullptr, 1, 0, R, T, H, x3 != 0, ws, hall, (cudaStream_t)stream);
+}
+extern "C" int fsn_debug_linear_tc(const float* x, int rows, int K, const float* W, const float* bias, int N, int act, int x3,
+                                   float* out, void* workspace, size_t workspace_bytes, fsn_stream_t stream) {
+  size_t off = 0;
+  fsn::LstmTcWs ws;
+  const int Hm = (N + 3) / 4 > 8 ? (N + 3) / 4 : 8;
+  fsn::lstm_tc_carve((char*)workspace, off, (size_t)rows, K, Hm, x3 != 0, ws);
+  FSN_REQUIRE(workspace && workspace_bytes >= off, FSN_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, off);
+  return fsn::linear_tc(x, (size_t)K, K, W, bias, N, act, out, (size_t)N, (size_t)rows, x3 != 0, ws, (cudaStream_t)stream);
+}

@@ -54,14 +54,15 @@ struct ModelWs {
   unsigned int* fb_barrier;
   float *sb_h0[2], *sb_h1[2], *sb_c0, *sb_c1;
   // tensor-core full-band path (fb_tc_forward): split operands, hoisted projection, layer-0 output, scratch
-  float *tc_a_hi, *tc_a_lo, *tc_w_hi, *tc_w_lo, *tc_P, *tc_h0all;
-  void* tc_rec;
+  LstmTcWs tc;
+  float* tc_h0all;
   size_t bytes;
 };
 
 // full-band stack on the tensor cores?  (tensor-core precisions, offline norm, enough clips to fill an MMA tile)
 static bool fb_tc_enabled(const fsn_model_desc* d, int B) {
-  static const int min_b = getenv("FSN_FB_TC_MIN_B") ? atoi(getenv("FSN_FB_TC_MIN_B")) : 16;
+  // every batch size takes the same path, so a clip's result does not depend on the batch it is enhanced in
+  static const int min_b = getenv("FSN_FB_TC_MIN_B") ? atoi(getenv("FSN_FB_TC_MIN_B")) : 1;
   if (d->precision != FSN_PREC_F16_TC && d->precision != FSN_PREC_F16X3_TC) return false;
   if (B < min_b) return false;
   return lstm_rec_tc_supported(d->fb_hidden, d->precision == FSN_PREC_F16X3_TC);
@@ -115,19 +116,13 @@ static void carve_model(const fsn_model_desc* d, const Dims& m, void* base, Mode
     w.sb_c0 = c.take<float>(RH);
     w.sb_c1 = c.take<float>(RH);
   }
-  w.tc_a_hi = w.tc_a_lo = w.tc_w_hi = w.tc_w_lo = w.tc_P = w.tc_h0all = nullptr;
-  w.tc_rec = nullptr;
+  memset(&w.tc, 0, sizeof(w.tc));
+  w.tc_h0all = nullptr;
   if (fb_tc_enabled(d, m.B)) {
-    const int Hf = d->fb_hidden, Fp = (m.F + 3) & ~3;
-    const size_t rows = (size_t)m.B * m.Tp, wa = (size_t)(Fp > Hf ? Fp : Hf);
-    const bool x3 = d->precision == FSN_PREC_F16X3_TC;
-    w.tc_a_hi = c.take<float>(rows * wa);
-    w.tc_a_lo = x3 ? c.take<float>(rows * wa) : nullptr;
-    w.tc_w_hi = c.take<float>((size_t)4 * Hf * wa);
-    w.tc_w_lo = x3 ? c.take<float>((size_t)4 * Hf * wa) : nullptr;
-    w.tc_P = c.take<float>(rows * 4 * Hf);
+    const int Hf = d->fb_hidden;
+    const size_t rows = (size_t)m.B * m.Tp;
+    lstm_tc_carve(c.base, c.off, rows, m.F > Hf ? m.F : Hf, Hf, d->precision == FSN_PREC_F16X3_TC, w.tc);
     w.tc_h0all = c.take<float>(rows * Hf);
-    w.tc_rec = c.take<char>(lstm_rec_tc_scratch_bytes(Hf, x3));
   }
   w.cum1 = w.cum2 = nullptr;
   if (d->norm_type == FSN_NORM_CUMULATIVE_LAPLACE) {
@@ -141,42 +136,19 @@ static void carve_model(const fsn_model_desc* d, const Dims& m, void* base, Mode
 // all steps as one tf32 GEMM (three passes on hi/lo splits when x3) and the recurrence in the persistent tcgen05
 // kernel; Linear(Hf -> F) + activation as the same GEMM + a bias/activation pass.  x3 keeps the fp32 error class.
 static int fb_tc_forward(const fsn_model_desc* d, const fsn_seq_weights* fb, const Dims& m, const ModelWs& w, cudaStream_t st) {
-  const int F = m.F, Tp = m.Tp, B = m.B, Hf = d->fb_hidden, Fp = (F + 3) & ~3;
+  const int F = m.F, Tp = m.Tp, B = m.B, Hf = d->fb_hidden;
   const bool x3 = d->precision == FSN_PREC_F16X3_TC;
-  const size_t rows = (size_t)B * Tp;
-  int rc;
-  // layer 0: x = magT * inv1[clip] (model.py:92), P = x W_ih0^T
-  // (cumulative norm: the scale of (clip, step) from the time-major table cum1[t*B + b], base_model.py:220-251)
   const bool cum = d->norm_type == FSN_NORM_CUMULATIVE_LAPLACE;
-  if ((rc = split_tf32_launch(w.magT, rows, F, (size_t)F, cum ? w.cum1 : w.inv1, Tp, w.tc_a_hi, w.tc_a_lo, Fp, st, cum ? B : 0)))
+  int rc;
+  fsn_lstm_layer L0{fb->w_ih[0], fb->w_hh[0], fb->b_ih[0], fb->b_hh[0]}, L1{fb->w_ih[1], fb->w_hh[1], fb->b_ih[1], fb->b_hh[1]};
+  // layer 0: x = magT * 1/(mu + 1e-5) of the clip (model.py:92); cumulative norm: the scale of (clip, step) from the
+  // time-major table cum1[t*B + b] (base_model.py:220-251)
+  if ((rc = lstm_layer_tc(L0, w.magT, (size_t)F, F, cum ? w.cum1 : w.inv1, Tp, cum ? B : 0, B, Tp, Hf, x3, w.tc, w.tc_h0all, st)))
     return rc;
-  if ((rc = gemm_tc_split_launch(w.tc_a_hi, w.tc_a_lo, Fp, fb->w_ih[0], 4 * Hf, F, w.tc_w_hi, w.tc_w_lo, w.tc_P,
-                                 (size_t)4 * Hf, rows, x3, st)))
-    return rc;
-  if ((rc = lstm_rec_tc_launch(fb->w_hh[0], fb->b_ih[0], fb->b_hh[0], w.tc_P, (size_t)Tp * 4 * Hf, (size_t)4 * Hf, w.tc_h0all,
-                               (size_t)Tp * Hf, (size_t)Hf, B, Tp, Hf, x3, w.tc_rec, st)))
-    return rc;
-  // layer 1: P = h0 W_ih1^T
-  const float *a_hi = w.tc_h0all, *a_lo = nullptr;
-  if (x3) {
-    if ((rc = split_tf32_launch(w.tc_h0all, rows, Hf, (size_t)Hf, nullptr, 1, w.tc_a_hi, w.tc_a_lo, Hf, st))) return rc;
-    a_hi = w.tc_a_hi; a_lo = w.tc_a_lo;
-  }
-  if ((rc = gemm_tc_split_launch(a_hi, a_lo, Hf, fb->w_ih[1], 4 * Hf, Hf, w.tc_w_hi, w.tc_w_lo, w.tc_P, (size_t)4 * Hf, rows,
-                                 x3, st)))
-    return rc;
-  if ((rc = lstm_rec_tc_launch(fb->w_hh[1], fb->b_ih[1], fb->b_hh[1], w.tc_P, (size_t)Tp * 4 * Hf, (size_t)4 * Hf, w.fb_h1all,
-                               (size_t)Tp * Hf, (size_t)Hf, B, Tp, Hf, x3, w.tc_rec, st)))
-    return rc;
+  if ((rc = lstm_layer_tc(L1, w.tc_h0all, (size_t)Hf, Hf, nullptr, 1, 0, B, Tp, Hf, x3, w.tc, w.fb_h1all, st))) return rc;
   // Linear(Hf -> F) + activation (sequence_model.py:119-123) -> fbT [B, Tp, F]
-  a_hi = w.fb_h1all; a_lo = nullptr;
-  if (x3) {
-    if ((rc = split_tf32_launch(w.fb_h1all, rows, Hf, (size_t)Hf, nullptr, 1, w.tc_a_hi, w.tc_a_lo, Hf, st))) return rc;
-    a_hi = w.tc_a_hi; a_lo = w.tc_a_lo;
-  }
-  if ((rc = gemm_tc_split_launch(a_hi, a_lo, Hf, fb->fc_w, F, Hf, w.tc_w_hi, w.tc_w_lo, w.fbT, (size_t)F, rows, x3, st)))
-    return rc;
-  return bias_act_launch(w.fbT, rows, F, (size_t)F, fb->fc_b, d->fb_activation, st);
+  return linear_tc(w.fb_h1all, (size_t)Hf, Hf, fb->fc_w, fb->fc_b, F, d->fb_activation, w.fbT, (size_t)F, (size_t)B * Tp, x3,
+                   w.tc, st);
 }
 
 // everything after the time-major magnitude exists: norms, full-band stack, sub-band stack

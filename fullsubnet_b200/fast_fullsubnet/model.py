@@ -67,7 +67,10 @@ class Model(BaseModel):
         if norm_type != "offline_laplace_norm":
             raise NotImplementedError(f"norm_type {norm_type!r} is not built for fast_fullsubnet (SURVEY 8f)")
         self.norm = self.norm_wrapper(norm_type)
-        # arithmetic of the bottleneck stack (92 % of the FLOPs): 'fp32' | 'f16_tc' (tcgen05 pair kernel) | 'auto'
+        # arithmetic: 'fp32' (FMA kernels) | 'f16x3_tc' (tensor cores, hi+lo split operands, the fp32 error class) |
+        # 'f16_tc' (tensor cores, single pass, ~1e-4) | 'auto' = f16x3_tc when the shape allows, else fp32.  The
+        # tensor-core modes run the bottleneck on the tcgen05 pair kernel and the encoder / decoder LSTMs + Linears
+        # on the hoisted-GEMM + persistent-recurrence kernels (fsn_lstm_rec_tc.cu)
         self.precision = precision or os.environ.get("FSN_PRECISION", "auto")
         self._packed = None
         self._packed_key = None
@@ -80,11 +83,11 @@ class Model(BaseModel):
         d = self._desc(_lib.PREC["f16_tc"])
         ok = _lib.load().fsn_fast_packed_bytes(C.byref(d)) > 0
         if self.precision == "auto":
-            return "f16_tc" if ok else "fp32"
-        if self.precision not in ("fp32", "f16_tc"):
-            raise ValueError("precision must be 'fp32', 'f16_tc' or 'auto'")
-        if self.precision == "f16_tc" and not ok:
-            raise NotImplementedError("f16_tc needs bottleneck_hidden_size = 384, 2 layers and input width <= 32")
+            return "f16x3_tc" if ok else "fp32"
+        if self.precision not in ("fp32", "f16_tc", "f16x3_tc"):
+            raise ValueError("precision must be 'fp32', 'f16x3_tc', 'f16_tc' or 'auto'")
+        if self.precision != "fp32" and not ok:
+            raise NotImplementedError("the tensor-core precisions need bottleneck_hidden_size = 384, 2 layers and input width <= 32")
         return self.precision
 
     def _desc(self, prec: int):
@@ -110,8 +113,8 @@ class Model(BaseModel):
         w.dec1, w.dec2 = self.decoder_lstm[0].layer_struct(0), self.decoder_lstm[1].layer_struct(0)
         w.dec_fc_w, w.dec_fc_b = self.decoder_lstm[1].fc_ptrs()
         w.bn_packed = None
-        if prec == "f16_tc":  # tile-ordered fp16 image of the bottleneck weights, rebuilt when a parameter changes
-            key = (self.bottleneck.version_key(), str(device))
+        if prec != "fp32":  # tile-ordered fp16 image of the bottleneck weights, rebuilt when a parameter changes
+            key = (self.bottleneck.version_key(), str(device), prec)
             if self._packed is None or self._packed_key != key:
                 lib = _lib.load()
                 buf = torch.empty(lib.fsn_fast_packed_bytes(C.byref(d)), dtype=torch.uint8, device=device)

@@ -334,6 +334,17 @@ int fsn_debug_reflect_count(int r, int F, int N);
 int fsn_debug_tgemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
                     int K, int accumulate, float* scratch, int64_t scratch_floats, fsn_stream_t stream);
 
+/* unit-test hooks for the tensor-core LSTM layer of the full-band stacks (fsn_lstm_rec_tc.cu;
+ * audio_zen/model/module/sequence_model.py:52-58,117): hall[r,t,:] of nn.LSTM(K -> H, 1 layer) over x [R,T,K]
+ * (hoisted input-projection GEMM + persistent tcgen05 recurrence), and out = act(x W^T + b) for x [rows,K], W [N,K];
+ * x3 != 0 selects the compensated (fp32-class) arithmetic.  Workspace of the Linear hook: the LSTM one with
+ * R*T = rows, H = max(8, ceil(N/4)). */
+size_t fsn_debug_lstm_tc_workspace_bytes(int R, int T, int K, int H, int x3);
+int fsn_debug_lstm_layer_tc(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, const float* x,
+                            int R, int T, int K, int H, int x3, float* hall, void* workspace, size_t workspace_bytes,
+                            fsn_stream_t stream);
+int fsn_debug_linear_tc(const float* x, int rows, int K, const float* W, const float* bias, int N, int act, int x3,
+                        float* out, void* workspace, size_t workspace_bytes, fsn_stream_t stream);
 
 #ifdef __cplusplus
 }

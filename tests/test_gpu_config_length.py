@@ -94,7 +94,7 @@ def test_training_step_4x3s_matches_reference(golden, dev, prec):
             assert np.abs(v.cpu().numpy().reshape(-1)[::SUB] - g["psub." + k]).max() < 2e-5, k
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 5e-5), ("f16_tc", CRM_TOL)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 5e-5), ("f16x3_tc", 5e-5), ("f16_tc", CRM_TOL)])
 def test_fast_fullsubnet_4s(golden, dev, precision, tol):
     from fullsubnet_b200.acoustics.feature import stft
     from fullsubnet_b200.fast_fullsubnet.model import Model

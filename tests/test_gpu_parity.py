@@ -237,7 +237,7 @@ def test_full_size_batch_properties(dev):
 
 
 # ------------------------------------------------------------------ fast_fullsubnet (config 4, A13)
-@pytest.mark.parametrize("precision,tol", [("fp32", 5e-5), ("f16_tc", CRM_TOL)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 5e-5), ("f16x3_tc", 5e-5), ("f16_tc", CRM_TOL)])
 def test_fast_fullsubnet_matches_reference(golden, dev, precision, tol):
     from fullsubnet_b200.fast_fullsubnet.model import Model
     from oracle import fast_fullsubnet_oracle as FO
