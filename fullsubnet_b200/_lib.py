@@ -13,13 +13,14 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libfsn_b200.so")
 
 FSN_OK, FSN_ERR_SHAPE, FSN_ERR_UNSUPPORTED, FSN_ERR_CUDA, FSN_ERR_WORKSPACE = 0, 1, 2, 3, 4
 ACT = {None: 0, False: 0, "": 0, "ReLU": 1, "Tanh": 2, "ReLU6": 3}
+CELL = {"LSTM": 0, "GRU": 1}
 PREC = {"fp32": 0, "f16_tc": 1, "tf32_tc": 2, "f16x3_tc": 3}
 
 
 class ModelDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "num_freqs", "look_ahead", "fb_num_neighbors", "sb_num_neighbors", "fb_hidden", "sb_hidden",
-        "fb_activation", "sb_activation", "norm_type", "num_groups_in_drop_band", "precision", "reserved")]
+        "fb_activation", "sb_activation", "norm_type", "num_groups_in_drop_band", "precision", "cell_type")]
 
 
 class SeqWeights(C.Structure):

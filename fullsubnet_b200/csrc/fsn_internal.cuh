@@ -29,6 +29,7 @@ enum { SEG0_DENSE = 0, SEG0_GATHER = 1 };
 
 struct StepParams {
   int R, K0, H, first;
+  int gru;  // 0: LSTM (4 gates i,f,g,o); 1: GRU (weights [3H,.] r,z,n; h_prev is read in the update; no cell state)
   const float* w_ih; const float* w_hh; const float* b_ih; const float* b_hh;
   const float* h_prev; size_t h_prev_stride;
   float* h_out; size_t h_out_stride;
@@ -114,17 +115,18 @@ int lstm_rec_tc_launch(const float* w_hh, const float* b_ih, const float* b_hh, 
                        float* hall, size_t h_row, size_t h_t, int R, int T, int H, bool x3, void* scratch,
                        cudaStream_t st);
 int split_tf32_launch(const float* in, size_t rows, int K, size_t ldi, const float* row_scale, int rows_per_scale,
-                      float* out_hi, float* out_lo, int ldo, cudaStream_t st, int scale_B = 0);
+                      float* out, int Kp, int cat, cudaStream_t st, int scale_B = 0);
 int bias_act_launch(float* x, size_t rows, int N, size_t ld, const float* bias, int act, cudaStream_t st);
-// workspace of lstm_layer_tc / linear_tc: operand splits [rows_T, Kmax], weight splits [4 Hmax, Kmax], P [rows_T, 4 Hmax]
-struct LstmTcWs { float *a_hi, *a_lo, *w_hi, *w_lo, *P; void* rec; };
+// workspace of lstm_layer_tc / linear_tc: prepared A operand [rows_T, Kmax (x3: 3 Kmax)], prepared weights
+// [4 Hmax, same], hoisted projection P [rows_T, 4 Hmax], recurrence scratch
+struct LstmTcWs { float *a, *w, *P; void* rec; };
 void lstm_tc_carve(char* base, size_t& off, size_t rows_T, int Kmax, int Hmax, bool x3, LstmTcWs& ws);
 int lstm_layer_tc(const fsn_lstm_layer& L, const float* x, size_t ldx, int K, const float* row_scale, int rows_per_scale,
                   int scale_B, int R, int T, int H, bool x3, const LstmTcWs& ws, float* hall, cudaStream_t st);
 int linear_tc(const float* x, size_t ldx, int K, const float* W, const float* bias, int N, int act, float* out, size_t ldo,
               size_t rows, bool x3, const LstmTcWs& ws, cudaStream_t st);
-int gemm_tc_split_launch(const float* A_hi, const float* A_lo, size_t lda, const float* W, int N, int K, float* w_hi,
-                         float* w_lo, float* C, size_t ldc, size_t M, bool x3, cudaStream_t st);
+int gemm_tc_split_launch(const float* a, size_t lda, const float* W, int N, int K, float* w, float* C, size_t ldc, size_t M,
+                         bool x3, cudaStream_t st);
 
 // tcgen05 sub-band stack (fsn_subband_tc.cu)
 struct SbTcArgs {

@@ -289,28 +289,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_tc_kernel(const __grid_c
   }
 }
 
-// out_hi = tf32-truncated in * scale, out_lo = in * scale - out_hi (both fp32, row stride ldo >= K, multiple of 4;
-// pad columns zero).  With out_lo == nullptr: plain scaled, padded copy.
+// Operand preparation for the tf32 GEMM.  v = in[r, k] * scale.
+//   cat == 0: out[r, :Kp] = v (zero padded to Kp): plain scaled, 16-byte aligned copy, single-pass GEMM.
+//   cat != 0: compensated GEMM as ONE pass over a 3x longer K: hi = tf32-truncated v (what the tensor core reads),
+//             lo = v - hi (exact); the A operand (cat == 1) is laid out [hi | lo | hi], the B operand (cat == 2)
+//             [hi | hi | lo], so that  A' B'^T = hi.hi + lo.hi + hi.lo  - the product to ~2^-21, one output write.
 // row_scale index of row r: r / rows_per_scale (per clip), or with scale_B > 0 the time-major entry
 // (r % rows_per_scale) * scale_B + r / rows_per_scale of a [T', B] table (cumulative norm).
 __global__ void split_tf32_kernel(const float* __restrict__ in, size_t rows, int K, size_t ldi, const float* __restrict__ row_scale,
-                                  int rows_per_scale, int scale_B, float* __restrict__ out_hi, float* __restrict__ out_lo, int ldo) {
-  const size_t n = rows * (size_t)ldo;
+                                  int rows_per_scale, int scale_B, float* __restrict__ out, int Kp, int cat) {
+  const size_t n = rows * (size_t)Kp;
+  const size_t ldo = cat ? (size_t)3 * Kp : (size_t)Kp;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = i / ldo;
-    const int k = (int)(i - r * ldo);
+    const size_t r = i / Kp;
+    const int k = (int)(i - r * Kp);
     float v = 0.f;
     if (k < K) {
       v = in[r * ldi + k];
       if (row_scale)
         v *= scale_B > 0 ? row_scale[(r % rows_per_scale) * scale_B + r / rows_per_scale] : row_scale[r / rows_per_scale];
     }
-    if (out_lo) {
+    float* o = out + r * ldo + k;
+    if (cat) {
       const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-      out_hi[i] = hi;
-      out_lo[i] = v - hi;
+      const float lo = v - hi;
+      o[0] = hi;
+      o[Kp] = (cat == 1) ? lo : hi;
+      o[2 * Kp] = (cat == 1) ? hi : lo;
     } else {
-      out_hi[i] = v;
+      o[0] = v;
     }
   }
 }
@@ -447,13 +454,13 @@ int lstm_rec_tc_launch(const float* w_hh, const float* b_ih, const float* b_hh, 
 }
 
 int split_tf32_launch(const float* in, size_t rows, int K, size_t ldi, const float* row_scale, int rows_per_scale,
-                      float* out_hi, float* out_lo, int ldo, cudaStream_t st, int scale_B) {
+                      float* out, int Kp, int cat, cudaStream_t st, int scale_B) {
   if (rows == 0) return FSN_OK;
-  const size_t n = rows * (size_t)ldo;
+  const size_t n = rows * (size_t)Kp;
   size_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   rec::split_tf32_kernel<<<(int)blocks, 256, 0, st>>>(in, rows, K, ldi, row_scale, rows_per_scale < 1 ? 1 : rows_per_scale,
-                                                      scale_B, out_hi, out_lo, ldo);
+                                                      scale_B, out, Kp, cat);
   FSN_CHECK_LAUNCH("split_tf32_kernel");
   return FSN_OK;
 }
@@ -468,57 +475,50 @@ int bias_act_launch(float* x, size_t rows, int N, size_t ld, const float* bias, 
   return FSN_OK;
 }
 
-// C[M,N] = A[M,K] W[N,K]^T on the tf32 tensor cores; x3: three passes on hi/lo splits (fp32 error class).
-// A_hi/A_lo [M, lda], W row-major [N, K] (split here into w_hi/w_lo scratch, [N, ldw], ldw = K rounded up to 4)
-int gemm_tc_split_launch(const float* A_hi, const float* A_lo, size_t lda, const float* W, int N, int K, float* w_hi,
-                         float* w_lo, float* C, size_t ldc, size_t M, bool x3, cudaStream_t st) {
-  const int ldw = (K + 3) & ~3;
+// C[M,N] = A[M,K] W[N,K]^T on the tf32 tensor cores.  `a` is the prepared A operand (prep_operand: [M, Keff], lda);
+// W row-major [N, K] is prepared here into `w` ([N, Keff]); x3: Keff = 3 * Kp (see split_tf32_kernel).
+int gemm_tc_split_launch(const float* a, size_t lda, const float* W, int N, int K, float* w, float* C, size_t ldc, size_t M,
+                         bool x3, cudaStream_t st) {
+  const int Kp = (K + 3) & ~3;
+  const int Keff = x3 ? 3 * Kp : K;
   int rc;
-  if ((rc = split_tf32_launch(W, (size_t)N, K, (size_t)K, nullptr, 1, w_hi, x3 ? w_lo : nullptr, ldw, st))) return rc;
+  if ((rc = split_tf32_launch(W, (size_t)N, K, (size_t)K, nullptr, 1, w, Kp, x3 ? 2 : 0, st, 0))) return rc;
   FSN_REQUIRE(M < ((size_t)1 << 31), FSN_ERR_SHAPE, "gemm_tc: too many rows");
-  if ((rc = tgemm_launch(A_hi, lda, w_hi, ldw, C, ldc, (int)M, N, K, false, nullptr, 0, st))) return rc;
-  if (x3) {
-    if ((rc = tgemm_launch(A_lo, lda, w_hi, ldw, C, ldc, (int)M, N, K, true, nullptr, 0, st))) return rc;
-    if ((rc = tgemm_launch(A_hi, lda, w_lo, ldw, C, ldc, (int)M, N, K, true, nullptr, 0, st))) return rc;
-  }
-  return FSN_OK;
+  return tgemm_launch(a, lda, w, x3 ? (size_t)3 * Kp : (size_t)Kp, C, ldc, (int)M, N, Keff, false, nullptr, 0, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // One full LSTM layer and one Linear layer on top of the pieces above (what the model files call).
 void lstm_tc_carve(char* base, size_t& off, size_t rows_T, int Kmax, int Hmax, bool x3, LstmTcWs& ws) {
   auto take = [&](size_t bytes) { char* r = base ? base + off : nullptr; off = align_up(off + bytes, 256); return r; };
-  const size_t wa = (size_t)((Kmax + 3) & ~3);
-  ws.a_hi = (float*)take(rows_T * wa * sizeof(float));
-  ws.a_lo = x3 ? (float*)take(rows_T * wa * sizeof(float)) : nullptr;
-  ws.w_hi = (float*)take((size_t)4 * Hmax * wa * sizeof(float));
-  ws.w_lo = x3 ? (float*)take((size_t)4 * Hmax * wa * sizeof(float)) : nullptr;
+  const size_t wa = (size_t)((Kmax + 3) & ~3) * (x3 ? 3 : 1);
+  ws.a = (float*)take(rows_T * wa * sizeof(float));
+  ws.w = (float*)take((size_t)4 * Hmax * wa * sizeof(float));
   ws.P = (float*)take(rows_T * 4 * Hmax * sizeof(float));
   ws.rec = take(lstm_rec_tc_scratch_bytes(Hmax, x3));
 }
 
-// operand A of a GEMM: x [rows, K] (row stride ldx) -> 16-byte aligned rows, scaled, split when x3
+// operand A of a GEMM: x [rows, K] (row stride ldx) -> 16-byte aligned rows, scaled; x3: the [hi | lo | hi] layout
 static int prep_operand(const float* x, size_t ldx, int K, size_t rows, const float* row_scale, int rows_per_scale, int scale_B,
-                        bool x3, const LstmTcWs& ws, const float*& a_hi, const float*& a_lo, size_t& lda, cudaStream_t st) {
+                        bool x3, const LstmTcWs& ws, const float*& a, size_t& lda, cudaStream_t st) {
   if (!x3 && !row_scale && (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-    a_hi = x; a_lo = nullptr; lda = ldx;
+    a = x; lda = ldx;
     return FSN_OK;
   }
   const int Kp = (K + 3) & ~3;
-  a_hi = ws.a_hi; a_lo = x3 ? ws.a_lo : nullptr; lda = (size_t)Kp;
-  return split_tf32_launch(x, rows, K, ldx, row_scale, rows_per_scale, ws.a_hi, x3 ? ws.a_lo : nullptr, Kp, st, scale_B);
+  a = ws.a; lda = (size_t)Kp * (x3 ? 3 : 1);
+  return split_tf32_launch(x, rows, K, ldx, row_scale, rows_per_scale, ws.a, Kp, x3 ? 1 : 0, st, scale_B);
 }
 
 // hall[r, t, :] (row stride T*H) of one LSTM layer over x[(r*T + t), :K] * scale
 int lstm_layer_tc(const fsn_lstm_layer& L, const float* x, size_t ldx, int K, const float* row_scale, int rows_per_scale,
                   int scale_B, int R, int T, int H, bool x3, const LstmTcWs& ws, float* hall, cudaStream_t st) {
   const size_t rows = (size_t)R * T;
-  const float *a_hi, *a_lo;
+  const float* a;
   size_t lda;
   int rc;
-  if ((rc = prep_operand(x, ldx, K, rows, row_scale, rows_per_scale, scale_B, x3, ws, a_hi, a_lo, lda, st))) return rc;
-  if ((rc = gemm_tc_split_launch(a_hi, a_lo, lda, L.w_ih, 4 * H, K, ws.w_hi, ws.w_lo, ws.P, (size_t)4 * H, rows, x3, st)))
-    return rc;
+  if ((rc = prep_operand(x, ldx, K, rows, row_scale, rows_per_scale, scale_B, x3, ws, a, lda, st))) return rc;
+  if ((rc = gemm_tc_split_launch(a, lda, L.w_ih, 4 * H, K, ws.w, ws.P, (size_t)4 * H, rows, x3, st))) return rc;
   return lstm_rec_tc_launch(L.w_hh, L.b_ih, L.b_hh, ws.P, (size_t)T * 4 * H, (size_t)4 * H, hall, (size_t)T * H, (size_t)H, R, T,
                             H, x3, ws.rec, st);
 }
@@ -526,11 +526,11 @@ int lstm_layer_tc(const fsn_lstm_layer& L, const float* x, size_t ldx, int K, co
 // out[rows, :N] (row stride ldo) = act(x[rows, :K] W[N,K]^T + bias)
 int linear_tc(const float* x, size_t ldx, int K, const float* W, const float* bias, int N, int act, float* out, size_t ldo,
               size_t rows, bool x3, const LstmTcWs& ws, cudaStream_t st) {
-  const float *a_hi, *a_lo;
+  const float* a;
   size_t lda;
   int rc;
-  if ((rc = prep_operand(x, ldx, K, rows, nullptr, 1, 0, x3, ws, a_hi, a_lo, lda, st))) return rc;
-  if ((rc = gemm_tc_split_launch(a_hi, a_lo, lda, W, N, K, ws.w_hi, ws.w_lo, out, ldo, rows, x3, st))) return rc;
+  if ((rc = prep_operand(x, ldx, K, rows, nullptr, 1, 0, x3, ws, a, lda, st))) return rc;
+  if ((rc = gemm_tc_split_launch(a, lda, W, N, K, ws.w, out, ldo, rows, x3, st))) return rc;
   if (!bias && act == FSN_ACT_NONE) return FSN_OK;
   return bias_act_launch(out, rows, N, ldo, bias, act, st);
 }

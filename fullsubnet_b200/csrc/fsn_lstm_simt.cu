@@ -77,6 +77,9 @@ __global__ void norm_scales_kernel(const float2* __restrict__ mag_sums, const fl
 // ------------------------------------------------------------------------------------------
 // One LSTM time step for R rows:  gates = [x_t | h_{t-1}] [W_ih | W_hh]^T + b_ih + b_hh, cell
 // update fused.  CTA tile: 64 rows x 32 hidden units (x4 gates), K chunks of 16.
+// GRU variant (p.gru; nn.GRU of audio_zen/model/module/sequence_model.py:59-66): the four accumulator slots hold
+// r = W_ir x + W_hr h, z = W_iz x + W_hz h, n_x = W_in x and n_h = W_hn h (kept apart because n = tanh(n_x + b_in +
+// r * (n_h + b_hn))); h' = (1 - z) n + z h.
 constexpr int BM = 64, BU = 32, BK = 16;
 
 template <int MODE>
@@ -112,8 +115,11 @@ __global__ void __launch_bounds__(256) lstm_step_kernel(const StepParams p) {
   // W-tile loader: thread -> (gate column = tid/2, 8 consecutive k)
   const int w_col = tid >> 1, w_k = (tid & 1) * 8;
   const int w_unit = u0 + (w_col & (BU - 1));
-  const int w_row = (w_col / BU) * p.H + w_unit;  // row of the [4H,K] PyTorch weight
+  const int w_slot = w_col / BU;                                    // accumulator slot 0..3
+  const int w_gate = p.gru ? (w_slot < 2 ? w_slot : 2) : w_slot;    // gate block of the PyTorch weight
+  const int w_row = w_gate * p.H + w_unit;  // row of the [4H,K] (GRU: [3H,K]) PyTorch weight
   const bool w_ok = w_unit < p.H;
+  const bool w_x_ok = !(p.gru && w_slot == 3), w_h_ok = !(p.gru && w_slot == 2);  // GRU: n_x has no h part, n_h no x part
 
   float acc[4][4][2];
 #pragma unroll
@@ -136,7 +142,9 @@ __global__ void __launch_bounds__(256) lstm_step_kernel(const StepParams p) {
     for (int j = 0; j < 8; ++j) {
       const int k = k0 + w_k + j;
       float v = 0.f;
-      if (w_ok && k < Ktot) v = (k < p.K0) ? p.w_ih[(size_t)w_row * p.K0 + k] : p.w_hh[(size_t)w_row * p.H + (k - p.K0)];
+      if (w_ok && k < Ktot)
+        v = (k < p.K0) ? (w_x_ok ? p.w_ih[(size_t)w_row * p.K0 + k] : 0.f)
+                       : (w_h_ok ? p.w_hh[(size_t)w_row * p.H + (k - p.K0)] : 0.f);
       Ws[w_k + j][w_col] = v;
     }
     __syncthreads();
@@ -162,6 +170,20 @@ __global__ void __launch_bounds__(256) lstm_step_kernel(const StepParams p) {
   for (int q = 0; q < 2; ++q) {
     const int u = u0 + tx + 16 * q;
     if (u >= p.H) continue;
+    if (p.gru) {
+      const float b_r = p.b_ih[u] + p.b_hh[u], b_z = p.b_ih[p.H + u] + p.b_hh[p.H + u];
+      const float b_in = p.b_ih[2 * p.H + u], b_hn = p.b_hh[2 * p.H + u];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = row0 + ty * 4 + i;
+        if (row >= p.R) continue;
+        const float r = sigmoidf_(acc[i][0][q] + b_r), z = sigmoidf_(acc[i][1][q] + b_z);
+        const float n = tanhf(acc[i][2][q] + b_in + r * (acc[i][3][q] + b_hn));
+        const float hp = p.first ? 0.f : p.h_prev[(size_t)row * p.h_prev_stride + u];
+        p.h_out[(size_t)row * p.h_out_stride + u] = (1.0f - z) * n + z * hp;
+      }
+      continue;
+    }
     float bias[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) bias[g] = p.b_ih[g * p.H + u] + p.b_hh[g * p.H + u];

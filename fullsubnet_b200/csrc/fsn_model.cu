@@ -64,6 +64,7 @@ static bool fb_tc_enabled(const fsn_model_desc* d, int B) {
   // every batch size takes the same path, so a clip's result does not depend on the batch it is enhanced in
   static const int min_b = getenv("FSN_FB_TC_MIN_B") ? atoi(getenv("FSN_FB_TC_MIN_B")) : 1;
   if (d->precision != FSN_PREC_F16_TC && d->precision != FSN_PREC_F16X3_TC) return false;
+  if (d->cell_type != FSN_CELL_LSTM) return false;
   if (B < min_b) return false;
   return lstm_rec_tc_supported(d->fb_hidden, d->precision == FSN_PREC_F16X3_TC);
 }
@@ -76,6 +77,8 @@ int make_dims(const fsn_model_desc* d, int B, int T, Dims& m) {
               FSN_ERR_UNSUPPORTED, "You must set up a type of Norm. (offline_laplace_norm / cumulative_laplace_norm are built)");
   FSN_REQUIRE(d->norm_type == FSN_NORM_OFFLINE_LAPLACE || d->precision != FSN_PREC_TF32_TC, FSN_ERR_UNSUPPORTED,
               "cumulative_laplace_norm is built for inference (the training step keeps the offline norm)");
+  FSN_REQUIRE(d->cell_type == FSN_CELL_LSTM || (d->cell_type == FSN_CELL_GRU && d->precision == FSN_PREC_FP32),
+              FSN_ERR_UNSUPPORTED, "model: sequence_model must be LSTM, or GRU on the fp32 kernels (precision fp32)");
   FSN_REQUIRE(d->sb_num_neighbors >= 0 && d->fb_num_neighbors >= 0 && d->sb_num_neighbors < d->num_freqs &&
                   d->fb_num_neighbors < d->num_freqs,
               FSN_ERR_SHAPE, "model: reflect padding needs num_neighbors < num_freqs");
@@ -168,7 +171,7 @@ static int model_core(const fsn_model_desc* d, const fsn_seq_weights* fb, const 
   const bool fb_tc = !fb_stepwise && fb_tc_enabled(d, B);
   if (fb_tc) {
     if ((rc = fb_tc_forward(d, fb, m, w, st))) return rc;
-  } else if (!fb_stepwise && !cum && fb_persistent_supported(F, Hf, Hf)) {
+  } else if (!fb_stepwise && !cum && d->cell_type == FSN_CELL_LSTM && fb_persistent_supported(F, Hf, Hf)) {
     // one persistent cooperative kernel per chunk of <= 256 clips: weights resident in shared memory,
     // layer wavefront, one grid barrier per time step
     for (int b0 = 0; b0 < B; b0 += 256) {
@@ -181,7 +184,7 @@ static int model_core(const fsn_model_desc* d, const fsn_seq_weights* fb, const 
   for (int t = 0; t < Tp; ++t) {
     StepParams p;
     memset(&p, 0, sizeof(p));
-    p.R = B; p.H = Hf; p.first = (t == 0);
+    p.R = B; p.H = Hf; p.first = (t == 0); p.gru = d->cell_type == FSN_CELL_GRU;
     // layer 0: x_t = magT[b,t,:] * inv1[b]
     p.K0 = F;
     p.w_ih = fb->w_ih[0]; p.w_hh = fb->w_hh[0]; p.b_ih = fb->b_ih[0]; p.b_hh = fb->b_hh[0];
@@ -231,7 +234,7 @@ static int model_core(const fsn_model_desc* d, const fsn_seq_weights* fb, const 
   for (int t = 0; t < Tp; ++t) {
     StepParams p;
     memset(&p, 0, sizeof(p));
-    p.R = m.R; p.H = Hs; p.first = (t == 0);
+    p.R = m.R; p.H = Hs; p.first = (t == 0); p.gru = d->cell_type == FSN_CELL_GRU;
     p.K0 = m.Ksb;
     p.w_ih = sb->w_ih[0]; p.w_hh = sb->w_hh[0]; p.b_ih = sb->b_ih[0]; p.b_hh = sb->b_hh[0];
     p.h_prev = w.sb_h0[(t + 1) & 1]; p.h_prev_stride = Hs;

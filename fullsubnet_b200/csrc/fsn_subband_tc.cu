@@ -677,6 +677,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sb_lstm_tc_kernel(const KArgs a) 
 }  // namespace tc
 
 bool sb_tc_supported(const fsn_model_desc* d) {
+  if (d->cell_type != FSN_CELL_LSTM) return false;  // GRU: fp32 kernels only
   const int Ksb = (2 * d->sb_num_neighbors + 1) + (2 * d->fb_num_neighbors + 1);
   if (d->precision == FSN_PREC_F16X3_TC) return sb_tc2_supported(d);  // compensated variant: pair kernel only
   return d->sb_hidden % 128 == 0 && d->sb_hidden / 128 <= tc::MAX_MT && d->sb_hidden >= 128 && Ksb <= tc::KS;

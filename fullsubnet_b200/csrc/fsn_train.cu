@@ -471,6 +471,7 @@ static int train_check(const fsn_model_desc* d) {
               "training: only offline_laplace_norm is built");
   FSN_REQUIRE(d->fb_num_neighbors == 0, FSN_ERR_UNSUPPORTED,
               "training: fb_num_neighbors > 0 is not built (every shipped recipe uses 0)");
+  FSN_REQUIRE(d->cell_type == FSN_CELL_LSTM, FSN_ERR_UNSUPPORTED, "training: the GRU cell is built for inference only");
   return FSN_OK;
 }
 

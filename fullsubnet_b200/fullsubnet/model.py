@@ -88,6 +88,7 @@ class Model(BaseModel):
             input_size=(sb_num_neighbors * 2 + 1) + (fb_num_neighbors * 2 + 1), output_size=2,
             hidden_size=sb_model_hidden_size, num_layers=2, bidirectional=False, sequence_model=sequence_model,
             output_activate_function=sb_output_activate_function)
+        self.sequence_model_type = sequence_model  # "LSTM" (every shipped recipe) | "GRU" (fp32 inference kernels)
         self.num_freqs = num_freqs
         self.sb_num_neighbors = sb_num_neighbors
         self.fb_num_neighbors = fb_num_neighbors
@@ -116,6 +117,8 @@ class Model(BaseModel):
             if self.precision not in ("fp32", "f16_tc", "f16x3_tc"):
                 raise ValueError("precision must be 'fp32', 'f16x3_tc', 'f16_tc' or 'auto'")
             return self.precision
+        if self.sequence_model_type != "LSTM":
+            return "fp32"
         d = self._desc("f16x3_tc", 1)
         return "f16x3_tc" if _lib.load().fsn_sb_packed_bytes(C.byref(d)) > 0 else "fp32"
 
@@ -133,7 +136,7 @@ class Model(BaseModel):
             sb_num_neighbors=self.sb_num_neighbors, fb_hidden=self.fb_model.hidden_size,
             sb_hidden=self.sb_model.hidden_size, fb_activation=_lib.ACT[self.fb_model.output_activate_function],
             sb_activation=_lib.ACT[self.sb_model.output_activate_function], norm_type=self.norm,
-            num_groups_in_drop_band=num_groups, precision=_lib.PREC[precision], reserved=0)
+            num_groups_in_drop_band=num_groups, precision=_lib.PREC[precision], cell_type=_lib.CELL[self.sequence_model_type])
 
     def _packed_sb(self, desc, sb_w, device):
         """Tile-ordered fp16 image of the sub-band weights, rebuilt when any parameter changes."""

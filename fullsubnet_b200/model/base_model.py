@@ -27,7 +27,7 @@ class BaseModel(nn.Module):
         if isinstance(m, nn.Linear):
             init.xavier_normal_(m.weight.data)
             init.normal_(m.bias.data)
-        elif isinstance(m, nn.LSTM):
+        elif isinstance(m, (nn.LSTM, nn.GRU)):
             for param in m.parameters():
                 if len(param.shape) >= 2:
                     init.orthogonal_(param.data)

@@ -21,11 +21,14 @@ class SequenceModel(nn.Module):
         if sequence_model == "LSTM":
             self.sequence_model = nn.LSTM(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers,
                                           batch_first=True, bidirectional=bidirectional)
+        elif sequence_model == "GRU":  # sequence_model.py:59-66 (weights [3H,K], gate order r,z,n)
+            self.sequence_model = nn.GRU(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers,
+                                         batch_first=True, bidirectional=bidirectional)
         else:
-            # sequence_model.py:59-79: GRU exists upstream; this build covers the LSTM configs only
-            raise NotImplementedError(f"Not implemented {sequence_model}")
+            raise NotImplementedError(f"Not implemented {sequence_model}")  # sequence_model.py:67-68
+        self.cell = sequence_model
         if bidirectional or not 1 <= num_layers <= 8:
-            raise NotImplementedError("libfsn_b200 builds uni-directional LSTM stacks of 1..8 layers")
+            raise NotImplementedError("libfsn_b200 builds uni-directional LSTM / GRU stacks of 1..8 layers")
         if int(output_size):  # sequence_model.py:82-84 (no Linear layer when output_size == 0)
             self.fc_output_layer = nn.Linear(hidden_size, output_size)
         self.num_layers = num_layers

@@ -45,6 +45,7 @@ enum { FSN_ACT_NONE = 0, FSN_ACT_RELU = 1, FSN_ACT_TANH = 2, FSN_ACT_RELU6 = 3 }
 /* FSN_NORM_CUMULATIVE_LAPLACE (audio_zen/model/base_model.py:220-251): causal running mean per clip (first norm) and
  * per sub-band unit (second norm); built for the fp32 inference path of fsn_model_forward / fsn_enhance */
 enum { FSN_NORM_OFFLINE_LAPLACE = 0, FSN_NORM_CUMULATIVE_LAPLACE = 1 };
+enum { FSN_CELL_LSTM = 0, FSN_CELL_GRU = 1 };
 /* arithmetic of the sub-band LSTM stack (99 % of the FLOPs):
  *   FSN_PREC_FP32     - fp32 FMA everywhere (bit-for-bit class of the reference CPU path, ~1e-6)
  *   FSN_PREC_TF32_TC  - training step only (fsn_train_*): every GEMM of the forward, of back-propagation through
@@ -117,7 +118,8 @@ typedef struct fsn_model_desc {
   int32_t norm_type;        /* FSN_NORM_* */
   int32_t num_groups_in_drop_band; /* applied when B > 1 (model.py:114), 1 = off */
   int32_t precision;        /* FSN_PREC_* for the sub-band stack */
-  int32_t reserved;
+  int32_t cell_type;        /* FSN_CELL_*: `sequence_model` = "LSTM" | "GRU" (sequence_model.py:52-66); GRU: weights
+                             * [3H,K] with gate order r,z,n, inference on the fp32 kernels (FSN_PREC_FP32) only */
 } fsn_model_desc;
 
 /* One SequenceModel (audio_zen/model/module/sequence_model.py:26-125): 2-layer nn.LSTM +

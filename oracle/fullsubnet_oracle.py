@@ -245,11 +245,43 @@ def lstm_stack(x: torch.Tensor, sd: Dict[str, torch.Tensor], prefix: str, num_la
     return inp
 
 
+def gru_stack(x: torch.Tensor, sd: Dict[str, torch.Tensor], prefix: str, num_layers: int = 2) -> torch.Tensor:
+    """nn.GRU(batch_first=True) restated (audio_zen/model/module/sequence_model.py:59-66,117): weights [3H,K] with gate
+    order (r,z,n); r = s(W_ir x + b_ir + W_hr h + b_hr), z likewise, n = tanh(W_in x + b_in + r * (W_hn h + b_hn)),
+    h' = (1 - z) n + z h; zero initial state.  x: [B,T,In] -> [B,T,H]."""
+    B, T, _ = x.shape
+    inp = x
+    for layer in range(num_layers):
+        w_ih = sd[f"{prefix}weight_ih_l{layer}"].t().contiguous()
+        w_hh = sd[f"{prefix}weight_hh_l{layer}"].t().contiguous()
+        b_ih, b_hh = sd[f"{prefix}bias_ih_l{layer}"], sd[f"{prefix}bias_hh_l{layer}"]
+        H = w_hh.shape[0]
+        h = torch.zeros(B, H)
+        outs = []
+        xproj = torch.addmm(b_ih, inp.reshape(B * T, -1), w_ih).reshape(B, T, 3 * H)
+        for t in range(T):
+            hp = torch.addmm(b_hh, h, w_hh)
+            xr, xz, xn = xproj[:, t].split(H, dim=1)
+            hr, hz, hn = hp.split(H, dim=1)
+            r = torch.sigmoid(xr + hr)
+            z = torch.sigmoid(xz + hz)
+            n = torch.tanh(xn + r * hn)
+            h = (1.0 - z) * n + z * h
+            outs.append(h)
+        inp = torch.stack(outs, dim=1)
+    return inp
+
+
 def sequence_model(x: torch.Tensor, sd: Dict[str, torch.Tensor], prefix: str,
                    activation: Optional[str], operand_round=None) -> torch.Tensor:
-    """audio_zen/model/module/sequence_model.py:106-125.  x: [B,F,T] -> [B,F_out,T]."""
+    """audio_zen/model/module/sequence_model.py:106-125.  x: [B,F,T] -> [B,F_out,T].  The cell (LSTM / GRU) is read off
+    the weight shapes: [4H,K] vs [3H,K]."""
     assert x.dim() == 3, f"The shape of input is {x.shape}."
-    o = lstm_stack(x.permute(0, 2, 1), sd, prefix + "sequence_model.", operand_round=operand_round)
+    pre = prefix + "sequence_model."
+    if sd[pre + "weight_hh_l0"].shape[0] == 3 * sd[pre + "weight_hh_l0"].shape[1]:
+        o = gru_stack(x.permute(0, 2, 1), sd, pre)
+    else:
+        o = lstm_stack(x.permute(0, 2, 1), sd, pre, operand_round=operand_round)
     o = o @ sd[prefix + "fc_output_layer.weight"].t() + sd[prefix + "fc_output_layer.bias"]
     if activation:
         if activation == "ReLU":
@@ -360,13 +392,14 @@ def state_dict_shapes(args: Optional[dict] = None) -> Sequence[Tuple[str, Tuple[
     F, Hf, Hs = a["num_freqs"], a["fb_model_hidden_size"], a["sb_model_hidden_size"]
     sb_in = (2 * a["sb_num_neighbors"] + 1) + (2 * a["fb_num_neighbors"] + 1)
     out = []
+    ng = 3 if a.get("sequence_model", "LSTM") == "GRU" else 4  # nn.GRU: [3H,K] (r,z,n); nn.LSTM: [4H,K] (i,f,g,o)
     for pre, In, H, Out in (("fb_model.", F, Hf, F), ("sb_model.", sb_in, Hs, 2)):
         for l in range(2):
             k = In if l == 0 else H
-            out += [(f"{pre}sequence_model.weight_ih_l{l}", (4 * H, k)),
-                    (f"{pre}sequence_model.weight_hh_l{l}", (4 * H, H)),
-                    (f"{pre}sequence_model.bias_ih_l{l}", (4 * H,)),
-                    (f"{pre}sequence_model.bias_hh_l{l}", (4 * H,))]
+            out += [(f"{pre}sequence_model.weight_ih_l{l}", (ng * H, k)),
+                    (f"{pre}sequence_model.weight_hh_l{l}", (ng * H, H)),
+                    (f"{pre}sequence_model.bias_ih_l{l}", (ng * H,)),
+                    (f"{pre}sequence_model.bias_hh_l{l}", (ng * H,))]
         out += [(f"{pre}fc_output_layer.weight", (Out, H)), (f"{pre}fc_output_layer.bias", (Out,))]
     return out
 
@@ -381,7 +414,7 @@ def make_state_dict(seed: int = 0, args: Optional[dict] = None, sb_fc_gain: floa
     for name, shape in state_dict_shapes(args):
         fan = shape[-1] if "fc_output_layer.weight" in name else None
         if "sequence_model" in name:
-            H = shape[0] // 4
+            H = shape[0] // (3 if (args or {}).get("sequence_model", "LSTM") == "GRU" else 4)
             k = 1.0 / math.sqrt(H)
         else:
             H = fan if fan is not None else sd[name.replace("bias", "weight")].shape[1]

@@ -396,3 +396,28 @@ def test_peak_normalize_int16_matches_numpy(dev, tmp_path):
     import wave
     with wave.open(str(tmp_path / "a.wav")) as f:
         assert f.getframerate() == 16000 and f.getnframes() == 6000 and f.getsampwidth() == 2
+
+
+# ------------------------------------------------------------------ GRU cell
+def test_gru_model_matches_reference(golden, dev):
+    """sequence_model="GRU" (audio_zen/model/module/sequence_model.py:59-66): fp32 kernels, 3-gate weights, both the
+    Model.forward contract (B=1, B=3 with drop_band) and the fused wav -> wav call; training is reported as not built."""
+    from oracle import fullsubnet_oracle as O
+    g = golden("model_gru")
+    args = dict(small_args(), sequence_model="GRU")
+    m = make_model(args, O.make_state_dict(seed=7, args=args), dev, "auto")
+    assert m._resolve_precision() == "fp32"
+    assert m.fb_model.sequence_model.weight_ih_l0.shape == (3 * 32, 33)
+    mag = T(g["small_mag"], dev).unsqueeze(1)
+    with torch.no_grad():
+        assert rel_max(m(mag[:1]).cpu(), g["small_b1"]) < 2e-5
+        assert rel_max(m(mag).cpu(), g["small_g2"]) < 2e-5
+    full = dict(O.DEFAULT_MODEL_ARGS, sequence_model="GRU")
+    mf = make_model(full, O.make_state_dict(seed=0, args=full, sb_fc_gain=60.0), dev, "auto")
+    wav, crm = mf.enhance(T(g["full_y"], dev), return_crm=True)
+    assert rel_max(crm.cpu(), g["full_crm"]) < 5e-5
+    assert np.abs(wav.cpu().numpy() - g["full_wav"]).max() < WAV_TOL
+    with pytest.raises(NotImplementedError), torch.no_grad():
+        make_model(full, O.make_state_dict(seed=0, args=full), dev, "f16_tc")(torch.rand(1, 1, 257, 4, device=dev))
+    with pytest.raises(NotImplementedError):
+        m.train()(mag)  # BPTT is built for the LSTM recipe

@@ -268,3 +268,18 @@ def test_oracle_at_config_length_4s(golden):
             wav, crm = O.enhance(y, O.make_state_dict(seed=0, sb_fc_gain=gain), return_crm=True)
         assert rel_max(crm, g[f"{tag}_crm"]) < 5e-5 and rel_l2(crm, g[f"{tag}_crm"]) < 5e-5
         assert np.abs(wav.numpy() - g[f"{tag}_wav"]).max() < 1e-4
+
+
+def test_gru_oracle_matches_reference(golden):
+    """sequence_model="GRU" (sequence_model.py:59-66): oracle gru_stack vs the unmodified reference."""
+    g = golden("model_gru")
+    a = dict(_small_args(), sequence_model="GRU")
+    sd = O.make_state_dict(seed=7, args=a)
+    assert sd["fb_model.sequence_model.weight_ih_l0"].shape == (3 * 32, 33)
+    mag = T(g["small_mag"]).unsqueeze(1)
+    assert rel_max(O.model_forward(mag[:1], sd, a), g["small_b1"]) < 1e-5
+    assert rel_max(O.model_forward(mag, sd, a), g["small_g2"]) < 1e-5
+    full = dict(O.DEFAULT_MODEL_ARGS, sequence_model="GRU")
+    wav, crm = O.enhance(T(g["full_y"]), O.make_state_dict(seed=0, args=full, sb_fc_gain=60.0), full, return_crm=True)
+    assert rel_max(crm, g["full_crm"]) < 2e-5
+    assert np.abs(wav.numpy() - g["full_wav"]).max() < 1e-5
