@@ -73,6 +73,7 @@ def main(args):
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist_mod.init_process_group("nccl", device_id=dev)
         dist = dist_mod
     line = measure(args, dist, dev, rank, world, local, cpu_leg=not args.no_cpu_baseline)

@@ -130,7 +130,7 @@ stft_kernel(const float* __restrict__ wav, int L, int n, int hop, int win_length
 __global__ void __launch_bounds__(kDspThreads)
 istft_kernel(const float* __restrict__ real, const float* __restrict__ imag, int cstride,
              const float* __restrict__ crm, int mask_mode, int T, int n, int hop, int win_length, int out_len,
-             int seg, int np_max, float* __restrict__ wav) {
+             int seg, int np_max, float* __restrict__ wav, unsigned int* __restrict__ peak_bits) {
   extern __shared__ float2 smem2[];
   const int log2n = ilog2(n);
   const int zstride = n + 1;
@@ -190,6 +190,7 @@ istft_kernel(const float* __restrict__ real, const float* __restrict__ imag, int
   const int full = n + hop * (T - 1);
   const float inv_n = 1.0f / (float)n;
   float* out = wav + (size_t)b * out_len;
+  float peak = 0.f;
   for (int s = s_begin + threadIdx.x; s < s_end; s += blockDim.x) {
     float acc = 0.f, env = 0.f;
     if (s < full) {
@@ -204,7 +205,25 @@ istft_kernel(const float* __restrict__ real, const float* __restrict__ imag, int
         env += w * w;
       }
     }
-    out[s - n / 2] = (env > 1e-11f) ? acc / env : 0.f;
+    const float y = (env > 1e-11f) ? acc / env : 0.f;
+    out[s - n / 2] = y;
+    peak = fmaxf(peak, fabsf(y));
+  }
+  if (peak_bits) {
+    // max|y| of the clip for the int16 scaling of the host loop (base_inferencer.py:181-182): non-negative floats
+    // order like their bit patterns, and max is order-independent, so the atomic is deterministic
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) peak = fmaxf(peak, __shfl_xor_sync(0xffffffffu, peak, o));
+    if ((threadIdx.x & 31) == 0 && peak > 0.f) atomicMax(peak_bits + b, __float_as_uint(peak));
+  }
+}
+
+// out = int16(gain * wav / peak) per clip, peak from the iSTFT epilogue (float32 mul, div, truncation like numpy)
+__global__ void scale_int16_kernel(const float* __restrict__ wav, const unsigned int* __restrict__ peak_bits, int L, float gain,
+                                   int16_t* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float m = __uint_as_float(peak_bits[i / L]);
+    out[i] = (m > 0.f) ? (int16_t)__fdiv_rn(__fmul_rn(gain, wav[i]), m) : (int16_t)0;
   }
 }
 
@@ -359,8 +378,13 @@ int stft_launch(const float* wav, int B, int L, int n_fft, int hop, int win_leng
 }
 
 int istft_launch(const float* real, const float* imag, int cstride, const float* crm, int B, int T, int n_fft,
-                 int hop, int win_length, int length, float* wav, cudaStream_t st, int mask_mode) {
+                 int hop, int win_length, int length, float* wav, cudaStream_t st, int mask_mode, unsigned int* peak_bits) {
   FSN_REQUIRE(B > 0 && T > 0, FSN_ERR_SHAPE, "istft: empty input");
+  if (peak_bits) {
+    FSN_REQUIRE(!dft_size_ok(n_fft), FSN_ERR_UNSUPPORTED, "istft: the fused peak is built for the power-of-two transform");
+    int rc = check_cuda(cudaMemsetAsync(peak_bits, 0, (size_t)B * sizeof(unsigned int), st), "istft peak memset");
+    if (rc) return rc;
+  }
   if (dft_size_ok(n_fft)) {
     FSN_REQUIRE(hop > 0 && hop <= n_fft && win_length > 0 && win_length <= n_fft, FSN_ERR_SHAPE,
                 "istft: bad hop/win_length");
@@ -386,7 +410,7 @@ int istft_launch(const float* real, const float* imag, int cstride, const float*
   }
   dim3 grid(cdiv(out_len, seg), B);
   istft_kernel<<<grid, kDspThreads, smem, st>>>(real, imag, cstride, crm, mask_mode, T, n_fft, hop, win_length, out_len,
-                                                seg, np_max, wav);
+                                                seg, np_max, wav, peak_bits);
   FSN_CHECK_LAUNCH("istft_kernel");
   return FSN_OK;
 }
@@ -402,7 +426,7 @@ extern "C" int fsn_stft(const float* wav, int B, int L, int n_fft, int hop, int 
 
 extern "C" int fsn_istft(const float* real, const float* imag, int cstride, const float* crm, int B, int T,
                          int n_fft, int hop, int win_length, int length, float* wav, fsn_stream_t stream) {
-  return istft_launch(real, imag, cstride, crm, B, T, n_fft, hop, win_length, length, wav, (cudaStream_t)stream, 1);
+  return istft_launch(real, imag, cstride, crm, B, T, n_fft, hop, win_length, length, wav, (cudaStream_t)stream, 1, nullptr);
 }
 
 extern "C" int fsn_peak_normalize_int16(const float* wav, int B, int L, float gain, int16_t* out, fsn_stream_t stream) {
@@ -418,6 +442,16 @@ extern "C" int fsn_si_sdr(const float* reference, const float* estimation, int B
   FSN_CHECK_LAUNCH("si_sdr_kernel");
   return FSN_OK;
 }
+
+// int16 scaling with the per-clip peak the iSTFT epilogue produced (fsn_enhance_pcm)
+namespace fsn {
+int scale_int16_launch(const float* wav, const unsigned int* peak_bits, int B, int L, float gain, int16_t* out, cudaStream_t st) {
+  const size_t n = (size_t)B * L;
+  scale_int16_kernel<<<ew_grid((int64_t)n), 256, 0, st>>>(wav, peak_bits, L, gain, out, n);
+  FSN_CHECK_LAUNCH("scale_int16_kernel");
+  return FSN_OK;
+}
+}  // namespace fsn
 
 extern "C" int fsn_decompress_cirm(const float* in, float* out, int64_t n, float K, float limit,
                                    fsn_stream_t stream) {

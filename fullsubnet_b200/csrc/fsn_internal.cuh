@@ -98,7 +98,11 @@ int stft_launch(const float* wav, int B, int L, int n_fft, int hop, int win_leng
                 float* real, float* imag, float* magT, int T_pad, cudaStream_t st);
 // mask_mode: 1 = decompress_cIRM + complex product (fullsubnet), 2 = element-wise re*crm0, im*crm1 (improved_fullsubnet)
 int istft_launch(const float* real, const float* imag, int cstride, const float* crm, int B, int T, int n_fft,
-                 int hop, int win_length, int length, float* wav, cudaStream_t st, int mask_mode = 1);
+                 int hop, int win_length, int length, float* wav, cudaStream_t st, int mask_mode = 1,
+                 unsigned int* peak_bits = nullptr);
+// peak_bits (optional, [B]): max|wav| per clip as float bits, reduced in the iSTFT epilogue; scale_int16_launch turns
+// it into the int16 scaling of the reference host loop (audio_zen/inferencer/base_inferencer.py:181-182)
+int scale_int16_launch(const float* wav, const unsigned int* peak_bits, int B, int L, float gain, int16_t* out, cudaStream_t st);
 
 // persistent cooperative full-band LSTM (fsn_fullband.cu)
 bool fb_persistent_supported(int F, int H0, int H1);

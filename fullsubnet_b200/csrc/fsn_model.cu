@@ -337,6 +337,7 @@ extern "C" int fsn_model_forward(const fsn_model_desc* d, const fsn_seq_weights*
 
 struct EnhanceWs {
   float *real, *imag, *crm;
+  unsigned int* peak;
   void* model;
   size_t bytes;
 };
@@ -354,6 +355,7 @@ static int carve_enhance(const fsn_model_desc* d, int B, int L, int n_fft, int h
   e.real = c.take<float>(BFT);
   e.imag = c.take<float>(BFT);
   e.crm = c.take<float>(2 * BFT);
+  e.peak = c.take<unsigned int>(B);
   ModelWs w;
   carve_model(d, m, nullptr, w);
   e.model = base ? (char*)base + c.off : nullptr;
@@ -370,10 +372,10 @@ extern "C" size_t fsn_enhance_workspace_bytes(const fsn_model_desc* d, int B, in
   return e.bytes;
 }
 
-extern "C" int fsn_enhance(const fsn_model_desc* d, const fsn_seq_weights* fb, const fsn_seq_weights* sb,
-                           const void* sb_packed, const float* wav, int B, int L, int n_fft, int hop,
-                           int win_length, float* enhanced, float* crm_out, void* workspace,
-                           size_t workspace_bytes, fsn_stream_t stream) {
+static int enhance_impl(const fsn_model_desc* d, const fsn_seq_weights* fb, const fsn_seq_weights* sb,
+                        const void* sb_packed, const float* wav, int B, int L, int n_fft, int hop, int win_length,
+                        float* enhanced, float* crm_out, int16_t* pcm, float pcm_gain, void* workspace,
+                        size_t workspace_bytes, fsn_stream_t stream) {
   g_launches = 0;
   // batched inference == loop of B=1 calls of the reference inferencer: drop_band off
   // (audio_zen/inferencer/base_inferencer.py:78,173)
@@ -397,7 +399,25 @@ extern "C" int fsn_enhance(const fsn_model_desc* d, const fsn_seq_weights* fb, c
     return rc;
   prof_mark(1, st);
   if ((rc = model_core(&dd, fb, sb, sb_packed, m, w, crm, st))) return rc;
-  rc = istft_launch(e.real, e.imag, 1, crm, B, m.T, n_fft, hop, win_length, L, enhanced, st);
+  rc = istft_launch(e.real, e.imag, 1, crm, B, m.T, n_fft, hop, win_length, L, enhanced, st, 1, pcm ? e.peak : nullptr);
+  if (!rc && pcm) rc = scale_int16_launch(enhanced, e.peak, B, L, pcm_gain, pcm, st);
   prof_mark(4, st);
   return rc;
+}
+
+extern "C" int fsn_enhance(const fsn_model_desc* d, const fsn_seq_weights* fb, const fsn_seq_weights* sb,
+                           const void* sb_packed, const float* wav, int B, int L, int n_fft, int hop,
+                           int win_length, float* enhanced, float* crm_out, void* workspace,
+                           size_t workspace_bytes, fsn_stream_t stream) {
+  return enhance_impl(d, fb, sb, sb_packed, wav, B, L, n_fft, hop, win_length, enhanced, crm_out, nullptr, 0.f, workspace,
+                      workspace_bytes, stream);
+}
+
+extern "C" int fsn_enhance_pcm(const fsn_model_desc* d, const fsn_seq_weights* fb, const fsn_seq_weights* sb,
+                               const void* sb_packed, const float* wav, int B, int L, int n_fft, int hop,
+                               int win_length, float* enhanced, int16_t* pcm, float gain, void* workspace,
+                               size_t workspace_bytes, fsn_stream_t stream) {
+  FSN_REQUIRE(pcm && enhanced, FSN_ERR_SHAPE, "enhance_pcm: output buffers missing");
+  return enhance_impl(d, fb, sb, sb_packed, wav, B, L, n_fft, hop, win_length, enhanced, nullptr, pcm, gain, workspace,
+                      workspace_bytes, stream);
 }

@@ -239,3 +239,26 @@ class Model(BaseModel):
                                        B, L, n_fft, hop_length, win_length, out.data_ptr(), _lib.ptr(crm),
                                        ws.data_ptr(), ws_bytes, _lib.stream_ptr(device)))
         return (out, crm) if return_crm else out
+
+    @torch.no_grad()
+    def enhance_pcm(self, noisy, n_fft=512, hop_length=256, win_length=512, gain=0.8 * 32767.0):
+        """``enhance`` plus the int16 scaling of the reference host loop (audio_zen/inferencer/base_inferencer.py:
+        181-182) in the same library call (fsn_enhance_pcm: per-clip max|y| reduced in the iSTFT epilogue):
+        noisy [B,L] -> (enhanced float32 [B,L], pcm int16 [B,L])."""
+        assert noisy.dim() == 2, "noisy must be [B, L]"
+        x = _lib.require_cuda(noisy, "noisy")
+        B, L = x.shape
+        device = x.device
+        lib = _lib.load()
+        with torch.cuda.device(device):
+            desc, fb_w, sb_w, packed = self._prepare(device, 1)
+            ws_bytes = lib.fsn_enhance_workspace_bytes(C.byref(desc), B, L, n_fft, hop_length)
+            if ws_bytes == 0:
+                _lib.check_workspace(ws_bytes)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+            out = torch.empty(B, L, dtype=torch.float32, device=device)
+            pcm = torch.empty(B, L, dtype=torch.int16, device=device)
+            _lib.check(lib.fsn_enhance_pcm(C.byref(desc), C.byref(fb_w), C.byref(sb_w), _lib.ptr(packed), x.data_ptr(),
+                                           B, L, n_fft, hop_length, win_length, out.data_ptr(), pcm.data_ptr(),
+                                           float(gain), ws.data_ptr(), ws_bytes, _lib.stream_ptr(device)))
+        return out, pcm

@@ -3,7 +3,8 @@
 audio_zen/inferencer/base_inferencer.py it relies on (attribute names ``model``, ``device``,
 ``torch_stft``, ``torch_istft``; ``_load_model`` :144-161).  Dataset / wav-file handling
 (librosa, soundfile) is outside the hot path and not rebuilt here: construct
-with a model, or with the reference's (config, checkpoint_path) pair."""
+with a model, or with the reference's (config, checkpoint_path) pair.  The host loop around the path (SURVEY 8f
+rank 2) is here in batched form: ``enhance_files`` (wav load -> grouped batches -> fused enhance + int16 -> wav write)."""
 from __future__ import annotations
 
 from functools import partial
@@ -89,6 +90,10 @@ class Inferencer:
         """enhance_batch + the int16 scaling of base_inferencer.py:181-182 on the device: noisy [B,L] -> int16 [B,L]
         (what the reference hands to ``sf.write``); only B*L*2 bytes come back to the host."""
         from . import _lib
+        if hasattr(self.model, "enhance_pcm") and self.n_fft & (self.n_fft - 1) == 0:
+            x = noisy.to(self.device, non_blocking=True)  # fused: peak in the iSTFT epilogue, one scaling pass
+            return self.model.enhance_pcm(x, self.n_fft, self.hop_length, self.win_length,
+                                          gain=0.8 * float(np.iinfo(np.int16).max))[1]
         enhanced = self.enhance_batch(noisy)
         B, L = enhanced.shape
         pcm = torch.empty(B, L, dtype=torch.int16, device=enhanced.device)
@@ -107,6 +112,83 @@ class Inferencer:
             f.setsampwidth(2)
             f.setframerate(int(sr))
             f.writeframes(np.ascontiguousarray(data, dtype="<i2").tobytes())
+
+    # ------------------------------------------------------------------ wav files (base_inferencer.py:163-195, dataset_inference.py:39-43)
+    @staticmethod
+    def load_wav(path, sr: int = 16000) -> np.ndarray:
+        """Mono float32 waveform at ``sr`` from a PCM wav file (8/16/24/32-bit; channels averaged like librosa).  The reference calls
+        ``librosa.load(path, sr=sr)`` (dataset_inference.py:41): same int -> float scaling (1/32768 for 16-bit); when the
+        file's rate differs, a windowed-sinc polyphase resampler stands in for librosa's soxr (not bit-identical to it -
+        the hot-path parity contract starts at the 16 kHz waveform)."""
+        import wave
+        with wave.open(str(path), "rb") as f:
+            nch, width, rate, n = f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()
+            raw = f.readframes(n)
+        if width == 2:
+            y = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+        elif width == 1:
+            y = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+        elif width == 4:
+            y = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
+        elif width == 3:
+            b = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+            v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+            y = (np.where(v >= 1 << 23, v - (1 << 24), v)).astype(np.float32) / 8388608.0
+        else:
+            raise NotImplementedError(f"wav sample width {width}")
+        if nch > 1:  # librosa.load(mono=True): mean over the channels
+            y = y.reshape(-1, nch).mean(axis=1).astype(np.float32)
+        if rate != sr:
+            y = Inferencer.resample(y, rate, sr)
+        return np.ascontiguousarray(y, dtype=np.float32)
+
+    @staticmethod
+    def resample(y: np.ndarray, sr_in: int, sr_out: int, zeros: int = 24) -> np.ndarray:
+        """Band-limited (hann-windowed sinc) polyphase resampling, host side."""
+        from math import gcd
+        g = gcd(int(sr_in), int(sr_out))
+        up, down = sr_out // g, sr_in // g
+        cutoff = min(1.0, up / down)
+        half = int(np.ceil(zeros / cutoff))
+        n_out = int(np.ceil(len(y) * up / down))
+        t_out = np.arange(n_out, dtype=np.float64) * down / up  # positions in input samples
+        base = np.floor(t_out).astype(np.int64)
+        k = np.arange(-half + 1, half + 1)
+        idx = base[:, None] + k[None, :]
+        d = t_out[:, None] - idx
+        w = cutoff * np.sinc(cutoff * d) * (0.5 + 0.5 * np.cos(np.pi * np.clip(d / half, -1, 1)))
+        ok = (idx >= 0) & (idx < len(y))
+        vals = np.where(ok, y[np.clip(idx, 0, len(y) - 1)], 0.0)
+        return (vals * w).sum(axis=1).astype(np.float32)
+
+    @torch.no_grad()
+    def enhance_files(self, paths, output_dir, batch_size: int = 64, sr=None):
+        """Batched form of the host loop of base_inferencer.py:163-195: files are grouped by length (a clip's result
+        depends on its own length through the per-clip norms, so clips are never padded), each group goes through ONE
+        fused library call per ``batch_size`` clips (pinned staging buffer -> H2D -> fsn_enhance_pcm -> int16 D2H), and
+        ``<output_dir>/<stem>.wav`` is written as 16-bit PCM like the reference.  Returns the written paths."""
+        from collections import defaultdict
+        from pathlib import Path
+        sr = int(sr or self.sr)
+        out_dir = Path(output_dir)
+        out_dir.mkdir(parents=True, exist_ok=True)
+        clips = [(Path(p), self.load_wav(p, sr)) for p in paths]
+        groups = defaultdict(list)
+        for i, (_, y) in enumerate(clips):
+            groups[len(y)].append(i)
+        written = [None] * len(clips)
+        for L, idxs in sorted(groups.items()):
+            for s0 in range(0, len(idxs), batch_size):
+                chunk = idxs[s0:s0 + batch_size]
+                stage = torch.empty(len(chunk), L, dtype=torch.float32).pin_memory()
+                for r, i in enumerate(chunk):
+                    stage[r] = torch.from_numpy(clips[i][1])
+                pcm = self.enhance_to_pcm(stage).cpu().numpy()
+                for r, i in enumerate(chunk):
+                    dst = out_dir / f"{clips[i][0].stem}.wav"
+                    self.write_wav(dst, pcm[r], sr)
+                    written[i] = dst
+        return written
 
     @torch.no_grad()
     def __call__(self, clips):

@@ -158,6 +158,14 @@ int fsn_enhance(const fsn_model_desc* d, const fsn_seq_weights* fb, const fsn_se
                 const void* sb_packed, const float* wav, int B, int L, int n_fft, int hop, int win_length,
                 float* enhanced, float* crm_out, void* workspace, size_t workspace_bytes,
                 fsn_stream_t stream);
+/* The same call followed by the int16 scaling of the reference host loop (audio_zen/inferencer/base_inferencer.py:
+ * 181-182: int16(gain * y / max|y|), gain = 0.8 * 32767): max|y| per clip is reduced in the iSTFT epilogue, so the
+ * float waveform is read once more and only 2 bytes per sample have to go back to the host.  `enhanced` (float,
+ * [B,L]) is still written; pcm [B,L] int16. */
+int fsn_enhance_pcm(const fsn_model_desc* d, const fsn_seq_weights* fb, const fsn_seq_weights* sb,
+                    const void* sb_packed, const float* wav, int B, int L, int n_fft, int hop, int win_length,
+                    float* enhanced, int16_t* pcm, float gain, void* workspace, size_t workspace_bytes,
+                    fsn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * recipes/dns_interspeech_2020/fast_fullsubnet/model.py:11-202  Model (BASELINE config 4)

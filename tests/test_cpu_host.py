@@ -272,3 +272,23 @@ def test_row_map_and_reflect_count_match_oracle():
     check_count()
     c = [lib.fsn_debug_reflect_count(r, 257, 15) for r in range(257)]
     assert c[0] == c[256] == 16 and set(c[1:16]) == {32} and set(c[16:241]) == {31}
+
+
+def test_wav_load_resample_write_roundtrip(tmp_path):
+    """Host loop pieces around the path: stdlib wav I/O with librosa's int -> float scaling, channel
+    mean, and the windowed-sinc resampler (48 kHz -> 16 kHz keeps an in-band tone to 1e-4)."""
+    from fullsubnet_b200.inferencer import Inferencer
+    t = np.arange(48000) / 48000.0
+    y = (0.5 * np.sin(2 * np.pi * 440 * t)).astype(np.float32)
+    pcm = np.round(y * 32767).astype(np.int16)
+    Inferencer.write_wav(tmp_path / "a.wav", pcm, 48000)
+    same = Inferencer.load_wav(tmp_path / "a.wav", 48000)
+    assert same.dtype == np.float32 and np.array_equal(same, pcm.astype(np.float32) / 32768.0)
+    z = Inferencer.load_wav(tmp_path / "a.wav", 16000)
+    ref = 0.5 * np.sin(2 * np.pi * 440 * np.arange(len(z)) / 16000.0)
+    assert len(z) == 16000 and np.abs(z[200:-200] - ref[200:-200]).max() < 2e-4
+    import wave
+    with wave.open(str(tmp_path / "st.wav"), "wb") as f:  # stereo: channels are averaged
+        f.setnchannels(2); f.setsampwidth(2); f.setframerate(16000)
+        f.writeframes(np.stack([pcm[:100], -pcm[:100]], 1).astype("<i2").tobytes())
+    assert np.abs(Inferencer.load_wav(tmp_path / "st.wav", 16000)).max() == 0.0

@@ -421,3 +421,40 @@ def test_gru_model_matches_reference(golden, dev):
         make_model(full, O.make_state_dict(seed=0, args=full), dev, "f16_tc")(torch.rand(1, 1, 257, 4, device=dev))
     with pytest.raises(NotImplementedError):
         m.train()(mag)  # BPTT is built for the LSTM recipe
+
+
+def test_batched_file_loop_matches_reference_host_loop(dev, tmp_path):
+    """Inferencer.enhance_files: wav files of two different lengths -> grouped batches -> fsn_enhance_pcm (int16 scaling
+    fused behind the iSTFT) -> wav files; every file equals the reference's per-file flow (base_inferencer.py:172-187:
+    full_band_crm_mask on that clip alone, int16(0.8 * 32767 * y / max|y|))."""
+    import wave
+    from fullsubnet_b200.inferencer import Inferencer
+    from oracle import fullsubnet_oracle as O
+    m = _full_model(dev, 1.0, "auto")
+    inf = Inferencer(model=m, device=dev)
+    lens = [6000, 4000, 6000, 6000, 4000]
+    paths = []
+    for i, L in enumerate(lens):
+        y = O.make_noisy(1, L, seed=50 + i, speechlike=True)[0].numpy()
+        p = tmp_path / f"n{i}.wav"
+        inf.write_wav(p, np.round(y / np.abs(y).max() * 20000).astype(np.int16), 16000)
+        paths.append(p)
+    out = inf.enhance_files(paths, tmp_path / "enh", batch_size=2)
+    amp = np.iinfo(np.int16).max
+    for p, q in zip(paths, out):
+        noisy = torch.from_numpy(inf.load_wav(p, 16000))[None].to(dev)
+        enhanced = inf.full_band_crm_mask(noisy, {})
+        ref = np.int16(0.8 * amp * enhanced / np.max(np.abs(enhanced)))
+        with wave.open(str(q)) as f:
+            got = np.frombuffer(f.readframes(f.getnframes()), dtype="<i2")
+            assert f.getframerate() == 16000
+        assert q.name == p.name and got.shape == ref.shape
+        assert np.abs(got.astype(np.int32) - ref).max() <= 1, int(np.abs(got.astype(np.int32) - ref).max())
+    # fused peak == separate peak-normalise kernel, bit for bit
+    y = O.make_noisy(3, 6000, seed=5, speechlike=True).to(dev)
+    enh, pcm = m.enhance_pcm(y)
+    from fullsubnet_b200 import _lib
+    pcm2 = torch.empty_like(pcm)
+    _lib.check(_lib.load().fsn_peak_normalize_int16(enh.data_ptr(), 3, 6000, 0.8 * 32767.0, pcm2.data_ptr(),
+                                                    torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(pcm, pcm2) and torch.equal(enh, m.enhance(y))
