@@ -121,6 +121,8 @@ _SIGNATURES = {
     "fsn_fullband_forward": (C.c_int, [C.POINTER(FullbandDesc), _P, _P, _P, _P, _I, _I, _P, _P, _S, _P]),
     "fsn_peak_normalize_int16": (C.c_int, [_P, _I, _I, _F, _P, _P]),
     "fsn_si_sdr": (C.c_int, [_P, _P, _I, _I, _P, _P]),
+    "fsn_rir_convolve": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "fsn_snr_mix": (C.c_int, [_P, _P, _P, _P, _F, _F, _I, _I, _P, _P, _P]),
     "fsn_debug_row_to_unit": (C.c_int, [_I, _I, _I, _I, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "fsn_debug_unit_to_row": (C.c_int, [_I, _I, _I, _I, _I]),
     "fsn_debug_reflect_count": (C.c_int, [_I, _I, _I]),

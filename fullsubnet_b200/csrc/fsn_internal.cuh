@@ -52,7 +52,7 @@ int lstm_step_launch(const StepParams& p, int mode, cudaStream_t st);
 // scaleT[t*R+r] of every sub-band unit (running mean over its K rows and the frames so far)
 int cum_clip_scale_launch(const float2* fs, int B, int Tp, int F, float eps, float* scale1T, cudaStream_t st);
 int cum_unit_scale_launch(const float* magT, const float* fbT, RowMap map, int R, int Tp, int Ns, int Nf, float eps,
-                          float* scaleT, cudaStream_t st);
+                          float* scaleT, cudaStream_t st, bool time_major = false);
 
 // tf32 tcgen05 GEMM (fsn_tgemm.cu): C[M,N] (+)= A[M,K] B[N,K]^T, fp32 row-major operands with 16-byte aligned rows
 bool tgemm_supported(const float* A, size_t lda, const float* Bm, size_t ldb, int K);

@@ -221,8 +221,9 @@ __global__ void cum_clip_scale_kernel(const float2* __restrict__ fs, int B, int 
   }
 }
 
+// mag / fb element (b, t, f) at b*bs + t*ts + f: clip-major [B,Tp,F] (inference) or time-major [Tp,B,F] (training)
 __global__ void cum_unit_scale_kernel(const float* __restrict__ magT, const float* __restrict__ fbT, RowMap map, int R,
-                                      int Tp, int Ns, int Nf, float eps, float* __restrict__ scaleT) {
+                                      int Tp, int Ns, int Nf, float eps, float* __restrict__ scaleT, size_t bs, size_t ts) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   int b, f;
@@ -230,7 +231,7 @@ __global__ void cum_unit_scale_kernel(const float* __restrict__ magT, const floa
   const int K = 2 * Ns + 1 + 2 * Nf + 1;
   float run = 0.f;
   for (int t = 0; t < Tp; ++t) {
-    const size_t base = ((size_t)b * Tp + t) * map.F;
+    const size_t base = (size_t)b * bs + (size_t)t * ts;
     float s = 0.f;
     for (int k = -Ns; k <= Ns; ++k) s += magT[base + reflect_idx(f + k, map.F)];
     for (int k = -Nf; k <= Nf; ++k) s += fbT[base + reflect_idx(f + k, map.F)];
@@ -246,8 +247,9 @@ int cum_clip_scale_launch(const float2* fs, int B, int Tp, int F, float eps, flo
 }
 
 int cum_unit_scale_launch(const float* magT, const float* fbT, RowMap map, int R, int Tp, int Ns, int Nf, float eps,
-                          float* scaleT, cudaStream_t st) {
-  cum_unit_scale_kernel<<<cdiv(R, 128), 128, 0, st>>>(magT, fbT, map, R, Tp, Ns, Nf, eps, scaleT);
+                          float* scaleT, cudaStream_t st, bool time_major) {
+  const size_t bs = time_major ? (size_t)map.F : (size_t)Tp * map.F, ts = time_major ? (size_t)map.B * map.F : (size_t)map.F;
+  cum_unit_scale_kernel<<<cdiv(R, 128), 128, 0, st>>>(magT, fbT, map, R, Tp, Ns, Nf, eps, scaleT, bs, ts);
   FSN_CHECK_LAUNCH("cum_unit_scale_kernel");
   return FSN_OK;
 }

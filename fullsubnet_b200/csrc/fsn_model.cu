@@ -75,8 +75,6 @@ int make_dims(const fsn_model_desc* d, int B, int T, Dims& m) {
   FSN_REQUIRE(B > 0 && T > 0, FSN_ERR_SHAPE, "model: empty input (B=%d, T=%d)", B, T);
   FSN_REQUIRE(d->norm_type == FSN_NORM_OFFLINE_LAPLACE || d->norm_type == FSN_NORM_CUMULATIVE_LAPLACE,
               FSN_ERR_UNSUPPORTED, "You must set up a type of Norm. (offline_laplace_norm / cumulative_laplace_norm are built)");
-  FSN_REQUIRE(d->norm_type == FSN_NORM_OFFLINE_LAPLACE || d->precision != FSN_PREC_TF32_TC, FSN_ERR_UNSUPPORTED,
-              "cumulative_laplace_norm is built for inference (the training step keeps the offline norm)");
   FSN_REQUIRE(d->cell_type == FSN_CELL_LSTM || (d->cell_type == FSN_CELL_GRU && d->precision == FSN_PREC_FP32),
               FSN_ERR_UNSUPPORTED, "model: sequence_model must be LSTM, or GRU on the fp32 kernels (precision fp32)");
   FSN_REQUIRE(d->sb_num_neighbors >= 0 && d->fb_num_neighbors >= 0 && d->sb_num_neighbors < d->num_freqs &&

@@ -239,8 +239,8 @@ __global__ void train_transpose_kernel(const float* __restrict__ mag, const floa
 
 // sub-band input X[t,r,k] (base_model.py:13-46 + model.py:98-119): unit (b,f) of row r, scaled by inv2[b]
 __global__ void train_gather_kernel(const float* __restrict__ raw, const float* __restrict__ fbz,
-                                    const float* __restrict__ inv2, float* __restrict__ X, RowMap map, int Tp, int R,
-                                    int Ns, int Nf) {
+                                    const float* __restrict__ inv2, const float* __restrict__ unit_scale,
+                                    float* __restrict__ X, RowMap map, int Tp, int R, int Ns, int Nf) {
   const int K = 2 * Ns + 1 + 2 * Nf + 1;
   const size_t n = (size_t)Tp * R * K;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -253,7 +253,61 @@ __global__ void train_gather_kernel(const float* __restrict__ raw, const float* 
     float v;
     if (k < 2 * Ns + 1) v = raw[base + reflect_idx(f + k - Ns, map.F)];
     else                v = fbz[base + reflect_idx(f + (k - 2 * Ns - 1) - Nf, map.F)];
-    X[i] = v * inv2[b];
+    X[i] = v * (unit_scale ? unit_scale[tr] : inv2[b]);  // cumulative norm: scale of (step t, unit r) at [t*R + r]
+  }
+}
+
+// ---- cumulative_laplace_norm in the training step (audio_zen/model/base_model.py:220-251)
+// frame sums of a time-major tensor raw [Tp,B,F] in the layout cum_clip_scale_launch reads: fs[b*Tp + t].x
+__global__ void train_frame_sum_kernel(const float* __restrict__ raw, int B, int F, int Tp, float2* __restrict__ fs) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // row = t*B + b
+  const int lane = threadIdx.x & 31;
+  if (row >= Tp * B) return;
+  const float* p = raw + (size_t)row * F;
+  float a = 0.f;
+  for (int f = lane; f < F; f += 32) a += p[f];
+  a = warp_sum(a);
+  if (lane == 0) { const int t = row / B, b = row - t * B; fs[(size_t)b * Tp + t] = make_float2(a, a); }
+}
+// xfb[t,b,f] = raw[t,b,f] * scale1T[t*B + b]
+__global__ void train_scale_tm_kernel(const float* __restrict__ raw, const float* __restrict__ scale1T, int F, size_t n,
+                                      float* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = raw[i] * scale1T[i / F];
+}
+// Backward of X[t,r,k] = u[t,r,k] * s[t,r], s = 1/(m + eps), m[t,r] = sum_{t'<=t} sum_k u[t',r,k] / (K (t+1)):
+//   d u[t,r,k] = dX[t,r,k] s[t,r] + sum_{t''>=t} q[t'',r],   q[t,r] = -s[t,r] <dX[t,r,:], X[t,r,:]> / (K (t+1)).
+// Only the full-band row k = K-1 has a parameter behind it (Nf = 0): dunit[t,r] = its gradient.  One thread per
+// unit, sequential in t (suffix sum in a fixed order).
+__global__ void train_cum_unit_bwd_kernel(const float* __restrict__ dX, const float* __restrict__ X,
+                                          const float* __restrict__ scaleT, int Tp, int R, int K, float* __restrict__ dunit) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  float suffix = 0.f;
+  for (int t = Tp - 1; t >= 0; --t) {
+    const size_t o = ((size_t)t * R + r) * K;
+    float dot = 0.f;
+    for (int k = 0; k < K; ++k) dot = fmaf(dX[o + k], X[o + k], dot);
+    const float s = scaleT[(size_t)t * R + r];
+    suffix += -s * dot / ((float)K * (float)(t + 1));
+    dunit[(size_t)t * R + r] = fmaf(dX[o + K - 1], s, suffix);
+  }
+}
+// dz[t,b,f] = act'(fbz) * dunit[t, row(b,f)]  (units removed by drop_band carry no gradient: their norm is their own)
+__global__ void train_dfbz_cum_kernel(const float* __restrict__ dunit, const float* __restrict__ fbz, RowMap map, int Tp,
+                                      int R, int act, float* __restrict__ dz) {
+  const size_t n = (size_t)Tp * map.B * map.F;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int f = (int)(i % map.F);
+    const size_t tb = i / map.F;
+    const int b = (int)(tb % map.B), t = (int)(tb / map.B);
+    const int r = unit_to_row(map, b, f);
+    float v = r >= 0 ? dunit[(size_t)t * R + r] : 0.f;
+    const float y = fbz[i];
+    if (act == FSN_ACT_RELU) v = y > 0.f ? v : 0.f;
+    else if (act == FSN_ACT_TANH) v *= 1.f - y * y;
+    else if (act == FSN_ACT_RELU6) v = (y > 0.f && y < 6.f) ? v : 0.f;
+    dz[i] = v;
   }
 }
 
@@ -417,6 +471,8 @@ struct TrainWs {
   // FSN_PREC_TF32_TC: transposed weights ([H,4H], [K0,4H]) and transposed dG / layer inputs for the weight gradients
   float *sb_whhT[2], *sb_wihT[2], *fb_whhT[2], *fb_wihT1;
   float *gT, *xT, *rec;
+  float *cum1, *cum2, *dunit;  // cumulative norm: scale of (step, clip), of (step, unit); gradient of the fb row per unit
+  float2* fs;
   size_t bytes;
 };
 
@@ -447,6 +503,11 @@ static void carve_train(const fsn_model_desc* d, const Dims& m, void* base, Trai
   for (int i = 0; i < 2; ++i) { w.dh_rec[i] = c.take(RH); w.dc[i] = c.take(RH); }
   w.dh_mid = c.take(RH);
   w.dot = c.take(B);
+  w.cum1 = w.cum2 = w.dunit = nullptr; w.fs = nullptr;
+  if (d->norm_type == FSN_NORM_CUMULATIVE_LAPLACE) {
+    w.cum1 = c.take(Tp * B); w.cum2 = c.take(Tp * R); w.dunit = c.take(Tp * R);
+    w.fs = (float2*)c.take(2 * Tp * B);
+  }
   w.splitk = c.take(SPLITK_SCRATCH_FLOATS);
   const size_t maxcols = 4 * (Hf > Hs ? Hf : Hs) > F ? 4 * (Hf > Hs ? Hf : Hs) : F;
   w.colsum = c.take((size_t)COLSUM_MAX_S * maxcols);
@@ -467,8 +528,8 @@ static void carve_train(const fsn_model_desc* d, const Dims& m, void* base, Trai
 }
 
 static int train_check(const fsn_model_desc* d) {
-  FSN_REQUIRE(d->norm_type == FSN_NORM_OFFLINE_LAPLACE, FSN_ERR_UNSUPPORTED,
-              "training: only offline_laplace_norm is built");
+  FSN_REQUIRE(d->norm_type == FSN_NORM_OFFLINE_LAPLACE || d->norm_type == FSN_NORM_CUMULATIVE_LAPLACE, FSN_ERR_UNSUPPORTED,
+              "training: offline_laplace_norm and cumulative_laplace_norm are built");
   FSN_REQUIRE(d->fb_num_neighbors == 0, FSN_ERR_UNSUPPORTED,
               "training: fb_num_neighbors > 0 is not built (every shipped recipe uses 0)");
   FSN_REQUIRE(d->cell_type == FSN_CELL_LSTM, FSN_ERR_UNSUPPORTED, "training: the GRU cell is built for inference only");
@@ -630,6 +691,15 @@ extern "C" int fsn_train_forward(const fsn_model_desc* d, const fsn_seq_weights*
   train_transpose_kernel<<<dim3(cdiv(Tp, 32), cdiv(F, 32), B), dim3(32, 8), 0, st>>>(noisy_mag, w.inv1, w.raw, w.xfb, B,
                                                                                      F, T, Tp);
   FSN_CHECK_LAUNCH("train_transpose_kernel");
+  const bool cum = d->norm_type == FSN_NORM_CUMULATIVE_LAPLACE;
+  const float cum_eps = 1.1920928955078125e-07f;  // audio_zen/constant.py:9
+  if (cum) {  // causal running mean per clip instead of the clip mean (base_model.py:220-251)
+    train_frame_sum_kernel<<<cdiv(Tp * B, 8), 256, 0, st>>>(w.raw, B, F, Tp, w.fs);
+    FSN_CHECK_LAUNCH("train_frame_sum_kernel");
+    if ((rc = cum_clip_scale_launch(w.fs, B, Tp, F, cum_eps, w.cum1, st))) return rc;
+    train_scale_tm_kernel<<<148 * 8, 256, 0, st>>>(w.raw, w.cum1, F, (size_t)Tp * B * F, w.xfb);
+    FSN_CHECK_LAUNCH("train_scale_tm_kernel");
+  }
   // full-band stack + Linear/activation (model.py:92-95)
   const bool tc_fb = tc_layer_ok(d, Hf), tc_sb = tc_layer_ok(d, Hs);
   if (tc_fb) {
@@ -646,8 +716,11 @@ extern "C" int fsn_train_forward(const fsn_model_desc* d, const fsn_seq_weights*
   if ((rc = norm_scales_launch(w.sums_mag, w.sums_fb, B, 1.f, (float)F * m.Ksb * Tp, nullptr, w.inv2, st))) return rc;
   // sub-band units (unfold + concat + norm + drop_band as one gather), then the sub-band stack (model.py:98-128)
   RowMap map{B, F, m.Fsub, m.G};
-  train_gather_kernel<<<148 * 8, 256, 0, st>>>(w.raw, w.fbz, w.inv2, w.xsb, map, Tp, m.R, d->sb_num_neighbors,
-                                               d->fb_num_neighbors);
+  if (cum && (rc = cum_unit_scale_launch(w.raw, w.fbz, map, m.R, Tp, d->sb_num_neighbors, d->fb_num_neighbors, cum_eps, w.cum2,
+                                         st, /*time_major=*/true)))
+    return rc;
+  train_gather_kernel<<<148 * 8, 256, 0, st>>>(w.raw, w.fbz, w.inv2, cum ? w.cum2 : nullptr, w.xsb, map, Tp, m.R,
+                                               d->sb_num_neighbors, d->fb_num_neighbors);
   FSN_CHECK_LAUNCH("train_gather_kernel");
   if (tc_sb) {
     if ((rc = layer_forward_save_tc(sb, 0, w.xsb, m.R, m.Ksb, Hs, Tp, w.sb[0], w.rec, st))) return rc;
@@ -710,11 +783,18 @@ extern "C" int fsn_train_backward(const fsn_model_desc* d, const fsn_seq_weights
     return rc;
   if ((rc = layer_weight_grads(s0, Tp, w.xsb, gsb->w_ih[0], gsb->w_hh[0], gsb->b_ih[0], gsb->b_hh[0], w, st))) return rc;
   // ---- second norm + drop_band + full-band Linear/activation
-  train_dot_kernel<<<B, 256, 0, st>>>(w.dxsb, w.xsb, Tp, R, m.Fsub, K, w.dot);
-  FSN_CHECK_LAUNCH("train_dot_kernel");
-  train_dfbz_kernel<<<148 * 8, 256, 0, st>>>(w.dxsb, w.fbz, w.inv2, w.dot, map, Tp, R, K, (float)F * K * Tp,
-                                             d->fb_activation, w.dz);
-  FSN_CHECK_LAUNCH("train_dfbz_kernel");
+  if (d->norm_type == FSN_NORM_CUMULATIVE_LAPLACE) {
+    train_cum_unit_bwd_kernel<<<cdiv(R, 128), 128, 0, st>>>(w.dxsb, w.xsb, w.cum2, Tp, R, K, w.dunit);
+    FSN_CHECK_LAUNCH("train_cum_unit_bwd_kernel");
+    train_dfbz_cum_kernel<<<148 * 8, 256, 0, st>>>(w.dunit, w.fbz, map, Tp, R, d->fb_activation, w.dz);
+    FSN_CHECK_LAUNCH("train_dfbz_cum_kernel");
+  } else {
+    train_dot_kernel<<<B, 256, 0, st>>>(w.dxsb, w.xsb, Tp, R, m.Fsub, K, w.dot);
+    FSN_CHECK_LAUNCH("train_dot_kernel");
+    train_dfbz_kernel<<<148 * 8, 256, 0, st>>>(w.dxsb, w.fbz, w.inv2, w.dot, map, Tp, R, K, (float)F * K * Tp,
+                                               d->fb_activation, w.dz);
+    FSN_CHECK_LAUNCH("train_dfbz_kernel");
+  }
   if ((rc = sgemm_launch(true, w.dz, F, w.fb[1].H, Hf, gfb->fc_w, Hf, F, Hf, Tp * B, false, w.splitk, st))) return rc;
   if ((rc = colsum_launch(w.dz, (size_t)Tp * B, F, F, gfb->fc_b, nullptr, w.colsum, st))) return rc;
   if ((rc = sgemm_launch(false, w.dz, F, fb->fc_w, Hf, w.dfh1, Hf, Tp * B, Hf, F, false, nullptr, st))) return rc;

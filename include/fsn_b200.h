@@ -333,6 +333,18 @@ int fsn_peak_normalize_int16(const float* wav, int B, int L, float gain, int16_t
  * reference, estimation [B,L] -> out[B] in dB; fixed-order reductions. */
 int fsn_si_sdr(const float* reference, const float* estimation, int B, int L, float* out, fsn_stream_t stream);
 
+/* recipes/dns_interspeech_2020/dataset_train.py:136-199  Dataset.snr_mix for a batch: the random
+ * draws (snr, noisy target dBFS, which RIR) are made by the caller and passed in.
+ *   fsn_rir_convolve: out[b,:L] = fftconvolve(x[b], rir[b,:rir_len[b]])[:L]  (dataset_train.py:161; direct form,
+ *                     rir [B,Lr_max], rir_len[b] == 0 copies the clip; rir_len may be NULL = Lr_max everywhere)
+ *   fsn_snr_mix:      norm_amplitude + tailor_dB_FS(target_dB_FS) of clean and noise, noise scaled to snr[b] dB,
+ *                     mixture tailored to noisy_target_dB_FS[b] (clean by the same factor), both divided by
+ *                     max|noisy| / (0.99 - eps) when the mixture exceeds 0.999 (audio_zen/acoustics/feature.py:99-114). */
+int fsn_rir_convolve(const float* x, const float* rir, const int* rir_len, int B, int L, int Lr_max, float* out,
+                     fsn_stream_t stream);
+int fsn_snr_mix(const float* clean, const float* noise, const float* snr, const float* noisy_target_dB_FS,
+                float target_dB_FS, float eps, int B, int L, float* noisy_out, float* clean_out, fsn_stream_t stream);
+
 /* unit-test hooks (host code only): the drop_band row map of Model.forward and its inverse (-1 = unit dropped), and
  * the reflect-padding multiplicity c[r] of the closed-form second norm */
 int fsn_debug_row_to_unit(int B, int F, int G, int r, int* b, int* f);

@@ -175,13 +175,15 @@ def test_workspace_queries_report_error_class_without_gpu():
     from fullsubnet_b200 import _lib
     lib = _lib.load()
     d = _lib.ModelDesc(num_freqs=257, look_ahead=2, fb_num_neighbors=0, sb_num_neighbors=15, fb_hidden=512, sb_hidden=384,
-                       fb_activation=1, sb_activation=0, norm_type=0, num_groups_in_drop_band=2, precision=2, reserved=0)
+                       fb_activation=1, sb_activation=0, norm_type=0, num_groups_in_drop_band=2, precision=2, cell_type=0)
     n = lib.fsn_train_workspace_bytes(C.byref(d), 64, 188)
     assert 40e9 < n < 50e9  # config 3: 28.7 GB of saved activations + transposed copies and scratch
     assert lib.fsn_train_workspace_bytes(C.byref(d), 2, 188) == 0  # B == G (feature.py:317-319)
     assert lib.fsn_last_error_code() == _lib.FSN_ERR_SHAPE and b"Batch size" in lib.fsn_last_error()
     d.norm_type = 1
-    assert lib.fsn_train_workspace_bytes(C.byref(d), 64, 188) == 0  # cumulative norm + tensor-core precision
+    assert lib.fsn_train_workspace_bytes(C.byref(d), 64, 188) > n  # cumulative norm: + the per-step scale tables
+    d.norm_type, d.cell_type, d.precision = 0, 1, 2
+    assert lib.fsn_model_workspace_bytes(C.byref(d), 4, 100) == 0  # GRU is built for the fp32 inference kernels only
     assert lib.fsn_last_error_code() == _lib.FSN_ERR_UNSUPPORTED
     with pytest.raises(NotImplementedError):
         _lib.check_workspace(0)

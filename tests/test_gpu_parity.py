@@ -322,14 +322,6 @@ def test_cumulative_laplace_norm_matches_reference(golden, dev):
             WAV_TOL if prec != "f16_tc" else 1e-2), prec
 
 
-def test_cumulative_laplace_norm_unsupported_combinations(dev):
-    from oracle import fullsubnet_oracle as O
-    full = dict(O.DEFAULT_MODEL_ARGS, norm_type="cumulative_laplace_norm")
-    sd = O.make_state_dict(seed=0, args=full)
-    with pytest.raises(NotImplementedError):
-        make_model(full, sd, dev, "auto").train()(torch.rand(3, 1, 257, 5, device=dev))  # training: offline norm only
-
-
 # ------------------------------------------------------------------ n_fft = 960 (direct-DFT kernels, fsn_dsp_dft.cu)
 def test_non_power_of_two_stft_istft(golden, dev):
     from fullsubnet_b200.acoustics.feature import stft, istft

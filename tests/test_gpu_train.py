@@ -329,3 +329,69 @@ def test_trainer_with_validation_loader(golden, dev, tmp_path):
         enh = torch.from_numpy(inf.full_band_crm_mask(noisy[i:i + 1].to(dev), {}))[None].to(dev)
         scores.append(float(si_sdr(clean[i:i + 1].to(dev), enh)[0]))
     assert abs(np.mean(scores) - v["si_sdr"]["With_reverb"]) < 1e-3
+
+
+def test_snr_mix_kernels_match_reference(golden, dev):
+    """fsn_rir_convolve + fsn_snr_mix vs the unmodified Dataset.snr_mix (tests/golden/mix.npz), all cases in ONE
+    batched call (clips without reverberation have rir_len 0)."""
+    from fullsubnet_b200.dataset import snr_mix
+    g = golden("mix")
+    cases = g["cases"]
+    n = len(cases)
+    Lr = max(int(c[2]) for c in cases)
+    clean = torch.from_numpy(np.stack([g[f"c{i}_clean"] for i in range(n)])).to(dev)
+    noise = torch.from_numpy(np.stack([g[f"c{i}_noise"] for i in range(n)])).to(dev)
+    rir = torch.zeros(n, Lr)
+    for i, c in enumerate(cases):
+        if c[2]:
+            rir[i, :c[2]] = torch.from_numpy(g[f"c{i}_rir"])
+    noisy, clean_out = snr_mix(clean, noise, cases[:, 0].astype(np.float32), -25, cases[:, 1].astype(np.float32),
+                               rir=rir.to(dev), rir_len=torch.from_numpy(cases[:, 2].astype(np.int32)))
+    for i in range(n):
+        assert rel_max(noisy[i].cpu(), g[f"c{i}_noisy"]) < 2e-5, i
+        assert rel_max(clean_out[i].cpu(), g[f"c{i}_clean_out"]) < 2e-5, i
+    # without any RIR the convolution is skipped entirely
+    noisy2, _ = snr_mix(clean[:2], noise[:2], cases[:2, 0].astype(np.float32), -25, cases[:2, 1].astype(np.float32))
+    assert torch.equal(noisy2, noisy[:2])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32_tc"])
+def test_cumulative_norm_training_matches_reference(golden, dev, prec):
+    """norm_type="cumulative_laplace_norm" in the training step (train_cumulativeLaplaceNorm.toml:82): per-(step, clip) and
+    per-(step, unit) running means in the forward, their suffix-sum backward; two golden steps of the unmodified reference,
+    and the full-size architecture against CPU autograd of the oracle."""
+    from fullsubnet_b200.loss import mse_loss
+    from fullsubnet_b200.optim import FusedClipAdam
+    from oracle import fullsubnet_oracle as O
+    from oracle import train_oracle as TO
+    g = golden("train_cum_small")
+    args = dict(small_args(), norm_type="cumulative_laplace_norm")
+    m = build(args, O.make_state_dict(seed=7, args=args, sb_fc_gain=8.0), dev, prec)
+    opt = FusedClipAdam(m.parameters(), lr=1e-3, betas=(0.9, 0.999), max_norm=10.0)
+    noisy, clean = T(g["noisy"], dev), T(g["clean"], dev)
+    for it in range(2):
+        opt.zero_grad()
+        loss, _, crm = reference_like_step(m, noisy, clean, 64, 32, mse_loss())
+        assert abs(float(loss.detach()) - g["loss"][it]) <= LOSS_TOL[prec] * abs(g["loss"][it]), (it, float(loss), g["loss"][it])
+        if it == 0:
+            assert rel_max(crm.detach().cpu(), g["crm"]) < (1e-5 if prec == "fp32" else 1e-3)
+            for k, p in m.named_parameters():
+                assert rel_l2(p.grad.cpu(), g["grad." + k]) < GRAD_TOL[prec], k
+        opt.step()
+        if prec == "fp32":
+            assert abs(float(opt.last_norm[0]) - g["gnorm"][it]) < 1e-4 * g["gnorm"][it]
+            for k, v in m.state_dict().items():
+                assert np.abs(v.cpu().numpy() - g[f"p{it}." + k]).max() < 2e-5, (it, k)
+    if prec != "fp32":
+        return
+    full = dict(O.DEFAULT_MODEL_ARGS, weight_init=False, norm_type="cumulative_laplace_norm")
+    sd = O.make_state_dict(seed=0, args=full, sb_fc_gain=40.0)
+    ny, cl = O.make_noisy(3, 2048, seed=5, speechlike=True), 0.5 * O.make_noisy(3, 2048, seed=6)
+    nm, cirm = TO.targets(ny, cl, 2)
+    ref_loss, ref_grads, _ = TO.loss_and_grads(nm, cirm, sd, full)
+    mf = build(full, sd, dev, "fp32")
+    loss = mse_loss()(cirm.to(dev), mf(nm.unsqueeze(1).to(dev)).permute(0, 2, 3, 1))
+    loss.backward()
+    assert abs(float(loss.detach()) - float(ref_loss)) < 1e-5 * float(ref_loss)
+    for k, p in mf.named_parameters():
+        assert rel_l2(p.grad.cpu(), ref_grads[k]) < 2e-4, k

@@ -283,3 +283,14 @@ def test_gru_oracle_matches_reference(golden):
     wav, crm = O.enhance(T(g["full_y"]), O.make_state_dict(seed=0, args=full, sb_fc_gain=60.0), full, return_crm=True)
     assert rel_max(crm, g["full_crm"]) < 2e-5
     assert np.abs(wav.numpy() - g["full_wav"]).max() < 1e-5
+
+
+def test_snr_mix_oracle_matches_reference(golden):
+    """Dataset.snr_mix (dataset_train.py:136-199): plain, negative SNR, reverberant and clipped cases."""
+    from oracle import mix_oracle as M
+    g = golden("mix")
+    for i, (snr, draw, rir_len) in enumerate(g["cases"]):
+        rir = g[f"c{i}_rir"] if rir_len else None
+        noisy, clean = M.snr_mix(g[f"c{i}_clean"], g[f"c{i}_noise"], float(snr), -25, float(draw), rir=rir)
+        assert rel_max(noisy, g[f"c{i}_noisy"]) < 2e-5 and rel_max(clean, g[f"c{i}_clean_out"]) < 2e-5, i
+    assert np.abs(g["c1_noisy"]).max() > 0.98  # the clipped case really took the rescale branch (max = 0.99 - eps)
