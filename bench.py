@@ -176,9 +176,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=256, help="clips per GPU (configs[1]: 256)")
     ap.add_argument("--precision", default="auto")
-    ap.add_argument("--model", default="fullsubnet", choices=["fullsubnet", "fast_fullsubnet", "fullsubnet_train"],
+    ap.add_argument("--model", default="fullsubnet", choices=["fullsubnet", "fast_fullsubnet", "improved_fullsubnet", "fullsubnet_train"],
                     help="fullsubnet = BASELINE configs[1] (the headline); fast_fullsubnet = configs[3] (use --batch 512); "
+                         "improved_fullsubnet = configs[4] (48 kHz, n_fft 1024, use --batch 128; --variant k48_960 = the "
+                         "reference's own 48 kHz example, k16 = the class defaults); "
                          "fullsubnet_train = configs[2], the training step (bench_train.py)")
+    ap.add_argument("--variant", default="k48", choices=["k48", "k48_960", "k16"], help="improved_fullsubnet constructor args")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the `precisions`, `latency_b1` and `train_dp` objects")
@@ -212,7 +215,23 @@ def main():
     lib = _lib.load()
     B, L = args.batch, SR * CLIP_SECONDS
     T = 1 + L // HOP
-    if args.model == "fast_fullsubnet":
+    imp_args = None
+    frame_rate = SR / HOP  # frames per second of real time (x RT = frames/s / frame_rate)
+    if args.model == "improved_fullsubnet":
+        from fullsubnet_b200.improved_fullsubnet.model import Model as ImpModel
+        from oracle import improved_fullsubnet_oracle as IO
+        imp_args = {"k48": IO.ARGS_48K_1024, "k48_960": IO.ARGS_48K_960, "k16": IO.DEFAULT_IMPROVED_ARGS}[args.variant]
+        sr = 16000 if args.variant == "k16" else 48000
+        L = sr * 2  # BASELINE configs[4]: 2 s clips
+        T = 1 + L // imp_args["hop_length"]
+        frame_rate = sr / imp_args["hop_length"]
+        model = ImpModel(**imp_args)
+        model.load_state_dict(IO.make_improved_state_dict(seed=5, args=imp_args), strict=True)
+        if args.precision != "auto":
+            model.precision = args.precision
+        model = model.to(dev).eval()
+        precision = model._resolve_precision()
+    elif args.model == "fast_fullsubnet":
         from fullsubnet_b200.fast_fullsubnet.model import Model as FastModel
         from oracle import fast_fullsubnet_oracle as FO
         model = FastModel(**FO.DEFAULT_FAST_ARGS, **({"precision": args.precision} if "precision" in
@@ -225,7 +244,7 @@ def main():
         model.load_state_dict(O.make_state_dict(seed=0), strict=True)
         model = model.to(dev).eval()
         precision = model._resolve_precision()
-    inf = Inferencer(model=model, device=dev)
+    inf = Inferencer(model=model, device=dev) if imp_args is None else None
     host_in = O.make_noisy(B, L, seed=rank).pin_memory()  # every rank enhances its own clips
     host_out = torch.empty(B, L, dtype=torch.float32).pin_memory()
     x_dev = host_in.to(dev)
@@ -264,12 +283,19 @@ def main():
     def step_resident():
         if args.model == "fullsubnet":
             model.enhance(x_dev, N_FFT, HOP, WIN)
+        elif args.model == "improved_fullsubnet":
+            with torch.no_grad():
+                model(x_dev)  # wav -> wav (improved_fullsubnet/model.py:541-591)
         else:
             inf.enhance_batch(x_dev)
 
     def step_e2e():
-        out = inf.enhance_batch(host_in)  # H2D inside
-        host_out.copy_(out, non_blocking=True)  # D2H inside
+        if args.model == "improved_fullsubnet":
+            with torch.no_grad():
+                out = model(host_in.to(dev, non_blocking=True))
+        else:
+            out = inf.enhance_batch(host_in)  # H2D inside
+        host_out.copy_(out.reshape(B, L), non_blocking=True)  # D2H inside
         torch.cuda.current_stream().synchronize()
 
     sampler = ClockSampler(local)
@@ -313,19 +339,22 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None,
         "dtype": {"f16_tc": "f16xf32acc", "f16x3_tc": "f16x3(hi+lo split, fp32-class)xf32acc"}.get(precision, "f32"),
-        "data": "synthetic", "rtf_x": value / (SR / HOP),
+        "data": "synthetic", "rtf_x": value / frame_rate,
         "config": {"workload": (f"fullsubnet inference, batch={B} x 4 s 16 kHz synthetic clips per GPU, "
                                 "n_fft=512 hop=256 N=15, 2xLSTM-512 fb + 2xLSTM-384 sb (BASELINE configs[1])"
                                 if args.model == "fullsubnet" else
-                                f"fast_fullsubnet inference, batch={B} x 4 s 16 kHz synthetic clips per GPU "
-                                "(BASELINE configs[3])"),
+                                (f"improved_fullsubnet inference ({args.variant}: n_fft={imp_args['n_fft']} "
+                                 f"hop={imp_args['hop_length']}), batch={B} x 2 s synthetic clips per GPU (BASELINE configs[4])"
+                                 if imp_args is not None else
+                                 f"fast_fullsubnet inference, batch={B} x 4 s 16 kHz synthetic clips per GPU "
+                                 "(BASELINE configs[3])")),
                    "clips_per_gpu": B, "frames_per_clip": T, "precision": precision,
                    "precision_note": "headline = the fastest arithmetic that meets BOTH parity gates (cRM 1e-3 rel, "
                                      "waveform 1e-4 abs) on BOTH weight sets W-a and W-b (tests/test_gpu_parity.py); "
                                      "single-pass f16_tc and fp32 are under `precisions`",
                    "l2": "256 MiB flush write between timed iterations", "parallelism": f"clips sharded x{world}"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * L * 4, "rtf_x": e2e_value / (SR / HOP)},
+                "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * L * 4, "rtf_x": e2e_value / frame_rate},
         "gpu_launches": launches,
         "clocks": clocks,
         "stage_ms": {"stft": stage_ms[0], "fullband": stage_ms[1], "subband": stage_ms[2], "mask_istft": stage_ms[3]},

@@ -103,6 +103,8 @@ struct ImpWs {
   float *fbs_h0[2], *fbs_c0, *fbs_c1;  // per-step full-band fallback
   LayerSave tc;                        // FSN_PREC_TF32_TC: gates / cell / hidden of every step of one layer
   float *tc_h1, *tc_rec;
+  LstmTcWs fbtc;                       // FSN_PREC_TF32_TC: full band on the hoisted-GEMM + persistent-recurrence kernels
+  float* fbtc_mid;
   size_t bytes;
 };
 
@@ -174,6 +176,12 @@ static void imp_carve(const fsn_improved_desc* d, const ImpDims& m, void* base, 
     w.tc_h1 = c.take<float>(TR * d->sb_hidden);
     w.tc_rec = c.take<float>(4 * RH);
   }
+  memset(&w.fbtc, 0, sizeof(w.fbtc));
+  w.fbtc_mid = nullptr;
+  if (d->precision == FSN_PREC_TF32_TC && lstm_rec_tc_supported(d->fb_hidden, false)) {
+    lstm_tc_carve(c.base, c.off, BT, m.Fu > d->fb_hidden ? m.Fu : d->fb_hidden, d->fb_hidden, false, w.fbtc);
+    w.fbtc_mid = c.take<float>(BT * d->fb_hidden);
+  }
   w.bytes = c.off;
 }
 
@@ -215,7 +223,17 @@ extern "C" int fsn_improved_forward(const fsn_improved_desc* d, const fsn_improv
   // full band: norm (566) -> 2xLSTM + Linear (567)
   if ((rc = clip_stats_launch(w.magc, B, T, Fu, 0, w.fs, w.sums, st))) return rc;
   if ((rc = norm_scales_launch(w.sums, w.sums, B, (float)Fu * T, 1.f, w.inv1, nullptr, st, eps))) return rc;
-  if (fb_persistent_supported(Fu, Hf, Hf)) {
+  const bool fb_tc = w.fbtc_mid != nullptr;
+  if (fb_tc) {
+    // tensor cores: per layer one hoisted input-projection GEMM (tf32) + the persistent tcgen05 recurrence, Linear likewise
+    fsn_lstm_layer L0{wt->fb.w_ih[0], wt->fb.w_hh[0], wt->fb.b_ih[0], wt->fb.b_hh[0]};
+    fsn_lstm_layer L1{wt->fb.w_ih[1], wt->fb.w_hh[1], wt->fb.b_ih[1], wt->fb.b_hh[1]};
+    if ((rc = lstm_layer_tc(L0, w.magc, (size_t)Fu, Fu, w.inv1, T, 0, B, T, Hf, false, w.fbtc, w.fbtc_mid, st))) return rc;
+    if ((rc = lstm_layer_tc(L1, w.fbtc_mid, (size_t)Hf, Hf, nullptr, 1, 0, B, T, Hf, false, w.fbtc, w.fb_h1all, st))) return rc;
+    if ((rc = linear_tc(w.fb_h1all, (size_t)Hf, Hf, wt->fb.fc_w, wt->fb.fc_b, Fu, d->fb_activation, w.fbT, (size_t)Fu,
+                        (size_t)B * T, false, w.fbtc, st)))
+      return rc;
+  } else if (fb_persistent_supported(Fu, Hf, Hf)) {
     for (int b0 = 0; b0 < B; b0 += 256) {
       const int nb = (B - b0 < 256) ? B - b0 : 256;
       if ((rc = fb_persistent_launch(&wt->fb, w.magc + (size_t)b0 * T * Fu, w.inv1 + b0, w.fb_pp,
@@ -244,7 +262,8 @@ extern "C" int fsn_improved_forward(const fsn_improved_desc* d, const fsn_improv
       if ((rc = lstm_step_launch(p, SEG0_DENSE, st))) return rc;
     }
   }
-  if ((rc = fc_gemm_launch(w.fb_h1all, wt->fb.fc_w, wt->fb.fc_b, w.fbT, B * T, Hf, Fu, d->fb_activation, st))) return rc;
+  if (!fb_tc && (rc = fc_gemm_launch(w.fb_h1all, wt->fb.fc_w, wt->fb.fc_b, w.fbT, B * T, Hf, Fu, d->fb_activation, st)))
+    return rc;
   // cRM, Nyquist row = 0 (572)
   if ((rc = check_cuda(cudaMemsetAsync(crm, 0, (size_t)2 * B * F * T * sizeof(float), st), "crm memset"))) return rc;
   // sub-band sections (408-447)
