@@ -48,7 +48,7 @@ struct Args {
   float* hall; size_t h_row, h_t;                             // hall[r*h_row + t*h_t + u]
   __half* state;                                              // [2 parity][PARTS][Rpad][Kp]
   unsigned int* barrier;                                      // one counter per group, 32 words apart
-  int R, T, H, Kp, Rpad, C, stages;
+  int R, T, H, Kp, Rpad, C, stages, fence_all;
 };
 
 __device__ __forceinline__ void tc_mma1_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -268,14 +268,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_rec_tc_kernel(const __grid_c
         }
       }
       if (p + 1 < T) {
-        // publish h_p: every writer orders its own stores at gpu scope (and towards the async proxy, which is what
-        // reads them - the other CTAs' TMA loads), then the CTA-scope barrier, then one release by the arriving thread.
-        // (A single fence by the arriving thread after the barrier is NOT enough for the TMA readers: measured as
-        // stale-state errors of ~3e-4 on long sequences.)
-        __threadfence();
-        fence_proxy_async();
+        // publish h_p: CTA-scope barrier over the 128 writers, then ONE gpu-scope fence (cumulative over the writes
+        // observed through the barrier - the grid.sync pattern) + async-proxy fence + release by the arriving thread.
+        // FSN_REC_FENCE_ALL=1 (debug) makes every writer fence for itself.
+        if (a.fence_all) { __threadfence(); fence_proxy_async(); }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        if (threadIdx.x == 64) {
+          __threadfence();
+          fence_proxy_async();
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        }
       }
     }
   }
@@ -444,6 +446,7 @@ int lstm_rec_tc_launch(const float* w_hh, const float* b_ih, const float* b_hh, 
     a.hall = hall + (size_t)r0 * h_row; a.h_row = h_row; a.h_t = h_t;
     a.state = state; a.barrier = barrier;
     a.R = nr; a.T = T; a.H = H; a.Kp = Kp; a.Rpad = Rpad; a.C = C; a.stages = stages;
+    a.fence_all = getenv("FSN_REC_FENCE_ALL") != nullptr;
     void* params[] = {(void*)&tm, (void*)&a};
     if ((rc = check_cuda(cudaLaunchCooperativeKernel(kern, dim3(G * C), dim3(rec::NTHREADS), params, smem, st),
                          "lstm_rec_tc cooperative launch")))
