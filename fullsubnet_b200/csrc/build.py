@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["fsn_dsp.cu", "fsn_dsp_dft.cu", "fsn_lstm_simt.cu", "fsn_subband_tc.cu", "fsn_subband_tc2.cu", "fsn_fullband.cu", "fsn_lstm_rec_tc.cu", "fsn_fast_model.cu", "fsn_improved.cu", "fsn_fullband_baseline.cu", "fsn_train.cu", "fsn_mix.cu", "fsn_tgemm.cu", "fsn_model.cu"]
+SOURCES = ["fsn_dsp.cu", "fsn_dsp_dft.cu", "fsn_lstm_simt.cu", "fsn_subband_tc.cu", "fsn_subband_tc2.cu", "fsn_subband_tc4.cu", "fsn_fullband.cu", "fsn_lstm_rec_tc.cu", "fsn_fast_model.cu", "fsn_improved.cu", "fsn_fullband_baseline.cu", "fsn_train.cu", "fsn_mix.cu", "fsn_tgemm.cu", "fsn_model.cu"]
 LIB = os.path.join(HERE, "libfsn_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

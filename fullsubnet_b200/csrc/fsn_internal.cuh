@@ -142,6 +142,7 @@ struct SbTcArgs {
   int steps, shrink;      // pair kernel only: LSTM steps (0 = Tp) and time down-sampling of the gathered input (0/1 = none)
   bool pair;              // packed for / run by the CTA-pair kernel
   bool x3;                // pair kernel only: error-compensated variant (FSN_PREC_F16X3_TC image)
+  bool quad;              // packed for / run by the 6-CTA-cluster kernel (fsn_subband_tc4.cu)
   RowMap map;
 };
 size_t sb_tc_packed_bytes(const fsn_model_desc* d);
@@ -155,6 +156,11 @@ size_t sb_tc2_packed_bytes(bool x3 = false);
 int sb_tc2_pack(const fsn_model_desc* d, const fsn_seq_weights* sb, void* packed, cudaStream_t st);
 int sb_tc2_forward(const SbTcArgs& a, cudaStream_t st);
 int sb_tc2_pack_raw(const fsn_seq_weights* sb, int Ksb, int fc_out, void* packed, cudaStream_t st, bool x3 = false);
+// cluster (three pairs = 6 CTAs, N = 128) variant (fsn_subband_tc4.cu); experimental, single fp16 pass, H = 384; FSN_TC_CLUSTER4=1
+bool sb_tc4_supported(const fsn_model_desc* d);
+size_t sb_tc4_packed_bytes();
+int sb_tc4_pack(const fsn_model_desc* d, const fsn_seq_weights* sb, void* packed, cudaStream_t st);
+int sb_tc4_forward(const SbTcArgs& a, cudaStream_t st);
 bool sb_tc2_enabled();  // H = 384 stacks may use the pair kernel (FSN_TC_PAIR != 0)
 
 }  // namespace fsn

@@ -223,6 +223,7 @@ static int model_core(const fsn_model_desc* d, const fsn_seq_weights* fb, const 
     a.B = B; a.F = F; a.Tp = Tp; a.la = d->look_ahead; a.Ns = d->sb_num_neighbors; a.Nf = d->fb_num_neighbors;
     a.H = Hs; a.act = d->sb_activation; a.map = map; a.pair = sb_tc2_supported(d); a.x3 = d->precision == FSN_PREC_F16X3_TC;
     a.unit_scale = cum ? w.cum2 : nullptr;
+    a.quad = sb_tc4_supported(d);
     rc = sb_tc_forward(a, st);
     prof_mark(3, st);
     return rc;

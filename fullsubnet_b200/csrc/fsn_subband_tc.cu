@@ -685,6 +685,7 @@ bool sb_tc_supported(const fsn_model_desc* d) {
 
 size_t sb_tc_packed_bytes(const fsn_model_desc* d) {
   if (!sb_tc_supported(d)) return 0;
+  if (sb_tc4_supported(d)) return sb_tc4_packed_bytes();
   if (sb_tc2_supported(d)) return sb_tc2_packed_bytes(d->precision == FSN_PREC_F16X3_TC);
   const int Ksb = (2 * d->sb_num_neighbors + 1) + (2 * d->fb_num_neighbors + 1);
   return tc::packed_layout(d->sb_hidden, Ksb).bytes;
@@ -693,6 +694,7 @@ size_t sb_tc_packed_bytes(const fsn_model_desc* d) {
 int sb_tc_pack(const fsn_model_desc* d, const fsn_seq_weights* sb, void* packed, cudaStream_t st) {
   FSN_REQUIRE(sb_tc_supported(d), FSN_ERR_UNSUPPORTED,
               "FSN_PREC_F16_TC needs sb_hidden in {128,256,384} and sub-band input width <= 32");
+  if (sb_tc4_supported(d)) return sb_tc4_pack(d, sb, packed, st);
   if (sb_tc2_supported(d)) return sb_tc2_pack(d, sb, packed, st);
   const int Ksb = (2 * d->sb_num_neighbors + 1) + (2 * d->fb_num_neighbors + 1);
   tc::pack_kernel<<<148 * 4, 256, 0, st>>>(sb->w_ih[0], sb->w_hh[0], sb->w_ih[1], sb->w_hh[1], sb->b_ih[0],
@@ -703,6 +705,7 @@ int sb_tc_pack(const fsn_model_desc* d, const fsn_seq_weights* sb, void* packed,
 }
 
 int sb_tc_forward(const SbTcArgs& s, cudaStream_t st) {
+  if (s.quad) return sb_tc4_forward(s, st);
   if (s.pair) return sb_tc2_forward(s, st);
   tc::KArgs a;
   a.packed = (const uint8_t*)s.packed;
