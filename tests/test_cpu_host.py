@@ -222,6 +222,18 @@ def test_c_abi_argument_validation_without_gpu():
     L.n = _lib.MAX_PARAM_TENSORS + 1
     assert lib.fsn_clip_adam(C.byref(L), 10.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, 1, None, None, 0, None) == _lib.FSN_ERR_SHAPE
     assert lib.fsn_peak_normalize_int16(None, 0, 10, 1.0, None, None) == _lib.FSN_ERR_SHAPE
+    # entry points added in round 2
+    assert lib.fsn_si_sdr(None, None, 0, 100, None, None) == _lib.FSN_ERR_SHAPE
+    assert lib.fsn_snr_mix(None, None, None, None, -25.0, 1e-6, 4, 0, None, None, None) == _lib.FSN_ERR_SHAPE
+    assert lib.fsn_rir_convolve(None, None, None, 2, 100, 0, None, None) == _lib.FSN_ERR_SHAPE
+    d = _lib.ModelDesc(num_freqs=257, look_ahead=2, fb_num_neighbors=0, sb_num_neighbors=15, fb_hidden=512, sb_hidden=384,
+                       fb_activation=1, sb_activation=0, norm_type=0, num_groups_in_drop_band=1, precision=3, cell_type=0)
+    assert lib.fsn_enhance_pcm(C.byref(d), None, None, None, None, 2, 4000, 512, 256, 512, None, None, 1.0, None, 0, None) \
+        == _lib.FSN_ERR_SHAPE  # output buffers missing
+    assert lib.fsn_enhance_workspace_bytes(C.byref(d), 2, 4000, 512, 256) > 0
+    d.cell_type = 1  # GRU with a tensor-core precision
+    assert lib.fsn_enhance_workspace_bytes(C.byref(d), 2, 4000, 512, 256) == 0
+    assert lib.fsn_last_error_code() == _lib.FSN_ERR_UNSUPPORTED and b"GRU" in lib.fsn_last_error()
     with pytest.raises(AssertionError):
         _lib.check(_lib.FSN_ERR_SHAPE)
     with pytest.raises(NotImplementedError):

@@ -395,3 +395,37 @@ def test_cumulative_norm_training_matches_reference(golden, dev, prec):
     assert abs(float(loss.detach()) - float(ref_loss)) < 1e-5 * float(ref_loss)
     for k, p in mf.named_parameters():
         assert rel_l2(p.grad.cpu(), ref_grads[k]) < 2e-4, k
+
+
+def test_packed_weight_cache_follows_fused_optimizer_steps(dev):
+    """FusedClipAdam writes parameters through raw pointers; the packed tensor-core image of the sub-band
+    weights is cached on (data_ptr, _version), so the optimiser must bump the versions - otherwise a train -> infer flow in
+    one process would enhance with stale sub-band weights.  infer, step, infer again: the tensor-core result must follow
+    the fp32 kernels (which read the live parameters) both times, and must have changed."""
+    from fullsubnet_b200.loss import mse_loss
+    from fullsubnet_b200.optim import FusedClipAdam
+    from oracle import fullsubnet_oracle as O
+    from oracle import train_oracle as TO
+    args = dict(O.DEFAULT_MODEL_ARGS, weight_init=False)
+    m = build(args, O.make_state_dict(seed=0, args=args, sb_fc_gain=40.0), dev, "fp32")
+    y = O.make_noisy(2, 4000, seed=3, speechlike=True).to(dev)
+
+    def both():
+        m.eval()
+        m.precision = "auto"
+        tc = m.enhance(y, return_crm=True)[1]
+        m.precision = "fp32"
+        ref = m.enhance(y, return_crm=True)[1]
+        m.train()
+        return tc, ref
+    tc0, ref0 = both()
+    assert rel_max(tc0.cpu(), ref0.cpu()) < 5e-5
+    opt = FusedClipAdam(m.parameters(), lr=5e-2, max_norm=10.0)  # a large step: the weights really move
+    ny, cl = O.make_noisy(3, 2048, seed=5, speechlike=True), 0.5 * O.make_noisy(3, 2048, seed=6)
+    nm, cirm = TO.targets(ny, cl, 2)
+    loss = mse_loss()(cirm.to(dev), m(nm.unsqueeze(1).to(dev)).permute(0, 2, 3, 1))
+    loss.backward()
+    opt.step()
+    tc1, ref1 = both()
+    assert rel_max(ref1.cpu(), ref0.cpu()) > 1e-2          # the update changed the model
+    assert rel_max(tc1.cpu(), ref1.cpu()) < 5e-5            # and the packed image was rebuilt from the new weights
