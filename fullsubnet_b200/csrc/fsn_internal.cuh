@@ -59,6 +59,13 @@ bool tgemm_supported(const float* A, size_t lda, const float* Bm, size_t ldb, in
 int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float* C, size_t ldc, int M, int N, int K,
                  bool accumulate, float* scratch, size_t scratch_floats, cudaStream_t st);
 
+// weight-gradient GEMMs C[M,N] (+)= A^T B over a long K with block-tiled K-major operand copies (fsn_tgemm.cu)
+size_t tgemm_blocked_floats(size_t K, int M);
+int transpose_blocked_launch(const float* in, size_t K, int M, size_t ld, float* out, cudaStream_t st);
+bool tgemm_blocked_enabled();
+int tgemm_blocked_launch(const float* Ablk, int nkb_a, int a_kb0, const float* Bblk, int nkb_b, int b_kb0, float* C, size_t ldc,
+                         int M, int N, int K, bool accumulate, float* scratch, size_t scratch_floats, cudaStream_t st);
+
 // one LSTM layer over all steps on the tf32 tensor-core path (fsn_train.cu): input projection of all steps hoisted
 // into one GEMM, then per step the recurrent GEMM into `rec` [R,4H] and the fused cell kernel.  G [Tp,R,4H]
 // (post-activation gates), C, H [Tp,R,H] receive every step.  X [Tp,R,K0] contiguous.

@@ -35,6 +35,9 @@ template <int BN> struct Cfg {
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// block-tiled operand addressing of tgemm_tma_kernel (weight-gradient GEMMs, see tgemm_blocked_launch)
+struct BlockedOps { int on, a_nkb, b_nkb, a_kb0, b_kb0; };
+
 struct Bars {
   uint64_t full[8];
   uint64_t empty[8];
@@ -197,7 +200,7 @@ template <int BN>
 __global__ void __launch_bounds__(160, Cfg<BN>::MIN_CTAS)
 tgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmB2, float* __restrict__ C, size_t ldc, int M, int N, int K,
-                 int k_per_split, int accumulate, size_t split_stride) {
+                 int k_per_split, int accumulate, size_t split_stride, BlockedOps bo) {
   using CF = Cfg<BN>;
   constexpr int STAGES = CF::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -230,9 +233,19 @@ tgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
           uint8_t* sa = smem + s * CF::STAGE_BYTES;
           mbar_expect_tx(&bars.full[s], CF::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, kb + i * BK, m0, &bars.full[s]);
-          tma_load_2d(sa + A_BYTES, &tmB, kb + i * BK, n0, &bars.full[s]);
-          if (BN > 256) tma_load_2d(sa + A_BYTES + 256 * 128, &tmB2, kb + i * BK, n0 + 256, &bars.full[s]);
+          if (bo.on) {
+            // block-tiled operands: tile (128 rows, k block of 32) = 16 contiguous KB, see tgemm_blocked_launch
+            const int kblk = (kb >> 5) + i;
+            tma_load_2d(sa, &tmA, 0, (blockIdx.x * bo.a_nkb + bo.a_kb0 + kblk) * 128, &bars.full[s]);
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j)
+              tma_load_2d(sa + A_BYTES + j * 128 * 128, &tmB, 0, ((blockIdx.y * (BN / 128) + j) * bo.b_nkb + bo.b_kb0 + kblk) * 128,
+                          &bars.full[s]);
+          } else {
+            tma_load_2d(sa, &tmA, kb + i * BK, m0, &bars.full[s]);
+            tma_load_2d(sa + A_BYTES, &tmB, kb + i * BK, n0, &bars.full[s]);
+            if (BN > 256) tma_load_2d(sa + A_BYTES + 256 * 128, &tmB2, kb + i * BK, n0 + 256, &bars.full[s]);
+          }
         }
         __syncwarp();
       }
@@ -346,13 +359,13 @@ int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float*
     }
     if (BN == 384)
       tg::tgemm_tma_kernel<384><<<grid, 160, tg::Cfg<384>::SMEM, st>>>(tmA, tmB, tmB2, dst, ldd, M, N, K, kps, acc,
-                                                                       (size_t)M * N);
+                                                                       (size_t)M * N, tg::BlockedOps{0, 0, 0, 0, 0});
     else if (BN == 256)
       tg::tgemm_tma_kernel<256><<<grid, 160, tg::Cfg<256>::SMEM, st>>>(tmA, tmB, tmB2, dst, ldd, M, N, K, kps, acc,
-                                                                       (size_t)M * N);
+                                                                       (size_t)M * N, tg::BlockedOps{0, 0, 0, 0, 0});
     else
       tg::tgemm_tma_kernel<128><<<grid, 160, tg::Cfg<128>::SMEM, st>>>(tmA, tmB, tmB2, dst, ldd, M, N, K, kps, acc,
-                                                                       (size_t)M * N);
+                                                                       (size_t)M * N, tg::BlockedOps{0, 0, 0, 0, 0});
     FSN_CHECK_LAUNCH("tgemm_tma_kernel");
     if (S > 1) return splitk_reduce_launch(scratch, S, M, N, C, ldc, accumulate, st);
     return FSN_OK;
@@ -386,6 +399,97 @@ int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float*
   return FSN_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight-gradient GEMMs  C[M,N] = A^T B  with A [K,M] and B [K,N] row-major (dW = dG^T X, K = T'R up to 1.5 M).
+// The tensor-core kernel wants K-major operands; a plain transposed copy [M,K] has a row pitch of K floats (6 MB), so
+// every 128-row TMA box touches 128 DRAM pages and the GEMM ran at 15 % of the HBM bandwidth.  Here the transposed copy
+// is BLOCK-TILED: tile (128 rows of M, k block of 32) = 16 contiguous KB at ((mt * nkb + kb) * 128 + row) * 32 + kk
+// (zero padded in M and K), viewed by TMA as a 2-D array [rows, 32] - one box = one contiguous burst.
+namespace tg {
+__global__ void transpose_blocked_kernel(const float* __restrict__ in, size_t K, int M, size_t ld, int nkb, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const size_t k0 = (size_t)blockIdx.x * 32;   // k block
+  const int m0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const size_t k = k0 + i;
+    const int m = m0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && m < M) ? in[k * ld + m] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int m = m0 + i;  // padded rows (m >= M) are written as zeros
+    out[(((size_t)(m >> 7) * nkb + blockIdx.x) * 128 + (m & 127)) * 32 + threadIdx.x] = tile[threadIdx.x][i];
+  }
+}
+}  // namespace tg
+
+size_t tgemm_blocked_floats(size_t K, int M) { return (size_t)cdiv(M, 128) * 128 * ((K + 31) / 32) * 32; }
+
+// in [K, M] (row stride ld) -> block-tiled transposed copy (tgemm_blocked_floats(K, M) floats)
+int transpose_blocked_launch(const float* in, size_t K, int M, size_t ld, float* out, cudaStream_t st) {
+  const int nkb = (int)((K + 31) / 32);
+  dim3 grid((unsigned)nkb, (unsigned)(cdiv(M, 128) * 4));
+  tg::transpose_blocked_kernel<<<grid, dim3(32, 8), 0, st>>>(in, K, M, ld, nkb, out);
+  FSN_CHECK_LAUNCH("transpose_blocked_kernel");
+  return FSN_OK;
+}
+
+bool tgemm_blocked_enabled() {
+  static const bool on = getenv("FSN_TGEMM_BLOCKED") == nullptr || atoi(getenv("FSN_TGEMM_BLOCKED")) != 0;
+  return on && tmap_encoder() != nullptr;
+}
+
+// C[M,N] (+)= A^T B over K, operands block-tiled (transpose_blocked_launch) with nkb_a / nkb_b k blocks per tile row;
+// a_kb0 / b_kb0: first k block of each operand (lets dW_hh pair dG[1:] with H[:-1])
+int tgemm_blocked_launch(const float* Ablk, int nkb_a, int a_kb0, const float* Bblk, int nkb_b, int b_kb0, float* C, size_t ldc,
+                         int M, int N, int K, bool accumulate, float* scratch, size_t scratch_floats, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return FSN_OK;
+  PFN_cuTensorMapEncodeTiled_v12000 fn = tmap_encoder();
+  FSN_REQUIRE(fn, FSN_ERR_UNSUPPORTED, "tgemm_blocked: cuTensorMapEncodeTiled unavailable");
+  int BN = (N > 256 && N <= 384) ? 384 : ((N > 128 && N <= 256) || N % 256 == 0 ? 256 : 128);
+  const int tiles = cdiv(M, tg::BM) * cdiv(N, BN);
+  int S = 1;
+  if (scratch && K >= 8192 && tiles < 296) {
+    const int slots = 148 * (BN == 128 ? 2 : 1);
+    double best = 1e30;
+    for (int s = 1; s <= 64 && s <= cdiv(K, 2048); ++s) {
+      if ((size_t)s * M * N > scratch_floats) break;
+      const double cost = (double)cdiv(tiles * s, slots) / s + 1e-4 * s;
+      if (cost < best) { best = cost; S = s; }
+    }
+  }
+  const int kps = cdiv(cdiv(K, S), tg::BK) * tg::BK;
+  S = cdiv(K, kps);
+  dim3 grid(cdiv(M, tg::BM), cdiv(N, BN), S);
+  float* dst = S > 1 ? scratch : C;
+  const size_t ldd = S > 1 ? (size_t)N : ldc;
+  const int acc = (S > 1) ? 0 : (accumulate ? 1 : 0);
+  CUtensorMap tmA, tmB;
+  cuuint64_t gstr[1] = {128};
+  cuuint32_t box[2] = {32, 128}, estr[2] = {1, 1};
+  cuuint64_t gA[2] = {32, (cuuint64_t)cdiv(M, 128) * 128 * (cuuint64_t)nkb_a};
+  cuuint64_t gB[2] = {32, (cuuint64_t)cdiv(N, 128) * 128 * (cuuint64_t)nkb_b};  // tiles past it: zero fill
+  FSN_REQUIRE(fn(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)Ablk, gA, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
+                  fn(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)Bblk, gB, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS,
+              FSN_ERR_CUDA, "tgemm_blocked: tensor-map encoding failed");
+  int rc;
+  if ((rc = check_cuda(cudaFuncSetAttribute(tg::tgemm_tma_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::Cfg<384>::SMEM), "tgemm smem attr"))) return rc;
+  if ((rc = check_cuda(cudaFuncSetAttribute(tg::tgemm_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::Cfg<256>::SMEM), "tgemm smem attr"))) return rc;
+  if ((rc = check_cuda(cudaFuncSetAttribute(tg::tgemm_tma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::Cfg<128>::SMEM), "tgemm smem attr"))) return rc;
+  const tg::BlockedOps bo{1, nkb_a, nkb_b, a_kb0, b_kb0};
+  if (BN == 384)
+    tg::tgemm_tma_kernel<384><<<grid, 160, tg::Cfg<384>::SMEM, st>>>(tmA, tmB, tmB, dst, ldd, M, N, K, kps, acc, (size_t)M * N, bo);
+  else if (BN == 256)
+    tg::tgemm_tma_kernel<256><<<grid, 160, tg::Cfg<256>::SMEM, st>>>(tmA, tmB, tmB, dst, ldd, M, N, K, kps, acc, (size_t)M * N, bo);
+  else
+    tg::tgemm_tma_kernel<128><<<grid, 160, tg::Cfg<128>::SMEM, st>>>(tmA, tmB, tmB, dst, ldd, M, N, K, kps, acc, (size_t)M * N, bo);
+  FSN_CHECK_LAUNCH("tgemm_tma_kernel");
+  if (S > 1) return splitk_reduce_launch(scratch, S, M, N, C, ldc, accumulate, st);
+  return FSN_OK;
+}
 }  // namespace fsn
 
 // debug / unit-test entry point (tests/test_gpu_train.py): C[M,N] (+)= A[M,K] B[N,K]^T on the tcgen05 path
@@ -394,4 +498,22 @@ extern "C" int fsn_debug_tgemm(const float* A, int64_t lda, const float* B, int6
                                fsn_stream_t stream) {
   return fsn::tgemm_launch(A, (size_t)lda, B, (size_t)ldb, C, (size_t)ldc, M, N, K, accumulate != 0, scratch,
                            (size_t)scratch_floats, (cudaStream_t)stream);
+}
+
+// unit-test hook: C[M,N] = A^T B for row-major A [K,M], B [K,N] through the block-tiled transposes + tgemm_blocked_launch
+// (a_k0 / b_k0: first k row of each operand, multiples of 32); scratch: tgemm_blocked_floats(K, M) + (K, N padded to the
+// tile) floats for the copies, then split-K space
+extern "C" int fsn_debug_tgemm_blocked(const float* A, const float* B, float* C, int M, int N, int K, int a_k0, int b_k0,
+                                       float* scratch, int64_t scratch_floats, fsn_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t Ka = (size_t)K + a_k0, Kb = (size_t)K + b_k0;
+  const size_t fa = fsn::tgemm_blocked_floats(Ka, M), fb = fsn::tgemm_blocked_floats(Kb, N);
+  FSN_REQUIRE((a_k0 & 31) == 0 && (b_k0 & 31) == 0 && scratch && (size_t)scratch_floats >= fa + fb, FSN_ERR_SHAPE,
+              "tgemm_blocked hook: bad offsets or scratch");
+  float *Ab = scratch, *Bb = scratch + fa;
+  int rc;
+  if ((rc = fsn::transpose_blocked_launch(A, Ka, M, (size_t)M, Ab, st))) return rc;
+  if ((rc = fsn::transpose_blocked_launch(B, Kb, N, (size_t)N, Bb, st))) return rc;
+  return fsn::tgemm_blocked_launch(Ab, (int)((Ka + 31) / 32), a_k0 / 32, Bb, (int)((Kb + 31) / 32), b_k0 / 32, C, (size_t)N, M, N, K,
+                                   false, scratch + fa + fb, (size_t)scratch_floats - fa - fb, st);
 }

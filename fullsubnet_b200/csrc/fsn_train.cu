@@ -518,9 +518,11 @@ static void carve_train(const fsn_model_desc* d, const Dims& m, void* base, Trai
       w.fb_whhT[l] = c.take(Hf * 4 * Hf);
     }
     w.fb_wihT1 = c.take(Hf * 4 * Hf);
-    const size_t g_sb = Tp * R * 4 * Hs, g_fb = Tp * B * 4 * Hf;
+    // K-major (block-tiled, zero padded: tgemm_blocked_floats) copies of dG and of the layer input / hidden states
+    const size_t g_sb = tgemm_blocked_floats(Tp * R, 4 * (int)Hs), g_fb = tgemm_blocked_floats(Tp * B, 4 * (int)Hf);
     w.gT = c.take(g_sb > g_fb ? g_sb : g_fb);
-    size_t x_sb = Tp * R * (Hs > (size_t)m.Ksb ? Hs : (size_t)m.Ksb), x_fb = Tp * B * (Hf > F ? Hf : F);
+    const size_t x_sb = tgemm_blocked_floats(Tp * R, Hs > (size_t)m.Ksb ? (int)Hs : m.Ksb),
+                 x_fb = tgemm_blocked_floats(Tp * B, Hf > F ? (int)Hf : (int)F);
     w.xT = c.take(x_sb > x_fb ? x_sb : x_fb);
     w.rec = c.take(4 * RH);
   }
@@ -631,6 +633,29 @@ static int layer_weight_grads(const LayerBwd& L, int Tp, const float* X, float* 
   const int H4 = 4 * L.H;
   const int rows = Tp * L.R;
   int rc;
+  if (L.w_hhT && tgemm_blocked_enabled()) {
+    // tensor-core path, block-tiled K-major copies (one contiguous 16 KB burst per TMA box instead of 128 rows with a
+    // pitch of `rows` floats): dW_ih = dG^T X, dW_hh = dG[1:]^T H[:-1]
+    const int nkb = (rows + 31) / 32;
+    if ((rc = transpose_blocked_launch(L.s.G, (size_t)rows, H4, (size_t)H4, w.gT, st))) return rc;
+    if ((rc = transpose_blocked_launch(X, (size_t)rows, L.K0, (size_t)L.K0, w.xT, st))) return rc;
+    if ((rc = tgemm_blocked_launch(w.gT, nkb, 0, w.xT, nkb, 0, g_w_ih, L.K0, H4, L.K0, rows, false, w.splitk, SPLITK_SCRATCH_FLOATS, st)))
+      return rc;
+    if (Tp > 1) {
+      if ((rc = transpose_blocked_launch(L.s.H, (size_t)rows, L.H, (size_t)L.H, w.xT, st))) return rc;
+      int a_kb0 = L.R / 32, a_nkb = nkb;
+      if (L.R & 31) {  // step offset not on a k block: a second copy that starts at step 1
+        a_kb0 = 0; a_nkb = (rows - L.R + 31) / 32;
+        if ((rc = transpose_blocked_launch(L.s.G + (size_t)L.R * H4, (size_t)(rows - L.R), H4, (size_t)H4, w.gT, st))) return rc;
+      }
+      if ((rc = tgemm_blocked_launch(w.gT, a_nkb, a_kb0, w.xT, nkb, 0, g_w_hh, L.H, H4, L.H, rows - L.R, false, w.splitk,
+                                     SPLITK_SCRATCH_FLOATS, st)))
+        return rc;
+    } else if ((rc = check_cuda(cudaMemsetAsync(g_w_hh, 0, (size_t)H4 * L.H * sizeof(float), st), "memset"))) {
+      return rc;
+    }
+    return colsum_launch(L.s.G, (size_t)rows, H4, H4, g_b_ih, g_b_hh, w.colsum, st);
+  }
   if (L.w_hhT && (L.R & 3) == 0) {
     // tensor-core path: K-major operands = transposed copies dG^T [4H, rows], X^T [K0, rows], H^T [H, rows]
     if ((rc = transpose_launch(L.s.G, (size_t)rows, H4, w.gT, st))) return rc;

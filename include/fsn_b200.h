@@ -356,6 +356,13 @@ int fsn_debug_reflect_count(int r, int F, int N);
 int fsn_debug_tgemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
                     int K, int accumulate, float* scratch, int64_t scratch_floats, fsn_stream_t stream);
 
+/* unit-test hook for the weight-gradient GEMMs of the training step (dW = dG^T X, torch autograd of nn.LSTM):
+ * C[M,N] = A[a_k0:a_k0+K, :M]^T B[b_k0:b_k0+K, :N] for row-major A [a_k0+K, M], B [b_k0+K, N]; both operands are first
+ * copied into the block-tiled K-major layout the TMA loads stream (a_k0, b_k0 multiples of 32); scratch holds the two
+ * copies (rounded up to 128 x 32 tiles) followed by split-K space */
+int fsn_debug_tgemm_blocked(const float* A, const float* B, float* C, int M, int N, int K, int a_k0, int b_k0,
+                            float* scratch, int64_t scratch_floats, fsn_stream_t stream);
+
 /* unit-test hooks for the tensor-core LSTM layer of the full-band stacks (fsn_lstm_rec_tc.cu;
  * audio_zen/model/module/sequence_model.py:52-58,117): hall[r,t,:] of nn.LSTM(K -> H, 1 layer) over x [R,T,K]
  * (hoisted input-projection GEMM + persistent tcgen05 recurrence), and out = act(x W^T + b) for x [rows,K], W [N,K];

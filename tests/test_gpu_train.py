@@ -212,6 +212,27 @@ def test_tf32_tensor_core_gemm_matches_truncated_reference(dev):
         assert torch.equal(Cc[:, N:], C0[:, N:])
 
 
+def test_blocked_weight_gradient_gemm_matches_truncated_reference(dev):
+    """fsn_debug_tgemm_blocked: C = A^T B over a long K through the block-tiled K-major copies (the dW_ih / dW_hh GEMMs of
+    the training step; the k offsets are the one-step shift of dW_hh) == fp64 GEMM of the tf32-truncated operands."""
+    from fullsubnet_b200 import _lib
+    lib = _lib.load()
+
+    def trunc(x):
+        return (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    torch.manual_seed(2)
+    for (M, N, K, a0, b0) in ((128, 128, 64, 0, 0), (1536, 33, 50000, 0, 0), (1536, 384, 70001, 64, 0), (2048, 257, 9000, 0, 0),
+                              (2048, 512, 40010, 32, 0), (200, 130, 4100, 0, 96)):
+        A, B = torch.randn(K + a0, M, device=dev), torch.randn(K + b0, N, device=dev)
+        Cc = torch.full((M, N), float("nan"), device=dev)
+        scratch = torch.empty((32 << 20) + (M + 128 + N + 128) * (K + 128), device=dev)
+        _lib.check(lib.fsn_debug_tgemm_blocked(A.data_ptr(), B.data_ptr(), Cc.data_ptr(), M, N, K, a0, b0, scratch.data_ptr(),
+                                               scratch.numel(), torch.cuda.current_stream().cuda_stream))
+        ref = trunc(A[a0:]).double().T @ trunc(B[b0:]).double()
+        err = ((Cc.double() - ref).abs().max() / ref.abs().max()).item()
+        assert err < 1e-4, (M, N, K, a0, b0, err)
+
+
 def test_reference_trainer_flow_ddp_autocast_gradscaler(golden, dev):
     """The reference's own optimisation flow (fullsubnet/trainer.py:56-69, base_trainer.py:32,46) on the drop-in Model:
     DistributedDataParallel (NCCL, world 1) + autocast + GradScaler + unscale_ + clip_grad_norm_ + torch.optim.Adam,
