@@ -61,7 +61,8 @@ int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float*
 
 // weight-gradient GEMMs C[M,N] (+)= A^T B over a long K with block-tiled K-major operand copies (fsn_tgemm.cu)
 size_t tgemm_blocked_floats(size_t K, int M);
-int transpose_blocked_launch(const float* in, size_t K, int M, size_t ld, float* out, cudaStream_t st);
+int transpose_blocked_launch(const float* in, size_t K, int M, size_t ld, float* out, cudaStream_t st, float* colsum_part,
+                             int max_slabs, int* slabs);
 bool tgemm_blocked_enabled();
 int tgemm_blocked_launch(const float* Ablk, int nkb_a, int a_kb0, const float* Bblk, int nkb_b, int b_kb0, float* C, size_t ldc,
                          int M, int N, int K, bool accumulate, float* scratch, size_t scratch_floats, cudaStream_t st);
@@ -71,7 +72,7 @@ int tgemm_blocked_launch(const float* Ablk, int nkb_a, int a_kb0, const float* B
 // (post-activation gates), C, H [Tp,R,H] receive every step.  X [Tp,R,K0] contiguous.
 struct LayerSave { float *G, *C, *H; };
 int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R, int K0, int H, int Tp,
-                          const LayerSave& s, float* rec, cudaStream_t st);
+                          const LayerSave& s, float* rec, cudaStream_t st, float* splitk = nullptr, size_t splitk_floats = 0);
 
 // shapes of one Model.forward call (fsn_model.cu)
 struct Dims {

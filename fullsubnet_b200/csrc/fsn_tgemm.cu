@@ -317,6 +317,14 @@ int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float*
   FSN_REQUIRE(tgemm_supported(A, lda, Bm, ldb, K), FSN_ERR_UNSUPPORTED, "tgemm: operands must be 16-byte aligned rows");
   static const int force_bn = getenv("FSN_TGEMM_BN") ? atoi(getenv("FSN_TGEMM_BN")) : 0;
   int BN = force_bn ? force_bn : ((N >= 256 && N % 256 == 0) ? 256 : 128);
+  // a handful of tiles (per-step GEMMs of the full-band stack, 64 rows): narrow tiles + split-K so that the weight
+  // matrix is streamed by ~64 CTAs instead of 2-8
+  const bool few = scratch && K < 8192 && cdiv(M, tg::BM) * cdiv(N, 128) <= 32;
+  if (few && !force_bn) BN = 128;
+  // short K, many tiles (hoisted input projections: output-write bound): 128-wide tiles, two CTAs per SM, so one CTA's
+  // epilogue overlaps the other's main loop (measured 1081 -> 945 us at K = 384, 778 -> 522 us at K = 32 per 195 k rows)
+  static const int smallk_bn = getenv("FSN_TGEMM_SMALLK_BN") ? atoi(getenv("FSN_TGEMM_SMALLK_BN")) : 128;
+  if (!force_bn && K <= 512 && BN == 256 && cdiv(M, tg::BM) >= 1024) BN = smallk_bn == 256 ? 256 : 128;
   // long-K, narrow output (weight gradients): the whole N extent in one CTA so the big A operand is read exactly once
   static const bool wide = getenv("FSN_TGEMM_NO384") == nullptr;
   if (!force_bn && wide && tmap_encoder() && scratch && K >= 65536 && N > 256 && N <= 384) BN = 384;
@@ -331,6 +339,12 @@ int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float*
       const double cost = (double)cdiv(tiles * s, slots) / s + 1e-4 * s;
       if (cost < best) { best = cost; S = s; }
     }
+  }
+  if (few && K >= 256) {
+    S = 64 / tiles;
+    if (S > K / 128) S = K / 128;
+    while (S > 1 && (size_t)S * M * N > scratch_floats) --S;
+    if (S < 1) S = 1;
   }
   const int kps = cdiv(cdiv(K, S), tg::BK) * tg::BK;
   S = cdiv(K, kps);
@@ -407,30 +421,60 @@ int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float*
 // is BLOCK-TILED: tile (128 rows of M, k block of 32) = 16 contiguous KB at ((mt * nkb + kb) * 128 + row) * 32 + kk
 // (zero padded in M and K), viewed by TMA as a 2-D array [rows, 32] - one box = one contiguous burst.
 namespace tg {
-__global__ void transpose_blocked_kernel(const float* __restrict__ in, size_t K, int M, size_t ld, int nkb, float* __restrict__ out) {
-  __shared__ float tile[32][33];
-  const size_t k0 = (size_t)blockIdx.x * 32;   // k block
-  const int m0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const size_t k = k0 + i;
-    const int m = m0 + threadIdx.x;
-    tile[i][threadIdx.x] = (k < K && m < M) ? in[k * ld + m] : 0.f;
+// one CTA: m tile of 128 columns x `kb_per` k blocks of 32 rows; 512-byte row pieces in, one contiguous 16 KB tile out per
+// k block.  CTAs are numbered m tile fastest, so the CTAs resident together read whole rows.  colsum_part (nullable):
+// [gridDim.y][M] column sums of this CTA's rows (bias gradients = column sums of dG, free while the tile is in SMEM)
+__global__ void __launch_bounds__(256) transpose_blocked_kernel(const float* __restrict__ in, size_t K, int M, size_t ld, int nkb,
+                                                                 int kb_per, float* __restrict__ out, float* __restrict__ colsum_part) {
+  __shared__ float tile[32][129];
+  const int tid = threadIdx.x;
+  const int mt = blockIdx.x, m0 = mt * 128;
+  const int kb0 = blockIdx.y * kb_per;
+  const int kb1 = (kb0 + kb_per < nkb) ? kb0 + kb_per : nkb;
+  const int col = tid & 127, rsub = tid >> 7;
+  const bool col_ok = m0 + col < M;
+  float csum = 0.f;
+  for (int kb = kb0; kb < kb1; ++kb) {
+    const size_t k0 = (size_t)kb * 32;
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const size_t k = k0 + i * 2 + rsub;
+      v[i] = (col_ok && k < K) ? __ldcs(in + k * ld + m0 + col) : 0.f;
+    }
+    __syncthreads();  // the previous tile has been read out
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tile[i * 2 + rsub][col] = v[i];
+    __syncthreads();
+    float* o = out + ((size_t)mt * nkb + kb) * (128 * 32);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int e = i * 256 + tid;
+      o[e] = tile[e & 31][e >> 5];
+    }
+    if (colsum_part && tid < 128) {
+#pragma unroll
+      for (int r = 0; r < 32; ++r) csum += tile[r][tid];  // fixed order
+    }
   }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int m = m0 + i;  // padded rows (m >= M) are written as zeros
-    out[(((size_t)(m >> 7) * nkb + blockIdx.x) * 128 + (m & 127)) * 32 + threadIdx.x] = tile[threadIdx.x][i];
-  }
+  if (colsum_part && tid < 128 && m0 + tid < M) colsum_part[(size_t)blockIdx.y * M + m0 + tid] = csum;
 }
 }  // namespace tg
 
 size_t tgemm_blocked_floats(size_t K, int M) { return (size_t)cdiv(M, 128) * 128 * ((K + 31) / 32) * 32; }
 
-// in [K, M] (row stride ld) -> block-tiled transposed copy (tgemm_blocked_floats(K, M) floats)
-int transpose_blocked_launch(const float* in, size_t K, int M, size_t ld, float* out, cudaStream_t st) {
+// in [K, M] (row stride ld) -> block-tiled transposed copy (tgemm_blocked_floats(K, M) floats).  colsum_part (nullable,
+// >= max_slabs * M floats): per-slab column sums, *slabs receives the number of slabs written
+int transpose_blocked_launch(const float* in, size_t K, int M, size_t ld, float* out, cudaStream_t st, float* colsum_part,
+                             int max_slabs, int* slabs) {
   const int nkb = (int)((K + 31) / 32);
-  dim3 grid((unsigned)nkb, (unsigned)(cdiv(M, 128) * 4));
-  tg::transpose_blocked_kernel<<<grid, dim3(32, 8), 0, st>>>(in, K, M, ld, nkb, out);
+  int kb_per = 8;  // 256 rows per CTA
+  if (colsum_part && cdiv(nkb, kb_per) > max_slabs) kb_per = cdiv(nkb, max_slabs);
+  const int S = cdiv(nkb, kb_per);
+  if (slabs) *slabs = S;
+  dim3 grid((unsigned)cdiv(M, 128), (unsigned)S);
+  FSN_REQUIRE(S <= 65535, FSN_ERR_SHAPE, "transpose_blocked: K too long");
+  tg::transpose_blocked_kernel<<<grid, 256, 0, st>>>(in, K, M, ld, nkb, kb_per, out, colsum_part);
   FSN_CHECK_LAUNCH("transpose_blocked_kernel");
   return FSN_OK;
 }
@@ -512,8 +556,8 @@ extern "C" int fsn_debug_tgemm_blocked(const float* A, const float* B, float* C,
               "tgemm_blocked hook: bad offsets or scratch");
   float *Ab = scratch, *Bb = scratch + fa;
   int rc;
-  if ((rc = fsn::transpose_blocked_launch(A, Ka, M, (size_t)M, Ab, st))) return rc;
-  if ((rc = fsn::transpose_blocked_launch(B, Kb, N, (size_t)N, Bb, st))) return rc;
+  if ((rc = fsn::transpose_blocked_launch(A, Ka, M, (size_t)M, Ab, st, nullptr, 0, nullptr))) return rc;
+  if ((rc = fsn::transpose_blocked_launch(B, Kb, N, (size_t)N, Bb, st, nullptr, 0, nullptr))) return rc;
   return fsn::tgemm_blocked_launch(Ab, (int)((Ka + 31) / 32), a_k0 / 32, Bb, (int)((Kb + 31) / 32), b_k0 / 32, C, (size_t)N, M, N, K,
                                    false, scratch + fa + fb, (size_t)scratch_floats - fa - fb, st);
 }

@@ -160,6 +160,39 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, int S, int c
   if (out2) out2[c] = s;
 }
 static const int COLSUM_MAX_S = 512;
+
+// dW [O,H] = dout^T Hm for a Linear with a few outputs (the sub-band Linear, O = 2; model.py:129-135 backwards):
+// dout [rows,O], Hm [rows,H].  One pass over Hm: a CTA owns a slab of rows, a thread one column; part [S][O][H], then
+// the fixed-order sum of colsum_final_kernel over S slabs of O*H "columns".
+template <int O>
+__global__ void __launch_bounds__(128) small_out_wgrad_kernel(const float* __restrict__ dout, const float* __restrict__ Hm,
+                                                              size_t rows, int H, size_t rows_per, float* __restrict__ part) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  const size_t r0 = (size_t)blockIdx.y * rows_per;
+  const size_t r1 = (r0 + rows_per < rows) ? r0 + rows_per : rows;
+  float acc[O];
+#pragma unroll
+  for (int o = 0; o < O; ++o) acc[o] = 0.f;
+  if (c < H) {
+    size_t r = r0;
+    for (; r + 4 <= r1; r += 4) {
+      float h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __ldcs(Hm + (r + j) * H + c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int o = 0; o < O; ++o) acc[o] = fmaf(dout[(r + j) * O + o], h[j], acc[o]);
+    }
+    for (; r < r1; ++r) {
+      const float h = Hm[r * H + c];
+#pragma unroll
+      for (int o = 0; o < O; ++o) acc[o] = fmaf(dout[r * O + o], h, acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < O; ++o) part[((size_t)blockIdx.y * O + o) * H + c] = acc[o];
+  }
+}
 static int colsum_launch(const float* X, size_t rows, int cols, size_t ldx, float* out, float* out2, float* scratch,
                          cudaStream_t st) {
   int S = (int)((rows + 2047) / 2048);
@@ -561,7 +594,7 @@ static int layer_forward_save(const fsn_seq_weights* w, int l, const float* X, i
 // tensor-core variant: input projection of ALL steps as one GEMM into the gate buffer, then per step
 // G_t += h_{t-1} W_hh^T (tcgen05 tf32) and the fused cell kernel
 int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R, int K0, int H, int Tp,
-                                 const LayerSave& s, float* rec, cudaStream_t st) {
+                                 const LayerSave& s, float* rec, cudaStream_t st, float* splitk, size_t splitk_floats) {
   int rc;
   const int rows = Tp * R;
   if (tgemm_supported(X, K0, w->w_ih[l], K0, K0)) {
@@ -575,7 +608,7 @@ int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R
   for (int t = 0; t < Tp; ++t) {
     float* Gt = s.G + (size_t)t * R * 4 * H;
     if (t > 0)
-      if ((rc = tgemm_launch(s.H + (size_t)(t - 1) * R * H, H, w->w_hh[l], H, rec, 4 * H, R, 4 * H, H, false, nullptr, 0, st)))
+      if ((rc = tgemm_launch(s.H + (size_t)(t - 1) * R * H, H, w->w_hh[l], H, rec, 4 * H, R, 4 * H, H, false, splitk, splitk_floats, st)))
         return rc;
     lstm_cell_fwd_kernel<<<blocks, 256, 0, st>>>(Gt, t > 0 ? rec : nullptr, w->b_ih[l], w->b_hh[l],
                                                  t > 0 ? s.C + (size_t)(t - 1) * R * H : nullptr,
@@ -593,6 +626,7 @@ struct LayerBwd {
   int R, K0, H;
   float *dh_rec, *dc;
   const float *w_hhT, *w_ihT;  // tensor-core path: [H,4H] / [K0,4H] transposed copies (else nullptr)
+  float* splitk;               // split-K space of the per-step GEMMs (used when the layer has only a few tiles)
 };
 
 // step t of one layer: pointwise gate gradients, then dh_rec = dG W_hh and (optionally) dx = dG W_ih
@@ -615,12 +649,12 @@ static int layer_bwd_step(const LayerBwd& L, int t, int Tp, const float* dh_abov
   FSN_CHECK_LAUNCH("lstm_bwd_point_kernel");
   int rc;
   if (t > 0) {
-    if (L.w_hhT) rc = tgemm_launch(p.G, 4 * L.H, L.w_hhT, 4 * L.H, L.dh_rec, L.H, L.R, L.H, 4 * L.H, false, nullptr, 0, st);
+    if (L.w_hhT) rc = tgemm_launch(p.G, 4 * L.H, L.w_hhT, 4 * L.H, L.dh_rec, L.H, L.R, L.H, 4 * L.H, false, L.splitk, SPLITK_SCRATCH_FLOATS, st);
     else         rc = sgemm_launch(false, p.G, 4 * L.H, L.w_hh, L.H, L.dh_rec, L.H, L.R, L.H, 4 * L.H, false, nullptr, st);
     if (rc) return rc;
   }
   if (dx) {
-    if (L.w_ihT) rc = tgemm_launch(p.G, 4 * L.H, L.w_ihT, 4 * L.H, dx, L.K0, L.R, L.K0, 4 * L.H, false, nullptr, 0, st);
+    if (L.w_ihT) rc = tgemm_launch(p.G, 4 * L.H, L.w_ihT, 4 * L.H, dx, L.K0, L.R, L.K0, 4 * L.H, false, L.splitk, SPLITK_SCRATCH_FLOATS, st);
     else         rc = sgemm_launch(false, p.G, 4 * L.H, L.w_ih, L.K0, dx, L.K0, L.R, L.K0, 4 * L.H, false, nullptr, st);
     if (rc) return rc;
   }
@@ -637,16 +671,20 @@ static int layer_weight_grads(const LayerBwd& L, int Tp, const float* X, float* 
     // tensor-core path, block-tiled K-major copies (one contiguous 16 KB burst per TMA box instead of 128 rows with a
     // pitch of `rows` floats): dW_ih = dG^T X, dW_hh = dG[1:]^T H[:-1]
     const int nkb = (rows + 31) / 32;
-    if ((rc = transpose_blocked_launch(L.s.G, (size_t)rows, H4, (size_t)H4, w.gT, st))) return rc;
-    if ((rc = transpose_blocked_launch(X, (size_t)rows, L.K0, (size_t)L.K0, w.xT, st))) return rc;
+    int slabs = 0;  // bias gradients = column sums of dG, taken while its tiles pass through shared memory
+    if ((rc = transpose_blocked_launch(L.s.G, (size_t)rows, H4, (size_t)H4, w.gT, st, w.colsum, COLSUM_MAX_S, &slabs))) return rc;
+    colsum_final_kernel<<<cdiv(H4, 128), 128, 0, st>>>(w.colsum, slabs, H4, g_b_ih, g_b_hh);
+    FSN_CHECK_LAUNCH("colsum_final_kernel");
+    if ((rc = transpose_blocked_launch(X, (size_t)rows, L.K0, (size_t)L.K0, w.xT, st, nullptr, 0, nullptr))) return rc;
     if ((rc = tgemm_blocked_launch(w.gT, nkb, 0, w.xT, nkb, 0, g_w_ih, L.K0, H4, L.K0, rows, false, w.splitk, SPLITK_SCRATCH_FLOATS, st)))
       return rc;
     if (Tp > 1) {
-      if ((rc = transpose_blocked_launch(L.s.H, (size_t)rows, L.H, (size_t)L.H, w.xT, st))) return rc;
+      if ((rc = transpose_blocked_launch(L.s.H, (size_t)rows, L.H, (size_t)L.H, w.xT, st, nullptr, 0, nullptr))) return rc;
       int a_kb0 = L.R / 32, a_nkb = nkb;
       if (L.R & 31) {  // step offset not on a k block: a second copy that starts at step 1
         a_kb0 = 0; a_nkb = (rows - L.R + 31) / 32;
-        if ((rc = transpose_blocked_launch(L.s.G + (size_t)L.R * H4, (size_t)(rows - L.R), H4, (size_t)H4, w.gT, st))) return rc;
+        if ((rc = transpose_blocked_launch(L.s.G + (size_t)L.R * H4, (size_t)(rows - L.R), H4, (size_t)H4, w.gT, st, nullptr, 0, nullptr)))
+          return rc;
       }
       if ((rc = tgemm_blocked_launch(w.gT, a_nkb, a_kb0, w.xT, nkb, 0, g_w_hh, L.H, H4, L.H, rows - L.R, false, w.splitk,
                                      SPLITK_SCRATCH_FLOATS, st)))
@@ -654,7 +692,7 @@ static int layer_weight_grads(const LayerBwd& L, int Tp, const float* X, float* 
     } else if ((rc = check_cuda(cudaMemsetAsync(g_w_hh, 0, (size_t)H4 * L.H * sizeof(float), st), "memset"))) {
       return rc;
     }
-    return colsum_launch(L.s.G, (size_t)rows, H4, H4, g_b_ih, g_b_hh, w.colsum, st);
+    return FSN_OK;
   }
   if (L.w_hhT && (L.R & 3) == 0) {
     // tensor-core path: K-major operands = transposed copies dG^T [4H, rows], X^T [K0, rows], H^T [H, rows]
@@ -728,8 +766,8 @@ extern "C" int fsn_train_forward(const fsn_model_desc* d, const fsn_seq_weights*
   // full-band stack + Linear/activation (model.py:92-95)
   const bool tc_fb = tc_layer_ok(d, Hf), tc_sb = tc_layer_ok(d, Hs);
   if (tc_fb) {
-    if ((rc = layer_forward_save_tc(fb, 0, w.xfb, B, F, Hf, Tp, w.fb[0], w.rec, st))) return rc;
-    if ((rc = layer_forward_save_tc(fb, 1, w.fb[0].H, B, Hf, Hf, Tp, w.fb[1], w.rec, st))) return rc;
+    if ((rc = layer_forward_save_tc(fb, 0, w.xfb, B, F, Hf, Tp, w.fb[0], w.rec, st, w.splitk, SPLITK_SCRATCH_FLOATS))) return rc;
+    if ((rc = layer_forward_save_tc(fb, 1, w.fb[0].H, B, Hf, Hf, Tp, w.fb[1], w.rec, st, w.splitk, SPLITK_SCRATCH_FLOATS))) return rc;
   } else {
     if ((rc = layer_forward_save(fb, 0, w.xfb, B, F, Hf, Tp, w.fb[0], st))) return rc;
     if ((rc = layer_forward_save(fb, 1, w.fb[0].H, B, Hf, Hf, Tp, w.fb[1], st))) return rc;
@@ -748,8 +786,8 @@ extern "C" int fsn_train_forward(const fsn_model_desc* d, const fsn_seq_weights*
                                                d->sb_num_neighbors, d->fb_num_neighbors);
   FSN_CHECK_LAUNCH("train_gather_kernel");
   if (tc_sb) {
-    if ((rc = layer_forward_save_tc(sb, 0, w.xsb, m.R, m.Ksb, Hs, Tp, w.sb[0], w.rec, st))) return rc;
-    if ((rc = layer_forward_save_tc(sb, 1, w.sb[0].H, m.R, Hs, Hs, Tp, w.sb[1], w.rec, st))) return rc;
+    if ((rc = layer_forward_save_tc(sb, 0, w.xsb, m.R, m.Ksb, Hs, Tp, w.sb[0], w.rec, st, w.splitk, SPLITK_SCRATCH_FLOATS))) return rc;
+    if ((rc = layer_forward_save_tc(sb, 1, w.sb[0].H, m.R, Hs, Hs, Tp, w.sb[1], w.rec, st, w.splitk, SPLITK_SCRATCH_FLOATS))) return rc;
   } else {
     if ((rc = layer_forward_save(sb, 0, w.xsb, m.R, m.Ksb, Hs, Tp, w.sb[0], st))) return rc;
     if ((rc = layer_forward_save(sb, 1, w.sb[0].H, m.R, Hs, Hs, Tp, w.sb[1], st))) return rc;
@@ -781,7 +819,17 @@ extern "C" int fsn_train_backward(const fsn_model_desc* d, const fsn_seq_weights
   // ---- sub-band Linear (model.py:129-135 backwards)
   train_dout_kernel<<<148 * 8, 256, 0, st>>>(dcrm, w.dout, R, m.Fsub, T, Tp, d->look_ahead);
   FSN_CHECK_LAUNCH("train_dout_kernel");
-  if ((rc = sgemm_launch(true, w.dout, 2, w.sb[1].H, Hs, gsb->fc_w, Hs, 2, Hs, Tp * R, false, w.splitk, st))) return rc;
+  {  // dW of the 2-output Linear: one streaming pass over h1 (2.4 GB at config 3)
+    const size_t rows = (size_t)Tp * R;
+    int S = (int)((rows + 2047) / 2048);
+    if (S > COLSUM_MAX_S) S = COLSUM_MAX_S;
+    while (S > 1 && (size_t)S * 2 * Hs > SPLITK_SCRATCH_FLOATS) --S;
+    const size_t rows_per = (rows + S - 1) / S;
+    small_out_wgrad_kernel<2><<<dim3(cdiv(Hs, 128), S), 128, 0, st>>>(w.dout, w.sb[1].H, rows, Hs, rows_per, w.splitk);
+    FSN_CHECK_LAUNCH("small_out_wgrad_kernel");
+    colsum_final_kernel<<<cdiv(2 * Hs, 128), 128, 0, st>>>(w.splitk, S, 2 * Hs, gsb->fc_w, nullptr);
+    FSN_CHECK_LAUNCH("colsum_final_kernel");
+  }
   if ((rc = colsum_launch(w.dout, (size_t)Tp * R, 2, 2, gsb->fc_b, nullptr, w.colsum, st))) return rc;
   // ---- sub-band stack, both layers one step apart
   const bool tc_fb = tc_layer_ok(d, Hf), tc_sb = tc_layer_ok(d, Hs);
@@ -797,9 +845,9 @@ extern "C" int fsn_train_backward(const fsn_model_desc* d, const fsn_seq_weights
     if ((rc = transpose_launch(fb->w_ih[1], (size_t)4 * Hf, Hf, w.fb_wihT1, st))) return rc;
   }
   LayerBwd s1{sb->w_ih[1], sb->w_hh[1], w.sb[1], R, Hs, Hs, w.dh_rec[1], w.dc[1], tc_sb ? w.sb_whhT[1] : nullptr,
-              tc_sb ? w.sb_wihT[1] : nullptr};
+              tc_sb ? w.sb_wihT[1] : nullptr, w.splitk};
   LayerBwd s0{sb->w_ih[0], sb->w_hh[0], w.sb[0], R, K, Hs, w.dh_rec[0], w.dc[0], tc_sb ? w.sb_whhT[0] : nullptr,
-              tc_sb ? w.sb_wihT[0] : nullptr};
+              tc_sb ? w.sb_wihT[0] : nullptr, w.splitk};
   for (int t = Tp - 1; t >= 0; --t) {
     if ((rc = layer_bwd_step(s1, t, Tp, nullptr, w.dout + (size_t)t * R * 2, sb->fc_w, 2, w.dh_mid, st))) return rc;
     if ((rc = layer_bwd_step(s0, t, Tp, w.dh_mid, nullptr, nullptr, 0, w.dxsb + (size_t)t * R * K, st))) return rc;
@@ -825,8 +873,8 @@ extern "C" int fsn_train_backward(const fsn_model_desc* d, const fsn_seq_weights
   if ((rc = sgemm_launch(false, w.dz, F, fb->fc_w, Hf, w.dfh1, Hf, Tp * B, Hf, F, false, nullptr, st))) return rc;
   // ---- full-band stack
   LayerBwd f1{fb->w_ih[1], fb->w_hh[1], w.fb[1], B, Hf, Hf, w.dh_rec[1], w.dc[1], tc_fb ? w.fb_whhT[1] : nullptr,
-              tc_fb ? w.fb_wihT1 : nullptr};
-  LayerBwd f0{fb->w_ih[0], fb->w_hh[0], w.fb[0], B, F, Hf, w.dh_rec[0], w.dc[0], tc_fb ? w.fb_whhT[0] : nullptr, nullptr};
+              tc_fb ? w.fb_wihT1 : nullptr, w.splitk};
+  LayerBwd f0{fb->w_ih[0], fb->w_hh[0], w.fb[0], B, F, Hf, w.dh_rec[0], w.dc[0], tc_fb ? w.fb_whhT[0] : nullptr, nullptr, w.splitk};
   for (int t = Tp - 1; t >= 0; --t) {
     if ((rc = layer_bwd_step(f1, t, Tp, w.dfh1 + (size_t)t * B * Hf, nullptr, nullptr, 0, w.dh_mid, st))) return rc;
     if ((rc = layer_bwd_step(f0, t, Tp, w.dh_mid, nullptr, nullptr, 0, nullptr, st))) return rc;
