@@ -262,6 +262,127 @@ tgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// One LSTM step of the training forward, GEMM and cell in one kernel (torch.nn.LSTM forward, saved for autograd):
+//   z = P_t + b_ih + b_hh + h_{t-1} W_hh^T;  (i,f,g,o) = act(z);  c_t = f c_{t-1} + i g;  h_t = o tanh(c_t)
+// The CTA tile is 128 rows x 128 gate columns = the FOUR gates of 32 hidden units: the B operand is four 32-row TMA
+// boxes of W_hh (rows g*H + 32 j ..), so the accumulator holds everything the cell of those units needs and the
+// recurrent product never goes to memory.  The epilogue turns the accumulator through shared memory so that every
+// global access is a full 128-byte row piece: reads P_t (the hoisted input projection, overwritten in place by the
+// post-activation gates the backward pass needs) and c_{t-1}, writes gates, c_t, h_t.  Two CTAs per SM: one drains
+// while the other multiplies.
+__global__ void __launch_bounds__(160, 2)
+lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ G,
+                     const float* __restrict__ b_ih, const float* __restrict__ b_hh, const float* __restrict__ C_prev,
+                     float* __restrict__ C_out, float* __restrict__ H_out, int R, int H) {
+  using CF = Cfg<128>;
+  constexpr int STAGES = CF::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Bars& bars = *reinterpret_cast<Bars*>(smem + STAGES * CF::STAGE_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM, u0 = blockIdx.y * 32;
+  const int nk = (H + BK - 1) / BK;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
+    mbar_init(&bars.acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
+                 "n"(CF::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars.tmem_base;
+  if (warp < 4) {
+    if (warp == 0) {
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % STAGES;
+        if (i >= STAGES) mbar_wait<false>(&bars.empty[s], (uint32_t)(((i / STAGES) - 1) & 1));
+        if (elect_one()) {
+          uint8_t* sa = smem + s * CF::STAGE_BYTES;
+          mbar_expect_tx(&bars.full[s], CF::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, i * BK, m0, &bars.full[s]);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tma_load_2d(sa + A_BYTES + g * 32 * 128, &tmB, i * BK, g * H + u0, &bars.full[s]);
+        }
+        __syncwarp();
+      }
+    }
+    // ---- epilogue: lane = hidden unit u0 + lane, the warp walks its 32 rows
+    const int u = u0 + lane;
+    const bool u_ok = u < H;
+    const int row0 = m0 + warp * 32;
+    constexpr int RB = 8;  // rows in flight per warp
+    float pz[RB][4], cp[RB];
+    const size_t H4 = (size_t)4 * H;
+    auto load_rows = [&](int r0) {
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        const int row = row0 + r0 + j;
+        const bool ok = u_ok && row < R;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) pz[j][g] = ok ? G[(size_t)row * H4 + (size_t)g * H + u] : 0.f;
+        cp[j] = (ok && C_prev) ? C_prev[(size_t)row * H + u] : 0.f;
+      }
+    };
+    load_rows(0);  // in flight while the main loop runs
+    float bi[4], bh[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) { bi[g] = u_ok ? b_ih[g * H + u] : 0.f; bh[g] = u_ok ? b_hh[g * H + u] : 0.f; }
+    mbar_wait<true>(&bars.acc_full, 0);
+    tc_fence_after();
+    float* slab = reinterpret_cast<float*>(smem) + warp * (4 * 32 * 33);  // [gate][row][33]; the stage buffers are free now
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float v[4][8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tc_ld8(taddr + g * 32 + q * 8, v[q]);
+      tc_wait_ld();
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) slab[(g * 32 + lane) * 33 + q * 8 + j] = v[q][j];
+    }
+    __syncwarp();
+    for (int r0 = 0; r0 < 32; r0 += RB) {
+      float gi[RB], gf[RB], gg[RB], go[RB], cn[RB], hn[RB];
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        float z[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) z[g] = pz[j][g] + bi[g] + bh[g] + slab[(g * 32 + r0 + j) * 33 + lane];
+        gi[j] = sigmoidf_(z[0]); gf[j] = sigmoidf_(z[1]); gg[j] = tanhf(z[2]); go[j] = sigmoidf_(z[3]);
+        cn[j] = gf[j] * cp[j] + gi[j] * gg[j];
+        hn[j] = go[j] * tanhf(cn[j]);
+      }
+      if (r0 + RB < 32) load_rows(r0 + RB);
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        const int row = row0 + r0 + j;
+        if (u_ok && row < R) {
+          float* gr = G + (size_t)row * H4 + u;
+          gr[0] = gi[j]; gr[H] = gf[j]; gr[2 * (size_t)H] = gg[j]; gr[3 * (size_t)H] = go[j];
+          C_out[(size_t)row * H + u] = cn[j];
+          H_out[(size_t)row * H + u] = hn[j];
+        }
+      }
+    }
+  } else {
+    mma_loop<128>(smem, bars, tmem_base, nk);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(CF::TMEM_COLS));
+  }
+}
+
 }  // namespace tg
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
@@ -410,6 +531,33 @@ int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float*
   }
   FSN_CHECK_LAUNCH("tgemm_kernel");
   if (S > 1) return splitk_reduce_launch(scratch, S, M, N, C, ldc, accumulate, st);
+  return FSN_OK;
+}
+
+
+// fused recurrent GEMM + LSTM cell of one training-forward step (tg::lstm_fwd_step_kernel); G_t [R,4H] holds the hoisted
+// input projection and receives the post-activation gates
+bool lstm_fwd_step_supported(const float* Hprev, const float* w_hh, int H) {
+  static const int mode = getenv("FSN_TRAIN_FUSED_FWD") ? atoi(getenv("FSN_TRAIN_FUSED_FWD")) : 1;
+  return mode != 0 && (H % 32) == 0 && tmap_encoder() != nullptr && tgemm_supported(Hprev, H, w_hh, H, H);
+}
+int lstm_fwd_step_launch(const float* Hprev, const float* w_hh, float* Gt, const float* b_ih, const float* b_hh,
+                         const float* C_prev, float* C_out, float* H_out, int R, int H, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  FSN_REQUIRE(make_tmap(&tmA, Hprev, H, R, H, tg::BM) && make_tmap(&tmB, w_hh, H, 4 * H, H, 32), FSN_ERR_CUDA,
+              "lstm_fwd_step: tensor-map encoding failed");
+  static bool attr_by_dev[64] = {};
+  int dev = 0; cudaGetDevice(&dev); bool& attr = attr_by_dev[dev & 63];
+  if (!attr) {
+    int rc;
+    if ((rc = check_cuda(cudaFuncSetAttribute(tg::lstm_fwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              tg::Cfg<128>::SMEM), "lstm_fwd_step smem attr")))
+      return rc;
+    attr = true;
+  }
+  tg::lstm_fwd_step_kernel<<<dim3(cdiv(R, tg::BM), H / 32), 160, tg::Cfg<128>::SMEM, st>>>(tmA, tmB, Gt, b_ih, b_hh, C_prev, C_out,
+                                                                                          H_out, R, H);
+  FSN_CHECK_LAUNCH("lstm_fwd_step_kernel");
   return FSN_OK;
 }
 

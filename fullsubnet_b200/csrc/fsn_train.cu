@@ -605,8 +605,16 @@ int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R
   const size_t n = (size_t)R * H;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
+  static const int fused_min_rows = getenv("FSN_TRAIN_FUSED_MIN_ROWS") ? atoi(getenv("FSN_TRAIN_FUSED_MIN_ROWS")) : 1;
+  const bool fused = R >= fused_min_rows && lstm_fwd_step_supported(s.H, w->w_hh[l], H);
   for (int t = 0; t < Tp; ++t) {
     float* Gt = s.G + (size_t)t * R * 4 * H;
+    if (t > 0 && fused) {  // GEMM + cell in one kernel, the recurrent product stays in TMEM
+      if ((rc = lstm_fwd_step_launch(s.H + (size_t)(t - 1) * R * H, w->w_hh[l], Gt, w->b_ih[l], w->b_hh[l],
+                                     s.C + (size_t)(t - 1) * R * H, s.C + (size_t)t * R * H, s.H + (size_t)t * R * H, R, H, st)))
+        return rc;
+      continue;
+    }
     if (t > 0)
       if ((rc = tgemm_launch(s.H + (size_t)(t - 1) * R * H, H, w->w_hh[l], H, rec, 4 * H, R, 4 * H, H, false, splitk, splitk_floats, st)))
         return rc;
