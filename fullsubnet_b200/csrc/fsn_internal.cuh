@@ -67,9 +67,11 @@ bool tgemm_blocked_enabled();
 int tgemm_blocked_launch(const float* Ablk, int nkb_a, int a_kb0, const float* Bblk, int nkb_b, int b_kb0, float* C, size_t ldc,
                          int M, int N, int K, bool accumulate, float* scratch, size_t scratch_floats, cudaStream_t st);
 
-bool lstm_fwd_step_supported(const float* Hprev, const float* w_hh, int H);
-int lstm_fwd_step_launch(const float* Hprev, const float* w_hh, float* Gt, const float* b_ih, const float* b_hh,
-                         const float* C_prev, float* C_out, float* H_out, int R, int H, cudaStream_t st);
+bool lstm_fwd_step_supported(const float* Hbuf, const float* w_hh, int H);
+bool lstm_fwd_step_folds_input(const float* X, const float* w_ih, int K0);
+int lstm_fwd_step_launch(const float* Hprev, const float* w_hh, const float* Xt, const float* w_ih, int K0, float* Gt,
+                         const float* b_ih, const float* b_hh, const float* C_prev, float* C_out, float* H_out, int R, int H,
+                         cudaStream_t st);
 
 // one LSTM layer over all steps on the tf32 tensor-core path (fsn_train.cu): input projection of all steps hoisted
 // into one GEMM, then per step the recurrent GEMM into `rec` [R,4H] and the fused cell kernel.  G [Tp,R,4H]

@@ -272,9 +272,10 @@ tgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // post-activation gates the backward pass needs) and c_{t-1}, writes gates, c_t, h_t.  Two CTAs per SM: one drains
 // while the other multiplies.
 __global__ void __launch_bounds__(160, 2)
-lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ G,
+lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWx, float* __restrict__ G,
                      const float* __restrict__ b_ih, const float* __restrict__ b_hh, const float* __restrict__ C_prev,
-                     float* __restrict__ C_out, float* __restrict__ H_out, int R, int H) {
+                     float* __restrict__ C_out, float* __restrict__ H_out, int R, int H, int nkx, int nkh, int fast_act) {
   using CF = Cfg<128>;
   constexpr int STAGES = CF::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -282,7 +283,9 @@ lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   Bars& bars = *reinterpret_cast<Bars*>(smem + STAGES * CF::STAGE_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM, u0 = blockIdx.y * 32;
-  const int nk = (H + BK - 1) / BK;
+  // k blocks: first nkx of x_t W_ih^T (a narrow layer input is folded in here instead of a hoisted projection: G then
+  // carries no P and is only written), then nkh of h_{t-1} W_hh^T (0 at the first step)
+  const int nk = nkx + nkh;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
     mbar_init(&bars.acc_full, 1);
@@ -305,9 +308,12 @@ lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (elect_one()) {
           uint8_t* sa = smem + s * CF::STAGE_BYTES;
           mbar_expect_tx(&bars.full[s], CF::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, i * BK, m0, &bars.full[s]);
+          const CUtensorMap* ma = i < nkx ? &tmX : &tmA;
+          const CUtensorMap* mb = i < nkx ? &tmWx : &tmB;
+          const int k0 = (i < nkx ? i : i - nkx) * BK;
+          tma_load_2d(sa, ma, k0, m0, &bars.full[s]);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) tma_load_2d(sa + A_BYTES + g * 32 * 128, &tmB, i * BK, g * H + u0, &bars.full[s]);
+          for (int g = 0; g < 4; ++g) tma_load_2d(sa + A_BYTES + g * 32 * 128, mb, k0, g * H + u0, &bars.full[s]);
         }
         __syncwarp();
       }
@@ -325,7 +331,7 @@ lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int row = row0 + r0 + j;
         const bool ok = u_ok && row < R;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) pz[j][g] = ok ? G[(size_t)row * H4 + (size_t)g * H + u] : 0.f;
+        for (int g = 0; g < 4; ++g) pz[j][g] = (ok && nkx == 0) ? G[(size_t)row * H4 + (size_t)g * H + u] : 0.f;
         cp[j] = (ok && C_prev) ? C_prev[(size_t)row * H + u] : 0.f;
       }
     };
@@ -356,9 +362,15 @@ lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         float z[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) z[g] = pz[j][g] + bi[g] + bh[g] + slab[(g * 32 + r0 + j) * 33 + lane];
-        gi[j] = sigmoidf_(z[0]); gf[j] = sigmoidf_(z[1]); gg[j] = tanhf(z[2]); go[j] = sigmoidf_(z[3]);
-        cn[j] = gf[j] * cp[j] + gi[j] * gg[j];
-        hn[j] = go[j] * tanhf(cn[j]);
+        if (fast_act) {  // ex2 + rcp forms (2 ulp class; the tf32 products around them are 1e-3 class)
+          gi[j] = fast_sigmoid(z[0]); gf[j] = fast_sigmoid(z[1]); gg[j] = fast_tanh(z[2]); go[j] = fast_sigmoid(z[3]);
+          cn[j] = gf[j] * cp[j] + gi[j] * gg[j];
+          hn[j] = go[j] * fast_tanh(cn[j]);
+        } else {
+          gi[j] = sigmoidf_(z[0]); gf[j] = sigmoidf_(z[1]); gg[j] = tanhf(z[2]); go[j] = sigmoidf_(z[3]);
+          cn[j] = gf[j] * cp[j] + gi[j] * gg[j];
+          hn[j] = go[j] * tanhf(cn[j]);
+        }
       }
       if (r0 + RB < 32) load_rows(r0 + RB);
 #pragma unroll
@@ -537,15 +549,32 @@ int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float*
 
 // fused recurrent GEMM + LSTM cell of one training-forward step (tg::lstm_fwd_step_kernel); G_t [R,4H] holds the hoisted
 // input projection and receives the post-activation gates
-bool lstm_fwd_step_supported(const float* Hprev, const float* w_hh, int H) {
+bool lstm_fwd_step_supported(const float* Hbuf, const float* w_hh, int H) {
   static const int mode = getenv("FSN_TRAIN_FUSED_FWD") ? atoi(getenv("FSN_TRAIN_FUSED_FWD")) : 1;
-  return mode != 0 && (H % 32) == 0 && tmap_encoder() != nullptr && tgemm_supported(Hprev, H, w_hh, H, H);
+  return mode != 0 && (H % 32) == 0 && tmap_encoder() != nullptr && tgemm_supported(Hbuf, H, w_hh, H, H);
 }
-int lstm_fwd_step_launch(const float* Hprev, const float* w_hh, float* Gt, const float* b_ih, const float* b_hh,
-                         const float* C_prev, float* C_out, float* H_out, int R, int H, cudaStream_t st) {
-  CUtensorMap tmA, tmB;
-  FSN_REQUIRE(make_tmap(&tmA, Hprev, H, R, H, tg::BM) && make_tmap(&tmB, w_hh, H, 4 * H, H, 32), FSN_ERR_CUDA,
+// the layer input is multiplied inside the step kernel (no hoisted projection, no P round trip through HBM: 2 x 9.6 GB per
+// sub-band layer at config 3).  Measured per training step: no fold 110.5 ms, fold K0 <= 64 105.6 ms, all layers 99.1 ms
+bool lstm_fwd_step_folds_input(const float* X, const float* w_ih, int K0) {
+  static const int maxk = getenv("FSN_TRAIN_FOLD_K") ? atoi(getenv("FSN_TRAIN_FOLD_K")) : 512;
+  return K0 <= maxk && tgemm_supported(X, K0, w_ih, K0, K0);
+}
+// Hprev == nullptr: first step (no recurrent term).  Xt / w_ih (nullable together): fold x_t W_ih^T in, G_t is then
+// write-only; otherwise G_t holds the hoisted projection P_t
+int lstm_fwd_step_launch(const float* Hprev, const float* w_hh, const float* Xt, const float* w_ih, int K0, float* Gt,
+                         const float* b_ih, const float* b_hh, const float* C_prev, float* C_out, float* H_out, int R, int H,
+                         cudaStream_t st) {
+  CUtensorMap tmA, tmB, tmX, tmWx;
+  const float* a = Hprev ? Hprev : H_out;  // any valid [R,H] block: not read when nkh == 0
+  FSN_REQUIRE(make_tmap(&tmA, a, H, R, H, tg::BM) && make_tmap(&tmB, w_hh, H, 4 * H, H, 32), FSN_ERR_CUDA,
               "lstm_fwd_step: tensor-map encoding failed");
+  if (Xt) {
+    FSN_REQUIRE(make_tmap(&tmX, Xt, K0, R, K0, tg::BM) && make_tmap(&tmWx, w_ih, K0, 4 * H, K0, 32), FSN_ERR_CUDA,
+                "lstm_fwd_step: tensor-map encoding failed");
+  } else {
+    tmX = tmA; tmWx = tmB;
+  }
+  static const int fast_act = getenv("FSN_TRAIN_FAST_ACT") ? atoi(getenv("FSN_TRAIN_FAST_ACT")) : 1;
   static bool attr_by_dev[64] = {};
   int dev = 0; cudaGetDevice(&dev); bool& attr = attr_by_dev[dev & 63];
   if (!attr) {
@@ -555,12 +584,13 @@ int lstm_fwd_step_launch(const float* Hprev, const float* w_hh, float* Gt, const
       return rc;
     attr = true;
   }
-  tg::lstm_fwd_step_kernel<<<dim3(cdiv(R, tg::BM), H / 32), 160, tg::Cfg<128>::SMEM, st>>>(tmA, tmB, Gt, b_ih, b_hh, C_prev, C_out,
-                                                                                          H_out, R, H);
+  const int nkx = Xt ? cdiv(K0, tg::BK) : 0, nkh = Hprev ? cdiv(H, tg::BK) : 0;
+  FSN_REQUIRE(nkx + nkh > 0, FSN_ERR_SHAPE, "lstm_fwd_step: nothing to multiply");
+  tg::lstm_fwd_step_kernel<<<dim3(cdiv(R, tg::BM), H / 32), 160, tg::Cfg<128>::SMEM, st>>>(
+      tmA, tmB, tmX, tmWx, Gt, b_ih, b_hh, C_prev, C_out, H_out, R, H, nkx, nkh, fast_act);
   FSN_CHECK_LAUNCH("lstm_fwd_step_kernel");
   return FSN_OK;
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------
 // Weight-gradient GEMMs  C[M,N] = A^T B  with A [K,M] and B [K,N] row-major (dW = dG^T X, K = T'R up to 1.5 M).

@@ -597,7 +597,13 @@ int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R
                                  const LayerSave& s, float* rec, cudaStream_t st, float* splitk, size_t splitk_floats) {
   int rc;
   const int rows = Tp * R;
-  if (tgemm_supported(X, K0, w->w_ih[l], K0, K0)) {
+  static const int fused_min_rows = getenv("FSN_TRAIN_FUSED_MIN_ROWS") ? atoi(getenv("FSN_TRAIN_FUSED_MIN_ROWS")) : 1;
+  const bool fused = R >= fused_min_rows && lstm_fwd_step_supported(s.H, w->w_hh[l], H);
+  // narrow layer input (the 32-wide sub-band units): x_t W_ih^T is one more k block of the step kernel - no hoisted
+  // projection, G is written once and never read in the forward pass
+  const bool fold = fused && lstm_fwd_step_folds_input(X, w->w_ih[l], K0);
+  if (fold) {
+  } else if (tgemm_supported(X, K0, w->w_ih[l], K0, K0)) {
     if ((rc = tgemm_launch(X, K0, w->w_ih[l], K0, s.G, 4 * H, rows, 4 * H, K0, false, nullptr, 0, st))) return rc;
   } else if ((rc = fc_gemm_launch(X, w->w_ih[l], nullptr, s.G, rows, K0, 4 * H, FSN_ACT_NONE, st))) {
     return rc;  // rows of X not 16-byte aligned (K0 % 4 != 0): fp32 SIMT GEMM
@@ -605,13 +611,13 @@ int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R
   const size_t n = (size_t)R * H;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  static const int fused_min_rows = getenv("FSN_TRAIN_FUSED_MIN_ROWS") ? atoi(getenv("FSN_TRAIN_FUSED_MIN_ROWS")) : 1;
-  const bool fused = R >= fused_min_rows && lstm_fwd_step_supported(s.H, w->w_hh[l], H);
   for (int t = 0; t < Tp; ++t) {
     float* Gt = s.G + (size_t)t * R * 4 * H;
-    if (t > 0 && fused) {  // GEMM + cell in one kernel, the recurrent product stays in TMEM
-      if ((rc = lstm_fwd_step_launch(s.H + (size_t)(t - 1) * R * H, w->w_hh[l], Gt, w->b_ih[l], w->b_hh[l],
-                                     s.C + (size_t)(t - 1) * R * H, s.C + (size_t)t * R * H, s.H + (size_t)t * R * H, R, H, st)))
+    if (fused && (t > 0 || fold)) {  // GEMM + cell in one kernel, the recurrent product stays in TMEM
+      if ((rc = lstm_fwd_step_launch(t > 0 ? s.H + (size_t)(t - 1) * R * H : nullptr, w->w_hh[l],
+                                     fold ? X + (size_t)t * R * K0 : nullptr, w->w_ih[l], K0, Gt, w->b_ih[l], w->b_hh[l],
+                                     t > 0 ? s.C + (size_t)(t - 1) * R * H : nullptr, s.C + (size_t)t * R * H,
+                                     s.H + (size_t)t * R * H, R, H, st)))
         return rc;
       continue;
     }
