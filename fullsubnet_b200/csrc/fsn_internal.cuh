@@ -1,5 +1,7 @@
 // Internal (non-ABI) declarations shared by the translation units of libfsn_b200.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "fsn_common.cuh"
 
 namespace fsn {
@@ -69,16 +71,27 @@ int tgemm_blocked_launch(const float* Ablk, int nkb_a, int a_kb0, const float* B
 
 bool lstm_fwd_step_supported(const float* Hbuf, const float* w_hh, int H);
 bool lstm_fwd_step_folds_input(const float* X, const float* w_ih, int K0);
+// optional fp16 MMA operands of the step kernel: previous hidden state, weights, folded layer input; H16_out receives h_t
+struct LstmStepHalf {
+  const __half *Hprev16, *w_hh16, *Xt16, *w_ih16;
+  __half* H16_out;
+};
+bool lstm_fwd_step_half_enabled(int H);
+int to_half_launch(const float* in, size_t n, __half* out, cudaStream_t st);
 int lstm_fwd_step_launch(const float* Hprev, const float* w_hh, const float* Xt, const float* w_ih, int K0, float* Gt,
                          const float* b_ih, const float* b_hh, const float* C_prev, float* C_out, float* H_out, int R, int H,
-                         cudaStream_t st);
+                         cudaStream_t st, const LstmStepHalf* h = nullptr);
 
 // one LSTM layer over all steps on the tf32 tensor-core path (fsn_train.cu): input projection of all steps hoisted
 // into one GEMM, then per step the recurrent GEMM into `rec` [R,4H] and the fused cell kernel.  G [Tp,R,4H]
 // (post-activation gates), C, H [Tp,R,H] receive every step.  X [Tp,R,K0] contiguous.
 struct LayerSave { float *G, *C, *H; };
+// fp16 side buffers of one layer (all nullable): H16 [Tp,R,H] copy of the hidden states (written by the step kernel, the
+// next layer's X16), X16 [Tp,R,K0] copy of the layer input, w16: 4H*(H+K0) halfs for the weight copies
+struct LayerHalf { __half* H16; const __half* X16; __half* w16; };
 int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R, int K0, int H, int Tp,
-                          const LayerSave& s, float* rec, cudaStream_t st, float* splitk = nullptr, size_t splitk_floats = 0);
+                          const LayerSave& s, float* rec, cudaStream_t st, float* splitk = nullptr, size_t splitk_floats = 0,
+                          const LayerHalf* half = nullptr);
 
 // shapes of one Model.forward call (fsn_model.cu)
 struct Dims {

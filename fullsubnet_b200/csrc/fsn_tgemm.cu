@@ -275,7 +275,8 @@ __global__ void __launch_bounds__(160, 2)
 lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWx, float* __restrict__ G,
                      const float* __restrict__ b_ih, const float* __restrict__ b_hh, const float* __restrict__ C_prev,
-                     float* __restrict__ C_out, float* __restrict__ H_out, int R, int H, int nkx, int nkh, int fast_act) {
+                     float* __restrict__ C_out, float* __restrict__ H_out, __half* __restrict__ H16_out, int R, int H, int nkx,
+                     int nkh, int x16, int h16, int fast_act) {
   using CF = Cfg<128>;
   constexpr int STAGES = CF::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -310,7 +311,8 @@ lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           mbar_expect_tx(&bars.full[s], CF::STAGE_BYTES);
           const CUtensorMap* ma = i < nkx ? &tmX : &tmA;
           const CUtensorMap* mb = i < nkx ? &tmWx : &tmB;
-          const int k0 = (i < nkx ? i : i - nkx) * BK;
+          // a stage row is 128 bytes: 32 tf32 or 64 fp16 k values
+          const int k0 = (i < nkx ? i * (x16 ? 2 * BK : BK) : (i - nkx) * (h16 ? 2 * BK : BK));
           tma_load_2d(sa, ma, k0, m0, &bars.full[s]);
 #pragma unroll
           for (int g = 0; g < 4; ++g) tma_load_2d(sa + A_BYTES + g * 32 * 128, mb, k0, g * H + u0, &bars.full[s]);
@@ -381,11 +383,35 @@ lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           gr[0] = gi[j]; gr[H] = gf[j]; gr[2 * (size_t)H] = gg[j]; gr[3 * (size_t)H] = go[j];
           C_out[(size_t)row * H + u] = cn[j];
           H_out[(size_t)row * H + u] = hn[j];
+          if (H16_out) H16_out[(size_t)row * H + u] = __float2half_rn(hn[j]);  // next step's / next layer's MMA operand
         }
       }
     }
   } else {
-    mma_loop<128>(smem, bars, tmem_base, nk);
+    // MMA issue: per stage four instructions over 32 bytes of k each (8 tf32 or 16 fp16 values); both kinds accumulate
+    // into the same fp32 tile
+    const uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t idesc16 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t smem_base = smem_u32(smem);
+    for (int i = 0; i < nk; ++i) {
+      const int s = i % STAGES;
+      mbar_wait<false>(&bars.full[s], (uint32_t)((i / STAGES) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_base + s * CF::STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+        const bool half_blk = i < nkx ? (x16 != 0) : (h16 != 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (half_blk) tc_mma1_f16(tmem_base, desc_sw128(sa + kk * 32), desc_sw128(sb + kk * 32), idesc16, (i > 0 || kk > 0) ? 1u : 0u);
+          else          tc_mma1_tf32(tmem_base, desc_sw128(sa + kk * 32), desc_sw128(sb + kk * 32), idesc32, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+        tc_commit1(&bars.empty[s]);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) tc_commit1(&bars.acc_full);
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -423,6 +449,19 @@ static bool make_tmap(CUtensorMap* m, const float* base, int K, int rows, size_t
   cuuint32_t box[2] = {(cuuint32_t)tg::BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+         CUDA_SUCCESS;
+}
+
+// fp16 [rows, K] row-major (ld halfs) -> boxes of box_rows x 64 halfs (128 bytes), 128B swizzle, zero fill outside
+static bool make_tmap16(CUtensorMap* m, const __half* base, int K, int rows, size_t ld, int box_rows) {
+  PFN_cuTensorMapEncodeTiled_v12000 fn = tmap_encoder();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)(2 * tg::BK), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
          CUDA_SUCCESS;
 }
@@ -559,21 +598,31 @@ bool lstm_fwd_step_folds_input(const float* X, const float* w_ih, int K0) {
   static const int maxk = getenv("FSN_TRAIN_FOLD_K") ? atoi(getenv("FSN_TRAIN_FOLD_K")) : 512;
   return K0 <= maxk && tgemm_supported(X, K0, w_ih, K0, K0);
 }
+// fp16 copies of the MMA operands (h and the weights rounded to nearest: the same 11-bit significand as tf32 reads, half the
+// bytes through L2 and twice the tensor rate); the fp32 state, the saved activations and the backward pass are unchanged
+bool lstm_fwd_step_half_enabled(int H) {
+  static const int on = getenv("FSN_TRAIN_F16_FWD") ? atoi(getenv("FSN_TRAIN_F16_FWD")) : 1;
+  return on != 0 && (H % 8) == 0;
+}
 // Hprev == nullptr: first step (no recurrent term).  Xt / w_ih (nullable together): fold x_t W_ih^T in, G_t is then
-// write-only; otherwise G_t holds the hoisted projection P_t
+// write-only; otherwise G_t holds the hoisted projection P_t.  h: optional fp16 operands (see LstmStepHalf)
 int lstm_fwd_step_launch(const float* Hprev, const float* w_hh, const float* Xt, const float* w_ih, int K0, float* Gt,
                          const float* b_ih, const float* b_hh, const float* C_prev, float* C_out, float* H_out, int R, int H,
-                         cudaStream_t st) {
+                         cudaStream_t st, const LstmStepHalf* h) {
   CUtensorMap tmA, tmB, tmX, tmWx;
-  const float* a = Hprev ? Hprev : H_out;  // any valid [R,H] block: not read when nkh == 0
-  FSN_REQUIRE(make_tmap(&tmA, a, H, R, H, tg::BM) && make_tmap(&tmB, w_hh, H, 4 * H, H, 32), FSN_ERR_CUDA,
-              "lstm_fwd_step: tensor-map encoding failed");
-  if (Xt) {
-    FSN_REQUIRE(make_tmap(&tmX, Xt, K0, R, K0, tg::BM) && make_tmap(&tmWx, w_ih, K0, 4 * H, K0, 32), FSN_ERR_CUDA,
-                "lstm_fwd_step: tensor-map encoding failed");
+  const bool h16 = h && h->w_hh16 && h->H16_out, x16 = h16 && Xt && h->Xt16 && h->w_ih16;
+  bool ok;
+  if (h16) {
+    const __half* a = Hprev ? h->Hprev16 : h->H16_out;  // any valid [R,H] block: not read when nkh == 0
+    ok = make_tmap16(&tmA, a, H, R, H, tg::BM) && make_tmap16(&tmB, h->w_hh16, H, 4 * H, H, 32);
   } else {
-    tmX = tmA; tmWx = tmB;
+    const float* a = Hprev ? Hprev : H_out;
+    ok = make_tmap(&tmA, a, H, R, H, tg::BM) && make_tmap(&tmB, w_hh, H, 4 * H, H, 32);
   }
+  if (Xt && x16) ok = ok && make_tmap16(&tmX, h->Xt16, K0, R, K0, tg::BM) && make_tmap16(&tmWx, h->w_ih16, K0, 4 * H, K0, 32);
+  else if (Xt)   ok = ok && make_tmap(&tmX, Xt, K0, R, K0, tg::BM) && make_tmap(&tmWx, w_ih, K0, 4 * H, K0, 32);
+  else { tmX = tmA; tmWx = tmB; }
+  FSN_REQUIRE(ok, FSN_ERR_CUDA, "lstm_fwd_step: tensor-map encoding failed");
   static const int fast_act = getenv("FSN_TRAIN_FAST_ACT") ? atoi(getenv("FSN_TRAIN_FAST_ACT")) : 1;
   static bool attr_by_dev[64] = {};
   int dev = 0; cudaGetDevice(&dev); bool& attr = attr_by_dev[dev & 63];
@@ -584,11 +633,26 @@ int lstm_fwd_step_launch(const float* Hprev, const float* w_hh, const float* Xt,
       return rc;
     attr = true;
   }
-  const int nkx = Xt ? cdiv(K0, tg::BK) : 0, nkh = Hprev ? cdiv(H, tg::BK) : 0;
+  const int nkx = Xt ? cdiv(K0, x16 ? 2 * tg::BK : tg::BK) : 0, nkh = Hprev ? cdiv(H, h16 ? 2 * tg::BK : tg::BK) : 0;
   FSN_REQUIRE(nkx + nkh > 0, FSN_ERR_SHAPE, "lstm_fwd_step: nothing to multiply");
   tg::lstm_fwd_step_kernel<<<dim3(cdiv(R, tg::BM), H / 32), 160, tg::Cfg<128>::SMEM, st>>>(
-      tmA, tmB, tmX, tmWx, Gt, b_ih, b_hh, C_prev, C_out, H_out, R, H, nkx, nkh, fast_act);
+      tmA, tmB, tmX, tmWx, Gt, b_ih, b_hh, C_prev, C_out, H_out, h16 ? h->H16_out : nullptr, R, H, nkx, nkh, x16 ? 1 : 0,
+      h16 ? 1 : 0, fast_act);
   FSN_CHECK_LAUNCH("lstm_fwd_step_kernel");
+  return FSN_OK;
+}
+
+namespace tg {
+__global__ void to_half_kernel(const float* __restrict__ in, size_t n, __half* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __float2half_rn(in[i]);
+}
+}  // namespace tg
+int to_half_launch(const float* in, size_t n, __half* out, cudaStream_t st) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  tg::to_half_kernel<<<blocks, 256, 0, st>>>(in, n, out);
+  FSN_CHECK_LAUNCH("to_half_kernel");
   return FSN_OK;
 }
 

@@ -504,6 +504,7 @@ struct TrainWs {
   // FSN_PREC_TF32_TC: transposed weights ([H,4H], [K0,4H]) and transposed dG / layer inputs for the weight gradients
   float *sb_whhT[2], *sb_wihT[2], *fb_whhT[2], *fb_wihT1;
   float *gT, *xT, *rec;
+  __half *fb_h16[2], *sb_h16[2], *w16;  // fp16 MMA operands of the forward step kernel (hidden states, weights)
   float *cum1, *cum2, *dunit;  // cumulative norm: scale of (step, clip), of (step, unit); gradient of the fb row per unit
   float2* fs;
   size_t bytes;
@@ -558,6 +559,14 @@ static void carve_train(const fsn_model_desc* d, const Dims& m, void* base, Trai
                  x_fb = tgemm_blocked_floats(Tp * B, Hf > F ? (int)Hf : (int)F);
     w.xT = c.take(x_sb > x_fb ? x_sb : x_fb);
     w.rec = c.take(4 * RH);
+    for (int l = 0; l < 2; ++l) {
+      w.fb_h16[l] = (__half*)c.take((Tp * B * Hf + 1) / 2);
+      w.sb_h16[l] = (__half*)c.take((Tp * R * Hs + 1) / 2);
+    }
+    const size_t wmax = Hf > Hs ? Hf : Hs;
+    w.w16 = (__half*)c.take((4 * wmax * 2 * wmax + 1) / 2);
+  } else {
+    w.fb_h16[0] = w.fb_h16[1] = w.sb_h16[0] = w.sb_h16[1] = w.w16 = nullptr;
   }
   w.bytes = c.off;
 }
@@ -594,7 +603,8 @@ static int layer_forward_save(const fsn_seq_weights* w, int l, const float* X, i
 // tensor-core variant: input projection of ALL steps as one GEMM into the gate buffer, then per step
 // G_t += h_{t-1} W_hh^T (tcgen05 tf32) and the fused cell kernel
 int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R, int K0, int H, int Tp,
-                                 const LayerSave& s, float* rec, cudaStream_t st, float* splitk, size_t splitk_floats) {
+                                 const LayerSave& s, float* rec, cudaStream_t st, float* splitk, size_t splitk_floats,
+                                 const LayerHalf* half) {
   int rc;
   const int rows = Tp * R;
   static const int fused_min_rows = getenv("FSN_TRAIN_FUSED_MIN_ROWS") ? atoi(getenv("FSN_TRAIN_FUSED_MIN_ROWS")) : 1;
@@ -602,6 +612,14 @@ int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R
   // narrow layer input (the 32-wide sub-band units): x_t W_ih^T is one more k block of the step kernel - no hoisted
   // projection, G is written once and never read in the forward pass
   const bool fold = fused && lstm_fwd_step_folds_input(X, w->w_ih[l], K0);
+  // fp16 MMA operands: h_t (written by the step kernel next to the fp32 copy) and the weights; the folded layer input too
+  // when the layer below left an fp16 copy (K0 % 8: 16-byte rows)
+  const bool h16 = fused && half && half->H16 && half->w16 && lstm_fwd_step_half_enabled(H);
+  const bool x16 = h16 && fold && half->X16 && (K0 % 8) == 0;
+  __half* w_hh16 = h16 ? half->w16 : nullptr;
+  __half* w_ih16 = x16 ? half->w16 + (size_t)4 * H * H : nullptr;
+  if (h16 && (rc = to_half_launch(w->w_hh[l], (size_t)4 * H * H, w_hh16, st))) return rc;
+  if (x16 && (rc = to_half_launch(w->w_ih[l], (size_t)4 * H * K0, w_ih16, st))) return rc;
   if (fold) {
   } else if (tgemm_supported(X, K0, w->w_ih[l], K0, K0)) {
     if ((rc = tgemm_launch(X, K0, w->w_ih[l], K0, s.G, 4 * H, rows, 4 * H, K0, false, nullptr, 0, st))) return rc;
@@ -614,13 +632,22 @@ int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R
   for (int t = 0; t < Tp; ++t) {
     float* Gt = s.G + (size_t)t * R * 4 * H;
     if (fused && (t > 0 || fold)) {  // GEMM + cell in one kernel, the recurrent product stays in TMEM
+      LstmStepHalf hs{nullptr, nullptr, nullptr, nullptr, nullptr};
+      if (h16) {
+        hs.Hprev16 = t > 0 ? half->H16 + (size_t)(t - 1) * R * H : nullptr;
+        hs.w_hh16 = w_hh16;
+        hs.H16_out = half->H16 + (size_t)t * R * H;
+        if (x16) { hs.Xt16 = half->X16 + (size_t)t * R * K0; hs.w_ih16 = w_ih16; }
+      }
       if ((rc = lstm_fwd_step_launch(t > 0 ? s.H + (size_t)(t - 1) * R * H : nullptr, w->w_hh[l],
                                      fold ? X + (size_t)t * R * K0 : nullptr, w->w_ih[l], K0, Gt, w->b_ih[l], w->b_hh[l],
                                      t > 0 ? s.C + (size_t)(t - 1) * R * H : nullptr, s.C + (size_t)t * R * H,
-                                     s.H + (size_t)t * R * H, R, H, st)))
+                                     s.H + (size_t)t * R * H, R, H, st, h16 ? &hs : nullptr)))
         return rc;
       continue;
     }
+    // (first step of a layer with a hoisted projection: no product at all, the plain cell kernel; its h_0 also goes out
+    // in fp16 below)
     if (t > 0)
       if ((rc = tgemm_launch(s.H + (size_t)(t - 1) * R * H, H, w->w_hh[l], H, rec, 4 * H, R, 4 * H, H, false, splitk, splitk_floats, st)))
         return rc;
@@ -628,6 +655,7 @@ int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R
                                                  t > 0 ? s.C + (size_t)(t - 1) * R * H : nullptr,
                                                  s.C + (size_t)t * R * H, s.H + (size_t)t * R * H, R, H);
     FSN_CHECK_LAUNCH("lstm_cell_fwd_kernel");
+    if (h16 && (rc = to_half_launch(s.H + (size_t)t * R * H, (size_t)R * H, half->H16 + (size_t)t * R * H, st))) return rc;
   }
   return FSN_OK;
 }
@@ -779,9 +807,12 @@ extern "C" int fsn_train_forward(const fsn_model_desc* d, const fsn_seq_weights*
   }
   // full-band stack + Linear/activation (model.py:92-95)
   const bool tc_fb = tc_layer_ok(d, Hf), tc_sb = tc_layer_ok(d, Hs);
+  // fp16 operand copies: layer 0's hidden states double as layer 1's input
+  const LayerHalf hf0{w.fb_h16[0], nullptr, w.w16}, hf1{w.fb_h16[1], w.fb_h16[0], w.w16};
+  const LayerHalf hs0{w.sb_h16[0], nullptr, w.w16}, hs1{w.sb_h16[1], w.sb_h16[0], w.w16};
   if (tc_fb) {
-    if ((rc = layer_forward_save_tc(fb, 0, w.xfb, B, F, Hf, Tp, w.fb[0], w.rec, st, w.splitk, SPLITK_SCRATCH_FLOATS))) return rc;
-    if ((rc = layer_forward_save_tc(fb, 1, w.fb[0].H, B, Hf, Hf, Tp, w.fb[1], w.rec, st, w.splitk, SPLITK_SCRATCH_FLOATS))) return rc;
+    if ((rc = layer_forward_save_tc(fb, 0, w.xfb, B, F, Hf, Tp, w.fb[0], w.rec, st, w.splitk, SPLITK_SCRATCH_FLOATS, &hf0))) return rc;
+    if ((rc = layer_forward_save_tc(fb, 1, w.fb[0].H, B, Hf, Hf, Tp, w.fb[1], w.rec, st, w.splitk, SPLITK_SCRATCH_FLOATS, &hf1))) return rc;
   } else {
     if ((rc = layer_forward_save(fb, 0, w.xfb, B, F, Hf, Tp, w.fb[0], st))) return rc;
     if ((rc = layer_forward_save(fb, 1, w.fb[0].H, B, Hf, Hf, Tp, w.fb[1], st))) return rc;
@@ -800,8 +831,8 @@ extern "C" int fsn_train_forward(const fsn_model_desc* d, const fsn_seq_weights*
                                                d->sb_num_neighbors, d->fb_num_neighbors);
   FSN_CHECK_LAUNCH("train_gather_kernel");
   if (tc_sb) {
-    if ((rc = layer_forward_save_tc(sb, 0, w.xsb, m.R, m.Ksb, Hs, Tp, w.sb[0], w.rec, st, w.splitk, SPLITK_SCRATCH_FLOATS))) return rc;
-    if ((rc = layer_forward_save_tc(sb, 1, w.sb[0].H, m.R, Hs, Hs, Tp, w.sb[1], w.rec, st, w.splitk, SPLITK_SCRATCH_FLOATS))) return rc;
+    if ((rc = layer_forward_save_tc(sb, 0, w.xsb, m.R, m.Ksb, Hs, Tp, w.sb[0], w.rec, st, w.splitk, SPLITK_SCRATCH_FLOATS, &hs0))) return rc;
+    if ((rc = layer_forward_save_tc(sb, 1, w.sb[0].H, m.R, Hs, Hs, Tp, w.sb[1], w.rec, st, w.splitk, SPLITK_SCRATCH_FLOATS, &hs1))) return rc;
   } else {
     if ((rc = layer_forward_save(sb, 0, w.xsb, m.R, m.Ksb, Hs, Tp, w.sb[0], st))) return rc;
     if ((rc = layer_forward_save(sb, 1, w.sb[0].H, m.R, Hs, Hs, Tp, w.sb[1], st))) return rc;
