@@ -271,12 +271,30 @@ tgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // global access is a full 128-byte row piece: reads P_t (the hoisted input projection, overwritten in place by the
 // post-activation gates the backward pass needs) and c_{t-1}, writes gates, c_t, h_t.  Two CTAs per SM: one drains
 // while the other multiplies.
-__global__ void __launch_bounds__(160, 2)
+// 1 / (1 + 2^(-x log2 e)) and 2 sigmoid(2x) - 1 on the MUFU unit (ex2.approx + rcp.approx: ~2 ulp; saturate correctly:
+// ex2 -> inf gives rcp -> 0, ex2 -> 0 gives 1)
+__device__ __forceinline__ float sigmoid_mufu(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+__device__ __forceinline__ float tanh_mufu(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -2.8853900817779268f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return fmaf(2.0f, r, -1.0f);
+}
+
+// HT: hidden size known at compile time (0: runtime) - every stride of the epilogue becomes an immediate offset
+template <bool FOLD, int HT>
+__global__ void __launch_bounds__(192, 2)
 lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWx, float* __restrict__ G,
                      const float* __restrict__ b_ih, const float* __restrict__ b_hh, const float* __restrict__ C_prev,
-                     float* __restrict__ C_out, float* __restrict__ H_out, __half* __restrict__ H16_out, int R, int H, int nkx,
-                     int nkh, int x16, int h16, int fast_act) {
+                     float* __restrict__ C_out, float* __restrict__ H_out, __half* __restrict__ H16_out, int R, int H_rt, int nkx,
+                     int nkh, int x16, int h16) {
+  const int H = HT ? HT : H_rt;
   using CF = Cfg<128>;
   constexpr int STAGES = CF::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -301,49 +319,55 @@ lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars.tmem_base;
-  if (warp < 4) {
-    if (warp == 0) {
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % STAGES;
-        if (i >= STAGES) mbar_wait<false>(&bars.empty[s], (uint32_t)(((i / STAGES) - 1) & 1));
-        if (elect_one()) {
-          uint8_t* sa = smem + s * CF::STAGE_BYTES;
-          mbar_expect_tx(&bars.full[s], CF::STAGE_BYTES);
-          const CUtensorMap* ma = i < nkx ? &tmX : &tmA;
-          const CUtensorMap* mb = i < nkx ? &tmWx : &tmB;
-          // a stage row is 128 bytes: 32 tf32 or 64 fp16 k values
-          const int k0 = (i < nkx ? i * (x16 ? 2 * BK : BK) : (i - nkx) * (h16 ? 2 * BK : BK));
-          tma_load_2d(sa, ma, k0, m0, &bars.full[s]);
+  if (warp == 5) {
+    // TMA producer (its own warp: the four epilogue warps start their global loads right away)
+    for (int i = 0; i < nk; ++i) {
+      const int s = i % STAGES;
+      if (i >= STAGES) mbar_wait<false>(&bars.empty[s], (uint32_t)(((i / STAGES) - 1) & 1));
+      if (elect_one()) {
+        uint8_t* sa = smem + s * CF::STAGE_BYTES;
+        mbar_expect_tx(&bars.full[s], CF::STAGE_BYTES);
+        const CUtensorMap* ma = i < nkx ? &tmX : &tmA;
+        const CUtensorMap* mb = i < nkx ? &tmWx : &tmB;
+        // a stage row is 128 bytes: 32 tf32 or 64 fp16 k values
+        const int k0 = (i < nkx ? i * (x16 ? 2 * BK : BK) : (i - nkx) * (h16 ? 2 * BK : BK));
+        tma_load_2d(sa, ma, k0, m0, &bars.full[s]);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) tma_load_2d(sa + A_BYTES + g * 32 * 128, mb, k0, g * H + u0, &bars.full[s]);
-        }
-        __syncwarp();
+        for (int g = 0; g < 4; ++g) tma_load_2d(sa + A_BYTES + g * 32 * 128, mb, k0, g * H + u0, &bars.full[s]);
       }
+      __syncwarp();
     }
-    // ---- epilogue: lane = hidden unit u0 + lane, the warp walks its 32 rows
+  } else if (warp < 4) {
+    // ---- epilogue: lane = hidden unit u0 + lane (H % 32 == 0), the warp walks its 32 rows in batches of 8.  Kept
+    // small on purpose: the straight-line version of this loop overflowed the instruction cache (ncu: 29 % of the
+    // samples on stall_no_inst) and the cell costs more issue slots than the MMAs
     const int u = u0 + lane;
-    const bool u_ok = u < H;
     const int row0 = m0 + warp * 32;
-    constexpr int RB = 8;  // rows in flight per warp
-    float pz[RB][4], cp[RB];
-    const size_t H4 = (size_t)4 * H;
+    const int nrows = R - row0 < 32 ? R - row0 : 32;  // may be <= 0: nothing to do but the barriers
+    constexpr int RB = 8;
+    const unsigned H4 = 4u * (unsigned)H;
+    float b[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) b[g] = b_ih[g * H + u] + b_hh[g * H + u];
+    const float* cp_ptr = C_prev ? C_prev + (size_t)row0 * H + u : nullptr;
+    float* g_ptr = G + (size_t)row0 * H4 + u;
+    float cp[RB], pz[FOLD ? 1 : RB][4];
     auto load_rows = [&](int r0) {
 #pragma unroll
       for (int j = 0; j < RB; ++j) {
-        const int row = row0 + r0 + j;
-        const bool ok = u_ok && row < R;
+        const bool ok = r0 + j < nrows;
+        cp[j] = (ok && cp_ptr) ? (cp_ptr + (size_t)r0 * H)[j * H] : 0.f;
+        if (!FOLD) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) pz[j][g] = (ok && nkx == 0) ? G[(size_t)row * H4 + (size_t)g * H + u] : 0.f;
-        cp[j] = (ok && C_prev) ? C_prev[(size_t)row * H + u] : 0.f;
+          for (int g = 0; g < 4; ++g) pz[j][g] = ok ? (g_ptr + (size_t)r0 * H4)[j * 4 * H + g * H] : 0.f;
+        }
       }
     };
     load_rows(0);  // in flight while the main loop runs
-    float bi[4], bh[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) { bi[g] = u_ok ? b_ih[g * H + u] : 0.f; bh[g] = u_ok ? b_hh[g * H + u] : 0.f; }
     mbar_wait<true>(&bars.acc_full, 0);
     tc_fence_after();
-    float* slab = reinterpret_cast<float*>(smem) + warp * (4 * 32 * 33);  // [gate][row][33]; the stage buffers are free now
+    // accumulator -> per-warp slab [gate][row][33] in the (now free) stage buffers, shared-space addresses
+    const uint32_t slab = smem_u32(smem) + (uint32_t)warp * (4 * 32 * 33 * 4);
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -354,40 +378,61 @@ lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) slab[(g * 32 + lane) * 33 + q * 8 + j] = v[q][j];
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(slab + (uint32_t)(((g * 32 + lane) * 33 + q * 8 + j) * 4)), "f"(v[q][j]));
     }
     __syncwarp();
+    float* c_ptr = C_out + (size_t)row0 * H + u;
+    float* h_ptr = H_out + (size_t)row0 * H + u;
+    __half* h16_ptr = H16_out ? H16_out + (size_t)row0 * H + u : nullptr;
+#pragma unroll 1
     for (int r0 = 0; r0 < 32; r0 += RB) {
       float gi[RB], gf[RB], gg[RB], go[RB], cn[RB], hn[RB];
 #pragma unroll
       for (int j = 0; j < RB; ++j) {
         float z[4];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) z[g] = pz[j][g] + bi[g] + bh[g] + slab[(g * 32 + r0 + j) * 33 + lane];
-        if (fast_act) {  // ex2 + rcp forms (2 ulp class; the tf32 products around them are 1e-3 class)
-          gi[j] = fast_sigmoid(z[0]); gf[j] = fast_sigmoid(z[1]); gg[j] = fast_tanh(z[2]); go[j] = fast_sigmoid(z[3]);
-          cn[j] = gf[j] * cp[j] + gi[j] * gg[j];
-          hn[j] = go[j] * fast_tanh(cn[j]);
-        } else {
-          gi[j] = sigmoidf_(z[0]); gf[j] = sigmoidf_(z[1]); gg[j] = tanhf(z[2]); go[j] = sigmoidf_(z[3]);
-          cn[j] = gf[j] * cp[j] + gi[j] * gg[j];
-          hn[j] = go[j] * tanhf(cn[j]);
+        for (int g = 0; g < 4; ++g) {
+          float a;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a) : "r"(slab + (uint32_t)(((g * 32 + r0 + j) * 33 + lane) * 4)));
+          z[g] = FOLD ? a + b[g] : (pz[j][g] + b[g]) + a;
         }
+        // ex2 + rcp forms (2 ulp class; the tf32 / fp16 products around them are 1e-3 class).  FSN_TRAIN_FAST_ACT=0
+        // selects the unfused GEMM + lstm_cell_fwd_kernel path with expf / IEEE division instead
+        gi[j] = sigmoid_mufu(z[0]); gf[j] = sigmoid_mufu(z[1]); gg[j] = tanh_mufu(z[2]); go[j] = sigmoid_mufu(z[3]);
+        cn[j] = fmaf(gf[j], cp[j], gi[j] * gg[j]);
+        hn[j] = go[j] * tanh_mufu(cn[j]);
       }
-      if (r0 + RB < 32) load_rows(r0 + RB);
+      // one base per array and batch, everything else an offset (immediate when HT != 0)
+      float* gr = g_ptr + (size_t)r0 * H4;
+      float* cr = c_ptr + (size_t)r0 * H;
+      float* hr = h_ptr + (size_t)r0 * H;
+      __half* h16r = h16_ptr + (size_t)r0 * H;
+      if (r0 + RB < 32) load_rows(r0 + RB);  // next batch in flight under this batch's stores
+      if (r0 + RB <= nrows) {                // whole batch inside the matrix: no per-row predicates
 #pragma unroll
-      for (int j = 0; j < RB; ++j) {
-        const int row = row0 + r0 + j;
-        if (u_ok && row < R) {
-          float* gr = G + (size_t)row * H4 + u;
-          gr[0] = gi[j]; gr[H] = gf[j]; gr[2 * (size_t)H] = gg[j]; gr[3 * (size_t)H] = go[j];
-          C_out[(size_t)row * H + u] = cn[j];
-          H_out[(size_t)row * H + u] = hn[j];
-          if (H16_out) H16_out[(size_t)row * H + u] = __float2half_rn(hn[j]);  // next step's / next layer's MMA operand
+        for (int j = 0; j < RB; ++j) {
+          gr[j * 4 * H] = gi[j]; gr[j * 4 * H + H] = gf[j]; gr[j * 4 * H + 2 * H] = gg[j]; gr[j * 4 * H + 3 * H] = go[j];
+          cr[j * H] = cn[j];
+          hr[j * H] = hn[j];
+        }
+        if (h16_ptr) {
+#pragma unroll
+          for (int j = 0; j < RB; ++j) h16r[j * H] = __float2half_rn(hn[j]);  // next step's / next layer's MMA operand
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+          if (r0 + j < nrows) {
+            gr[j * 4 * H] = gi[j]; gr[j * 4 * H + H] = gf[j]; gr[j * 4 * H + 2 * H] = gg[j]; gr[j * 4 * H + 3 * H] = go[j];
+            cr[j * H] = cn[j];
+            hr[j * H] = hn[j];
+            if (h16_ptr) h16r[j * H] = __float2half_rn(hn[j]);
+          }
         }
       }
     }
-  } else {
+  } else if (warp == 4) {
     // MMA issue: per stage four instructions over 32 bytes of k each (8 tf32 or 16 fp16 values); both kinds accumulate
     // into the same fp32 tile
     const uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -590,7 +635,8 @@ int tgemm_launch(const float* A, size_t lda, const float* Bm, size_t ldb, float*
 // input projection and receives the post-activation gates
 bool lstm_fwd_step_supported(const float* Hbuf, const float* w_hh, int H) {
   static const int mode = getenv("FSN_TRAIN_FUSED_FWD") ? atoi(getenv("FSN_TRAIN_FUSED_FWD")) : 1;
-  return mode != 0 && (H % 32) == 0 && tmap_encoder() != nullptr && tgemm_supported(Hbuf, H, w_hh, H, H);
+  static const int fast_act = getenv("FSN_TRAIN_FAST_ACT") ? atoi(getenv("FSN_TRAIN_FAST_ACT")) : 1;
+  return mode != 0 && fast_act != 0 && (H % 32) == 0 && tmap_encoder() != nullptr && tgemm_supported(Hbuf, H, w_hh, H, H);
 }
 // the layer input is multiplied inside the step kernel (no hoisted projection, no P round trip through HBM: 2 x 9.6 GB per
 // sub-band layer at config 3).  Measured per training step: no fold 110.5 ms, fold K0 <= 64 105.6 ms, all layers 99.1 ms
@@ -623,21 +669,32 @@ int lstm_fwd_step_launch(const float* Hprev, const float* w_hh, const float* Xt,
   else if (Xt)   ok = ok && make_tmap(&tmX, Xt, K0, R, K0, tg::BM) && make_tmap(&tmWx, w_ih, K0, 4 * H, K0, 32);
   else { tmX = tmA; tmWx = tmB; }
   FSN_REQUIRE(ok, FSN_ERR_CUDA, "lstm_fwd_step: tensor-map encoding failed");
-  static const int fast_act = getenv("FSN_TRAIN_FAST_ACT") ? atoi(getenv("FSN_TRAIN_FAST_ACT")) : 1;
   static bool attr_by_dev[64] = {};
   int dev = 0; cudaGetDevice(&dev); bool& attr = attr_by_dev[dev & 63];
   if (!attr) {
     int rc;
-    if ((rc = check_cuda(cudaFuncSetAttribute(tg::lstm_fwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              tg::Cfg<128>::SMEM), "lstm_fwd_step smem attr")))
-      return rc;
+#define FSN_STEP_ATTR(FOLD, HT)                                                                                          \
+  if ((rc = check_cuda(cudaFuncSetAttribute(tg::lstm_fwd_step_kernel<FOLD, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            tg::Cfg<128>::SMEM), "lstm_fwd_step smem attr")))                             \
+    return rc
+    FSN_STEP_ATTR(true, 384); FSN_STEP_ATTR(true, 512); FSN_STEP_ATTR(true, 0);
+    FSN_STEP_ATTR(false, 384); FSN_STEP_ATTR(false, 512); FSN_STEP_ATTR(false, 0);
+#undef FSN_STEP_ATTR
     attr = true;
   }
   const int nkx = Xt ? cdiv(K0, x16 ? 2 * tg::BK : tg::BK) : 0, nkh = Hprev ? cdiv(H, h16 ? 2 * tg::BK : tg::BK) : 0;
   FSN_REQUIRE(nkx + nkh > 0, FSN_ERR_SHAPE, "lstm_fwd_step: nothing to multiply");
-  tg::lstm_fwd_step_kernel<<<dim3(cdiv(R, tg::BM), H / 32), 160, tg::Cfg<128>::SMEM, st>>>(
-      tmA, tmB, tmX, tmWx, Gt, b_ih, b_hh, C_prev, C_out, H_out, h16 ? h->H16_out : nullptr, R, H, nkx, nkh, x16 ? 1 : 0,
-      h16 ? 1 : 0, fast_act);
+  const dim3 grid(cdiv(R, tg::BM), H / 32);
+#define FSN_STEP_LAUNCH(FOLD, HT)                                                                                             \
+  tg::lstm_fwd_step_kernel<FOLD, HT><<<grid, 192, tg::Cfg<128>::SMEM, st>>>(tmA, tmB, tmX, tmWx, Gt, b_ih, b_hh, C_prev, C_out, \
+                                                                            H_out, h16 ? h->H16_out : nullptr, R, H, nkx, nkh,  \
+                                                                            x16 ? 1 : 0, h16 ? 1 : 0)
+  if (Xt) {
+    if (H == 384) FSN_STEP_LAUNCH(true, 384); else if (H == 512) FSN_STEP_LAUNCH(true, 512); else FSN_STEP_LAUNCH(true, 0);
+  } else {
+    if (H == 384) FSN_STEP_LAUNCH(false, 384); else if (H == 512) FSN_STEP_LAUNCH(false, 512); else FSN_STEP_LAUNCH(false, 0);
+  }
+#undef FSN_STEP_LAUNCH
   FSN_CHECK_LAUNCH("lstm_fwd_step_kernel");
   return FSN_OK;
 }
