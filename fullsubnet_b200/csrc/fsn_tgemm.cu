@@ -287,8 +287,14 @@ __device__ __forceinline__ float tanh_mufu(float x) {
 }
 
 // HT: hidden size known at compile time (0: runtime) - every stride of the epilogue becomes an immediate offset
-template <bool FOLD, int HT>
-__global__ void __launch_bounds__(192, 2)
+// ST: TMA stages (3: 2 CTAs per SM; 2: 3 CTAs per SM - the kernel is bound by the latency chain of one CTA - load, multiply,
+// drain, cell - not by any unit, so more CTAs in flight is what raises the throughput)
+template <int ST> struct StepCfg {
+  static constexpr int MAIN = (ST * Cfg<128>::STAGE_BYTES > 4 * 4 * 32 * 33 * 4 ? ST * Cfg<128>::STAGE_BYTES : 4 * 4 * 32 * 33 * 4 + 1023) & ~1023;
+  static constexpr int SMEM = MAIN + 1024 /*align*/ + 256 /*barriers*/;
+};
+template <bool FOLD, int HT, int ST>
+__global__ void __launch_bounds__(192, (ST == 2 && HT != 0 && FOLD) ? 3 : 2)
 lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWx, float* __restrict__ G,
                      const float* __restrict__ b_ih, const float* __restrict__ b_hh, const float* __restrict__ C_prev,
@@ -296,10 +302,10 @@ lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                      int nkh, int x16, int h16) {
   const int H = HT ? HT : H_rt;
   using CF = Cfg<128>;
-  constexpr int STAGES = CF::STAGES;
+  constexpr int STAGES = ST;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  Bars& bars = *reinterpret_cast<Bars*>(smem + STAGES * CF::STAGE_BYTES);
+  Bars& bars = *reinterpret_cast<Bars*>(smem + StepCfg<ST>::MAIN);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM, u0 = blockIdx.y * 32;
   // k blocks: first nkx of x_t W_ih^T (a narrow layer input is folded in here instead of a hoisted projection: G then
@@ -673,9 +679,12 @@ int lstm_fwd_step_launch(const float* Hprev, const float* w_hh, const float* Xt,
   int dev = 0; cudaGetDevice(&dev); bool& attr = attr_by_dev[dev & 63];
   if (!attr) {
     int rc;
-#define FSN_STEP_ATTR(FOLD, HT)                                                                                          \
-  if ((rc = check_cuda(cudaFuncSetAttribute(tg::lstm_fwd_step_kernel<FOLD, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                            tg::Cfg<128>::SMEM), "lstm_fwd_step smem attr")))                             \
+#define FSN_STEP_ATTR(FOLD, HT)                                                                                               \
+  if ((rc = check_cuda(cudaFuncSetAttribute(tg::lstm_fwd_step_kernel<FOLD, HT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            tg::StepCfg<2>::SMEM), "lstm_fwd_step smem attr")))                             \
+    return rc;                                                                                                                \
+  if ((rc = check_cuda(cudaFuncSetAttribute(tg::lstm_fwd_step_kernel<FOLD, HT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            tg::StepCfg<3>::SMEM), "lstm_fwd_step smem attr")))                             \
     return rc
     FSN_STEP_ATTR(true, 384); FSN_STEP_ATTR(true, 512); FSN_STEP_ATTR(true, 0);
     FSN_STEP_ATTR(false, 384); FSN_STEP_ATTR(false, 512); FSN_STEP_ATTR(false, 0);
@@ -685,15 +694,24 @@ int lstm_fwd_step_launch(const float* Hprev, const float* w_hh, const float* Xt,
   const int nkx = Xt ? cdiv(K0, x16 ? 2 * tg::BK : tg::BK) : 0, nkh = Hprev ? cdiv(H, h16 ? 2 * tg::BK : tg::BK) : 0;
   FSN_REQUIRE(nkx + nkh > 0, FSN_ERR_SHAPE, "lstm_fwd_step: nothing to multiply");
   const dim3 grid(cdiv(R, tg::BM), H / 32);
-#define FSN_STEP_LAUNCH(FOLD, HT)                                                                                             \
-  tg::lstm_fwd_step_kernel<FOLD, HT><<<grid, 192, tg::Cfg<128>::SMEM, st>>>(tmA, tmB, tmX, tmWx, Gt, b_ih, b_hh, C_prev, C_out, \
-                                                                            H_out, h16 ? h->H16_out : nullptr, R, H, nkx, nkh,  \
-                                                                            x16 ? 1 : 0, h16 ? 1 : 0)
+  static const int stages = getenv("FSN_TRAIN_STEP_STAGES") ? atoi(getenv("FSN_TRAIN_STEP_STAGES")) : 2;
+#define FSN_STEP_LAUNCH(FOLD, HT)                                                                                              \
+  do {                                                                                                                         \
+    if (stages == 2)                                                                                                           \
+      tg::lstm_fwd_step_kernel<FOLD, HT, 2><<<grid, 192, tg::StepCfg<2>::SMEM, st>>>(                                          \
+          tmA, tmB, tmX, tmWx, Gt, b_ih, b_hh, C_prev, C_out, H_out, h16 ? h->H16_out : nullptr, R, H, nkx, nkh, x16 ? 1 : 0,  \
+          h16 ? 1 : 0);                                                                                                        \
+    else                                                                                                                       \
+      tg::lstm_fwd_step_kernel<FOLD, HT, 3><<<grid, 192, tg::StepCfg<3>::SMEM, st>>>(                                          \
+          tmA, tmB, tmX, tmWx, Gt, b_ih, b_hh, C_prev, C_out, H_out, h16 ? h->H16_out : nullptr, R, H, nkx, nkh, x16 ? 1 : 0,  \
+          h16 ? 1 : 0);                                                                                                        \
+  } while (0)
   if (Xt) {
     if (H == 384) FSN_STEP_LAUNCH(true, 384); else if (H == 512) FSN_STEP_LAUNCH(true, 512); else FSN_STEP_LAUNCH(true, 0);
   } else {
     if (H == 384) FSN_STEP_LAUNCH(false, 384); else if (H == 512) FSN_STEP_LAUNCH(false, 512); else FSN_STEP_LAUNCH(false, 0);
   }
+  (void)0;
 #undef FSN_STEP_LAUNCH
   FSN_CHECK_LAUNCH("lstm_fwd_step_kernel");
   return FSN_OK;
