@@ -187,7 +187,7 @@ def measure(args, dist, dev, rank, world, local, cpu_leg=True):
     line = {
         "metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "tf32xf32acc" if precision == "tf32_tc" else "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "tf32+f16 operands, f32 accumulate/state" if precision == "tf32_tc" else "f32", "data": "synthetic",
         "rtf_x": value / (SR / HOP),
         "config": {"workload": f"fullsubnet training step, batch={B} x 3 s 16 kHz synthetic clips per GPU, cIRM MSE "
                                "loss, drop_band G=2, clip 10 + Adam 1e-3 (BASELINE configs[2])",
@@ -197,8 +197,9 @@ def measure(args, dist, dev, rank, world, local, cpu_leg=True):
         "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 2 * B * L * 4,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clocks,
-        "roofline": {"kernel": "whole training step; dominant kernel tgemm_tma_kernel (tcgen05 kind::tf32, 69 % of the "
-                               "step: hoisted input projections, recurrent GEMMs, BPTT, weight gradients)"
+        "roofline": {"kernel": "whole training step; tcgen05 kernels: lstm_fwd_step_kernel (fused recurrent GEMM + cell, "
+                               "kind::f16 / tf32) and tgemm_tma_kernel (kind::tf32: BPTT and weight-gradient GEMMs), "
+                               "together about 60 % of the step (profiles/r02h_train_step_launches_summary.txt)"
                                if precision == "tf32_tc" else "whole training step (fp32 FMA GEMMs)",
                      "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf, "traffic": traffic,

@@ -501,6 +501,7 @@ struct TrainWs {
   float *xsb, *dxsb, *dout, *dz, *dfh1;
   float *dh_rec[2], *dc[2], *dh_mid, *dot;
   float *splitk, *colsum;
+  float *splitk2, *colsum2;  // scratch of the side stream (full-band backward overlapped with the sub-band weight gradients)
   // FSN_PREC_TF32_TC: transposed weights ([H,4H], [K0,4H]) and transposed dG / layer inputs for the weight gradients
   float *sb_whhT[2], *sb_wihT[2], *fb_whhT[2], *fb_wihT1;
   float *gT, *xT, *rec;
@@ -545,6 +546,8 @@ static void carve_train(const fsn_model_desc* d, const Dims& m, void* base, Trai
   w.splitk = c.take(SPLITK_SCRATCH_FLOATS);
   const size_t maxcols = 4 * (Hf > Hs ? Hf : Hs) > F ? 4 * (Hf > Hs ? Hf : Hs) : F;
   w.colsum = c.take((size_t)COLSUM_MAX_S * maxcols);
+  w.splitk2 = c.take(SPLITK_SCRATCH_FLOATS);
+  w.colsum2 = c.take((size_t)COLSUM_MAX_S * maxcols);
   if (d->precision == FSN_PREC_TF32_TC) {
     for (int l = 0; l < 2; ++l) {
       w.sb_whhT[l] = c.take(Hs * 4 * Hs);
@@ -844,6 +847,33 @@ extern "C" int fsn_train_forward(const fsn_model_desc* d, const fsn_seq_weights*
   return FSN_OK;
 }
 
+namespace fsn {
+// Side stream of the backward pass: the full-band BPTT is a chain of ~1 900 tiny launches (64 rows), the sub-band weight
+// gradients are a dozen HBM-bound kernels with no dependency on it - they run side by side.  One high-priority
+// non-blocking stream and two events per device, created on first use; fork / join through events only, so the pattern
+// is also legal inside a stream capture.
+struct SideStream { cudaStream_t s; cudaEvent_t fork, join; bool ok; };
+static SideStream* side_stream() {
+  static SideStream per_dev[64] = {};
+  static bool tried[64] = {};
+  static const bool enabled = getenv("FSN_TRAIN_OVERLAP") == nullptr || atoi(getenv("FSN_TRAIN_OVERLAP")) != 0;
+  if (!enabled) return nullptr;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SideStream& x = per_dev[dev & 63];
+  if (!tried[dev & 63]) {
+    tried[dev & 63] = true;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    x.ok = cudaStreamCreateWithPriority(&x.s, cudaStreamNonBlocking, hi) == cudaSuccess &&
+           cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) == cudaSuccess;
+    if (!x.ok) cudaGetLastError();
+  }
+  return x.ok ? &x : nullptr;
+}
+}  // namespace fsn
+
 extern "C" int fsn_train_backward(const fsn_model_desc* d, const fsn_seq_weights* fb, const fsn_seq_weights* sb,
                                   const float* dcrm, int B, int T, const fsn_seq_grads* gfb, const fsn_seq_grads* gsb,
                                   void* workspace, size_t workspace_bytes, fsn_stream_t stream) {
@@ -897,32 +927,46 @@ extern "C" int fsn_train_backward(const fsn_model_desc* d, const fsn_seq_weights
     if ((rc = layer_bwd_step(s1, t, Tp, nullptr, w.dout + (size_t)t * R * 2, sb->fc_w, 2, w.dh_mid, st))) return rc;
     if ((rc = layer_bwd_step(s0, t, Tp, w.dh_mid, nullptr, nullptr, 0, w.dxsb + (size_t)t * R * K, st))) return rc;
   }
+  // ---- fork: sub-band weight gradients on the caller's stream, the rest of the chain (second norm, full-band Linear, full-band
+  // BPTT) on the side stream with its own split-K / column-sum scratch
+  SideStream* side = side_stream();
+  cudaStream_t st2 = st;
+  float *splitk2 = w.splitk, *colsum2 = w.colsum;
+  if (side) {
+    if ((rc = check_cuda(cudaEventRecord(side->fork, st), "event record"))) return rc;
+    if ((rc = check_cuda(cudaStreamWaitEvent(side->s, side->fork, 0), "stream wait"))) return rc;
+    st2 = side->s; splitk2 = w.splitk2; colsum2 = w.colsum2;
+  }
   if ((rc = layer_weight_grads(s1, Tp, w.sb[0].H, gsb->w_ih[1], gsb->w_hh[1], gsb->b_ih[1], gsb->b_hh[1], w, st)))
     return rc;
   if ((rc = layer_weight_grads(s0, Tp, w.xsb, gsb->w_ih[0], gsb->w_hh[0], gsb->b_ih[0], gsb->b_hh[0], w, st))) return rc;
   // ---- second norm + drop_band + full-band Linear/activation
   if (d->norm_type == FSN_NORM_CUMULATIVE_LAPLACE) {
-    train_cum_unit_bwd_kernel<<<cdiv(R, 128), 128, 0, st>>>(w.dxsb, w.xsb, w.cum2, Tp, R, K, w.dunit);
+    train_cum_unit_bwd_kernel<<<cdiv(R, 128), 128, 0, st2>>>(w.dxsb, w.xsb, w.cum2, Tp, R, K, w.dunit);
     FSN_CHECK_LAUNCH("train_cum_unit_bwd_kernel");
-    train_dfbz_cum_kernel<<<148 * 8, 256, 0, st>>>(w.dunit, w.fbz, map, Tp, R, d->fb_activation, w.dz);
+    train_dfbz_cum_kernel<<<148 * 8, 256, 0, st2>>>(w.dunit, w.fbz, map, Tp, R, d->fb_activation, w.dz);
     FSN_CHECK_LAUNCH("train_dfbz_cum_kernel");
   } else {
-    train_dot_kernel<<<B, 256, 0, st>>>(w.dxsb, w.xsb, Tp, R, m.Fsub, K, w.dot);
+    train_dot_kernel<<<B, 256, 0, st2>>>(w.dxsb, w.xsb, Tp, R, m.Fsub, K, w.dot);
     FSN_CHECK_LAUNCH("train_dot_kernel");
-    train_dfbz_kernel<<<148 * 8, 256, 0, st>>>(w.dxsb, w.fbz, w.inv2, w.dot, map, Tp, R, K, (float)F * K * Tp,
-                                               d->fb_activation, w.dz);
+    train_dfbz_kernel<<<148 * 8, 256, 0, st2>>>(w.dxsb, w.fbz, w.inv2, w.dot, map, Tp, R, K, (float)F * K * Tp,
+                                                d->fb_activation, w.dz);
     FSN_CHECK_LAUNCH("train_dfbz_kernel");
   }
-  if ((rc = sgemm_launch(true, w.dz, F, w.fb[1].H, Hf, gfb->fc_w, Hf, F, Hf, Tp * B, false, w.splitk, st))) return rc;
-  if ((rc = colsum_launch(w.dz, (size_t)Tp * B, F, F, gfb->fc_b, nullptr, w.colsum, st))) return rc;
-  if ((rc = sgemm_launch(false, w.dz, F, fb->fc_w, Hf, w.dfh1, Hf, Tp * B, Hf, F, false, nullptr, st))) return rc;
+  if ((rc = sgemm_launch(true, w.dz, F, w.fb[1].H, Hf, gfb->fc_w, Hf, F, Hf, Tp * B, false, splitk2, st2))) return rc;
+  if ((rc = colsum_launch(w.dz, (size_t)Tp * B, F, F, gfb->fc_b, nullptr, colsum2, st2))) return rc;
+  if ((rc = sgemm_launch(false, w.dz, F, fb->fc_w, Hf, w.dfh1, Hf, Tp * B, Hf, F, false, nullptr, st2))) return rc;
   // ---- full-band stack
   LayerBwd f1{fb->w_ih[1], fb->w_hh[1], w.fb[1], B, Hf, Hf, w.dh_rec[1], w.dc[1], tc_fb ? w.fb_whhT[1] : nullptr,
-              tc_fb ? w.fb_wihT1 : nullptr, w.splitk};
-  LayerBwd f0{fb->w_ih[0], fb->w_hh[0], w.fb[0], B, F, Hf, w.dh_rec[0], w.dc[0], tc_fb ? w.fb_whhT[0] : nullptr, nullptr, w.splitk};
+              tc_fb ? w.fb_wihT1 : nullptr, splitk2};
+  LayerBwd f0{fb->w_ih[0], fb->w_hh[0], w.fb[0], B, F, Hf, w.dh_rec[0], w.dc[0], tc_fb ? w.fb_whhT[0] : nullptr, nullptr, splitk2};
   for (int t = Tp - 1; t >= 0; --t) {
-    if ((rc = layer_bwd_step(f1, t, Tp, w.dfh1 + (size_t)t * B * Hf, nullptr, nullptr, 0, w.dh_mid, st))) return rc;
-    if ((rc = layer_bwd_step(f0, t, Tp, w.dh_mid, nullptr, nullptr, 0, nullptr, st))) return rc;
+    if ((rc = layer_bwd_step(f1, t, Tp, w.dfh1 + (size_t)t * B * Hf, nullptr, nullptr, 0, w.dh_mid, st2))) return rc;
+    if ((rc = layer_bwd_step(f0, t, Tp, w.dh_mid, nullptr, nullptr, 0, nullptr, st2))) return rc;
+  }
+  if (side) {  // join: the full-band weight gradients share gT / xT / splitk / colsum with the sub-band ones
+    if ((rc = check_cuda(cudaEventRecord(side->join, side->s), "event record"))) return rc;
+    if ((rc = check_cuda(cudaStreamWaitEvent(st, side->join, 0), "stream wait"))) return rc;
   }
   if ((rc = layer_weight_grads(f1, Tp, w.fb[0].H, gfb->w_ih[1], gfb->w_hh[1], gfb->b_ih[1], gfb->b_hh[1], w, st)))
     return rc;
