@@ -131,6 +131,7 @@ _SIGNATURES = {
     "fsn_debug_linear_tc": (C.c_int, [_P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _S, _P]),
     "fsn_debug_tgemm": (C.c_int, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _P, _L, _P]),
     "fsn_debug_tgemm_blocked": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _L, _P]),
+    "fsn_debug_lstm_fwd_step": (C.c_int, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _L, _P]),
     "fsn_last_error_code": (C.c_int, []),
     "fsn_last_launch_count": (C.c_int64, []),
     "fsn_total_launch_count": (C.c_int64, []),

@@ -878,3 +878,37 @@ extern "C" int fsn_debug_tgemm_blocked(const float* A, const float* B, float* C,
   return fsn::tgemm_blocked_launch(Ab, (int)((Ka + 31) / 32), a_k0 / 32, Bb, (int)((Kb + 31) / 32), b_k0 / 32, C, (size_t)N, M, N, K,
                                    false, scratch + fa + fb, (size_t)scratch_floats - fa - fb, st);
 }
+
+// unit-test hook for the fused training-forward step (tg::lstm_fwd_step_kernel; torch.nn.LSTM cell math): one step
+//   z = [X W_ih^T  or  the P already in G] + b_ih + b_hh + Hprev W_hh^T;  G <- act(z) (i,f,g,o), C_out, H_out
+// Hprev nullable (first step), X nullable (then G [R,4H] holds the hoisted projection on entry).  half != 0: fp16 MMA
+// operands, converted here into `scratch` (>= 2 * (2 R H + 4 H (H + K0) + R K0) bytes)
+extern "C" int fsn_debug_lstm_fwd_step(const float* Hprev, const float* w_hh, const float* X, const float* w_ih, int K0, float* G,
+                                       const float* b_ih, const float* b_hh, const float* C_prev, float* C_out, float* H_out,
+                                       int R, int H, int half, void* scratch, int64_t scratch_bytes, fsn_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  FSN_REQUIRE(R > 0 && H > 0 && w_hh && G && b_ih && b_hh && C_out && H_out && (!X || (w_ih && K0 > 0)), FSN_ERR_SHAPE,
+              "lstm_fwd_step hook: missing arguments");
+  FSN_REQUIRE(fsn::lstm_fwd_step_supported(H_out, w_hh, H), FSN_ERR_UNSUPPORTED,
+              "lstm_fwd_step hook: needs H %% 32 == 0, 16-byte aligned operands and the TMA driver entry point");
+  FSN_REQUIRE(!X || fsn::tgemm_supported(X, K0, w_ih, K0, K0), FSN_ERR_UNSUPPORTED, "lstm_fwd_step hook: X rows must be 16-byte aligned");
+  if (!half) return fsn::lstm_fwd_step_launch(Hprev, w_hh, X, w_ih, K0, G, b_ih, b_hh, C_prev, C_out, H_out, R, H, st, nullptr);
+  const size_t nh = (size_t)R * H, nw = (size_t)4 * H * H, nx = X ? (size_t)R * K0 : 0, nwx = X ? (size_t)4 * H * K0 : 0;
+  FSN_REQUIRE((H % 8) == 0 && (!X || (K0 % 8) == 0), FSN_ERR_UNSUPPORTED, "lstm_fwd_step hook: fp16 rows must be 16-byte aligned");
+  FSN_REQUIRE(scratch && (size_t)scratch_bytes >= 2 * (2 * nh + nw + nx + nwx) + 1024, FSN_ERR_WORKSPACE,
+              "lstm_fwd_step hook: scratch too small");
+  auto up = [](size_t n) { return (n + 127) & ~(size_t)127; };  // keep every block 256-byte aligned
+  __half* hp = (__half*)scratch;
+  __half* ho = hp + up(nh);
+  __half* wh = ho + up(nh);
+  __half* xx = wh + up(nw);
+  __half* wx = xx + up(nx);
+  FSN_REQUIRE((size_t)((char*)(wx + up(nwx)) - (char*)scratch) <= (size_t)scratch_bytes, FSN_ERR_WORKSPACE,
+              "lstm_fwd_step hook: scratch too small");
+  int rc;
+  if (Hprev && (rc = fsn::to_half_launch(Hprev, nh, hp, st))) return rc;
+  if ((rc = fsn::to_half_launch(w_hh, nw, wh, st))) return rc;
+  if (X && ((rc = fsn::to_half_launch(X, nx, xx, st)) || (rc = fsn::to_half_launch(w_ih, nwx, wx, st)))) return rc;
+  fsn::LstmStepHalf hs{Hprev ? hp : nullptr, wh, X ? xx : nullptr, X ? wx : nullptr, ho};
+  return fsn::lstm_fwd_step_launch(Hprev, w_hh, X, w_ih, K0, G, b_ih, b_hh, C_prev, C_out, H_out, R, H, st, &hs);
+}

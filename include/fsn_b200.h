@@ -363,6 +363,15 @@ int fsn_debug_tgemm(const float* A, int64_t lda, const float* B, int64_t ldb, fl
 int fsn_debug_tgemm_blocked(const float* A, const float* B, float* C, int M, int N, int K, int a_k0, int b_k0,
                             float* scratch, int64_t scratch_floats, fsn_stream_t stream);
 
+/* unit-test hook for the fused forward step of the training path (one LSTM step of torch.nn.LSTM as used by
+ * audio_zen/model/module/sequence_model.py:52-58): z = x W_ih^T (or the projection already in G) + b_ih + b_hh +
+ * h_prev W_hh^T; G [R,4H] <- post-activation gates (i,f,g,o), c_out = f c_prev + i g, h_out = o tanh(c_out).
+ * h_prev, c_prev nullable (first step); x nullable (G then holds x W_ih^T on entry).  half != 0: fp16 MMA operands
+ * (converted into scratch, >= 2 * (2 R H + 4 H (H + K0) + R K0) + 1024 bytes); H % 32 == 0 */
+int fsn_debug_lstm_fwd_step(const float* h_prev, const float* w_hh, const float* x, const float* w_ih, int K0, float* G,
+                            const float* b_ih, const float* b_hh, const float* c_prev, float* c_out, float* h_out, int R,
+                            int H, int half, void* scratch, int64_t scratch_bytes, fsn_stream_t stream);
+
 /* unit-test hooks for the tensor-core LSTM layer of the full-band stacks (fsn_lstm_rec_tc.cu;
  * audio_zen/model/module/sequence_model.py:52-58,117): hall[r,t,:] of nn.LSTM(K -> H, 1 layer) over x [R,T,K]
  * (hoisted input-projection GEMM + persistent tcgen05 recurrence), and out = act(x W^T + b) for x [rows,K], W [N,K];

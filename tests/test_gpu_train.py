@@ -450,3 +450,65 @@ def test_packed_weight_cache_follows_fused_optimizer_steps(dev):
     tc1, ref1 = both()
     assert rel_max(ref1.cpu(), ref0.cpu()) > 1e-2          # the update changed the model
     assert rel_max(tc1.cpu(), ref1.cpu()) < 5e-5            # and the packed image was rebuilt from the new weights
+
+
+def test_fused_lstm_forward_step_matches_float64_cell(dev):
+    """fsn_debug_lstm_fwd_step (tg::lstm_fwd_step_kernel, the per-step kernel of the training forward): one nn.LSTM step
+    against a float64 cell - folded input (tf32 / fp16 operands), hoisted projection already in G, first step without
+    h / c, row counts off the 128-row tile, the compile-time (384, 512) and run-time (64) hidden sizes.  Tolerance:
+    11-bit operand rounding of K <= 1024 products plus the MUFU activations."""
+    from fullsubnet_b200 import _lib
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    torch.manual_seed(11)
+    cases = [  # R, H, K0, half, fold, first
+        (200, 384, 32, 0, True, False), (200, 384, 32, 1, True, False), (333, 384, 384, 1, True, False),
+        (64, 512, 512, 1, True, False), (130, 512, 0, 1, False, False), (130, 512, 0, 0, False, False),
+        (100, 64, 16, 1, True, False), (100, 64, 16, 0, True, True), (257, 384, 32, 1, True, True),
+    ]
+    for (R, H, K0, half, fold, first) in cases:
+        k = 1.0 / H ** 0.5
+        w_hh = (torch.rand(4 * H, H, device=dev) * 2 - 1) * k
+        w_ih = (torch.rand(4 * H, max(K0, 1), device=dev) * 2 - 1) * k
+        b_ih, b_hh = (torch.rand(4 * H, device=dev) * 2 - 1) * k, (torch.rand(4 * H, device=dev) * 2 - 1) * k
+        hp, cp = torch.rand(R, H, device=dev) * 2 - 1, torch.randn(R, H, device=dev)
+        x = torch.randn(R, max(K0, 1), device=dev)
+        P = torch.randn(R, 4 * H, device=dev)
+        pad = 8  # rows past R must stay untouched
+        G = torch.full((R + pad, 4 * H), 7.0, device=dev)
+        if not fold:
+            G[:R] = P
+        C_out, H_out = torch.full((R + pad, H), 7.0, device=dev), torch.full((R + pad, H), 7.0, device=dev)
+        scratch = torch.empty(2 * (2 * R * H + 4 * H * (H + K0) + R * K0) + 4096, dtype=torch.uint8, device=dev)
+        _lib.check(lib.fsn_debug_lstm_fwd_step(None if first else hp.data_ptr(), w_hh.data_ptr(), x.data_ptr() if fold else None,
+                                               w_ih.data_ptr() if fold else None, K0, G.data_ptr(), b_ih.data_ptr(),
+                                               b_hh.data_ptr(), None if first else cp.data_ptr(), C_out.data_ptr(),
+                                               H_out.data_ptr(), R, H, half, scratch.data_ptr(), scratch.numel(), st))
+        z = (x.double() @ w_ih.double().T if fold else P.double()) + b_ih.double() + b_hh.double()
+        if not first:
+            z = z + hp.double() @ w_hh.double().T
+        i, f, g, o = z[:, :H].sigmoid(), z[:, H:2 * H].sigmoid(), z[:, 2 * H:3 * H].tanh(), z[:, 3 * H:].sigmoid()
+        c = i * g if first else f * cp.double() + i * g
+        h = o * c.tanh()
+        ref_g = torch.cat([i, f, g, o], dim=1)
+        case = (R, H, K0, half, fold, first)
+        assert (G[:R].double() - ref_g).abs().max().item() < 2e-3, case
+        assert (C_out[:R].double() - c).abs().max().item() < 4e-3, case
+        assert (H_out[:R].double() - h).abs().max().item() < 4e-3, case
+        assert bool((G[R:] == 7.0).all()) and bool((C_out[R:] == 7.0).all()) and bool((H_out[R:] == 7.0).all()), case
+
+
+def test_unfused_training_paths_in_a_subprocess():
+    """The fallbacks behind the fused / overlapped training kernels (environment switches, read once per process): separate
+    recurrent GEMM + cell kernel, plain transposed weight-gradient operands, single stream - the golden steps of the
+    unmodified reference still pass."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FSN_TRAIN_FUSED_FWD="0", FSN_TGEMM_BLOCKED="0", FSN_TRAIN_OVERLAP="0")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_train.py"), "-m", "gpu", "-x", "-q",
+                          "-k", "two_steps_match_reference or full_size_model_step or cumulative_norm_training"],
+                         env=env, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
+    assert " passed" in out.stdout and "failed" not in out.stdout, out.stdout[-1000:]
