@@ -9,6 +9,12 @@
 //              to the tensor core.  After the last k-step the same warps drain TMEM (warp w <-> lanes 32w..32w+31).
 //   warp 4     MMA issue (converged warp, one elected lane): 4 MMAs (K = 8) per stage, tcgen05.commit frees it.
 // No operand conversion pass: the tensor core reads fp32 bits as tf32 (10-bit mantissa, truncation).
+//
+// Also in this file, built from the same pieces:
+//   tgemm_tma_kernel        the same tile fed by TMA (default); BlockedOps mode streams block-tiled operand copies
+//                           (transpose_blocked_kernel) for the long-K weight-gradient GEMMs dW = dG^T X
+//   lstm_fwd_step_kernel    one LSTM step of the training forward: [x_t | h_{t-1}] [W_ih | W_hh]^T (fp16 / tf32 operands)
+//                           and the cell in one launch; tile = 128 rows x (4 gates x 32 hidden units)
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <string.h>
