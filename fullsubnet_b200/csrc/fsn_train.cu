@@ -603,8 +603,10 @@ static int layer_forward_save(const fsn_seq_weights* w, int l, const float* X, i
   return FSN_OK;
 }
 
-// tensor-core variant: input projection of ALL steps as one GEMM into the gate buffer, then per step
-// G_t += h_{t-1} W_hh^T (tcgen05 tf32) and the fused cell kernel
+// tensor-core variant.  Default: ONE kernel per step (lstm_fwd_step_kernel, fsn_tgemm.cu): [x_t | h_{t-1}] [W_ih | W_hh]^T on
+// tcgen05 and the cell in its epilogue, gates / cell / hidden saved.  Fallbacks, step by step: a layer input whose rows
+// are not 16-byte aligned keeps a hoisted projection of all steps (one GEMM into the gate buffer) that the step kernel
+// adds; with the fused kernel switched off (or H % 32 != 0) every step is a recurrent GEMM into `rec` + lstm_cell_fwd_kernel
 int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R, int K0, int H, int Tp,
                                  const LayerSave& s, float* rec, cudaStream_t st, float* splitk, size_t splitk_floats,
                                  const LayerHalf* half) {
@@ -612,8 +614,8 @@ int layer_forward_save_tc(const fsn_seq_weights* w, int l, const float* X, int R
   const int rows = Tp * R;
   static const int fused_min_rows = getenv("FSN_TRAIN_FUSED_MIN_ROWS") ? atoi(getenv("FSN_TRAIN_FUSED_MIN_ROWS")) : 1;
   const bool fused = R >= fused_min_rows && lstm_fwd_step_supported(s.H, w->w_hh[l], H);
-  // narrow layer input (the 32-wide sub-band units): x_t W_ih^T is one more k block of the step kernel - no hoisted
-  // projection, G is written once and never read in the forward pass
+  // x_t W_ih^T as leading k blocks of the step kernel - no hoisted projection, G is written once and never read in the
+  // forward pass (FSN_TRAIN_FOLD_K bounds the input width this is done for)
   const bool fold = fused && lstm_fwd_step_folds_input(X, w->w_ih[l], K0);
   // fp16 MMA operands: h_t (written by the step kernel next to the fp32 copy) and the weights; the folded layer input too
   // when the layer below left an fp16 copy (K0 % 8: 16-byte rows)
