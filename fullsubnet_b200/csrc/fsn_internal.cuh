@@ -115,6 +115,8 @@ int rows_fc_launch(const float* h, int R, int H, const float* W, const float* bi
                    size_t row_stride, size_t o_stride, cudaStream_t st);
 int sb_fc_step_launch(const float* h, int R, int H, const float* W, const float* bias, int O, int act, float* crm,
                       int Fsub, int T_out, int t_out, cudaStream_t st);
+int sb_fc_steps_launch(const float* h, int R, int H, int steps, const float* W, const float* bias, int O, int act, float* crm,
+                       int Fsub, int T_out, int t_out0, cudaStream_t st);
 int transpose_mag_launch(const float* in, float* out, int B, int F, int T, int T_pad, cudaStream_t st);
 int clip_stats_launch(const float* x, int B, int T_pad, int F, int N, float2* fs, float2* sums, cudaStream_t st);
 int clip_reduce_only_launch(const float2* fs, int B, int T_pad, float2* sums, cudaStream_t st);

@@ -331,11 +331,13 @@ int fc_gemm_launch(const float* A, const float* W, const float* bias, float* out
 // crm[b', o, f', t_out] (model.py:129-135: reshape/permute + look-ahead slice fused)
 __global__ void sb_fc_step_kernel(const float* __restrict__ h, int R, int H, const float* __restrict__ W,
                                   const float* __restrict__ bias, int O, int act, float* __restrict__ crm, int Fsub,
-                                  int T_out, int t_out) {
+                                  int T_out, int t_out, size_t step_stride) {
+  // blockIdx.y: step (h of step y starts step_stride floats further and lands in frame t_out + y)
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
-  const float* hp = h + (size_t)row * H;
+  t_out += blockIdx.y;
+  const float* hp = h + (size_t)blockIdx.y * step_stride + (size_t)row * H;
   const int bq = row / Fsub, fq = row - bq * Fsub;
   for (int o = 0; o < O; ++o) {
     float s = 0.f;
@@ -369,7 +371,17 @@ int rows_fc_launch(const float* h, int R, int H, const float* W, const float* bi
 
 int sb_fc_step_launch(const float* h, int R, int H, const float* W, const float* bias, int O, int act, float* crm,
                       int Fsub, int T_out, int t_out, cudaStream_t st) {
-  sb_fc_step_kernel<<<cdiv(R, 8), 256, 0, st>>>(h, R, H, W, bias, O, act, crm, Fsub, T_out, t_out);
+  sb_fc_step_kernel<<<cdiv(R, 8), 256, 0, st>>>(h, R, H, W, bias, O, act, crm, Fsub, T_out, t_out, 0);
+  FSN_CHECK_LAUNCH("sb_fc_step_kernel");
+  return FSN_OK;
+}
+
+// the same Linear for `steps` consecutive steps of a time-major [steps, R, H] block in one launch (training forward)
+int sb_fc_steps_launch(const float* h, int R, int H, int steps, const float* W, const float* bias, int O, int act, float* crm,
+                       int Fsub, int T_out, int t_out0, cudaStream_t st) {
+  if (steps <= 0) return FSN_OK;
+  FSN_REQUIRE(steps <= 65535, FSN_ERR_SHAPE, "sb_fc_steps: too many steps");
+  sb_fc_step_kernel<<<dim3(cdiv(R, 8), steps), 256, 0, st>>>(h, R, H, W, bias, O, act, crm, Fsub, T_out, t_out0, (size_t)R * H);
   FSN_CHECK_LAUNCH("sb_fc_step_kernel");
   return FSN_OK;
 }

@@ -842,11 +842,9 @@ extern "C" int fsn_train_forward(const fsn_model_desc* d, const fsn_seq_weights*
     if ((rc = layer_forward_save(sb, 0, w.xsb, m.R, m.Ksb, Hs, Tp, w.sb[0], st))) return rc;
     if ((rc = layer_forward_save(sb, 1, w.sb[0].H, m.R, Hs, Hs, Tp, w.sb[1], st))) return rc;
   }
-  for (int t = d->look_ahead; t < Tp; ++t)
-    if ((rc = sb_fc_step_launch(w.sb[1].H + (size_t)t * m.R * Hs, m.R, Hs, sb->fc_w, sb->fc_b, 2, d->sb_activation, crm,
-                                m.Fsub, m.T, t - d->look_ahead, st)))
-      return rc;
-  return FSN_OK;
+  // sub-band Linear of every output frame in one launch (model.py:129-135; the first look_ahead steps have no frame)
+  return sb_fc_steps_launch(w.sb[1].H + (size_t)d->look_ahead * m.R * Hs, m.R, Hs, Tp - d->look_ahead, sb->fc_w, sb->fc_b, 2,
+                            d->sb_activation, crm, m.Fsub, m.T, 0, st);
 }
 
 namespace fsn {
