@@ -306,3 +306,23 @@ def test_wav_load_resample_write_roundtrip(tmp_path):
         f.setnchannels(2); f.setsampwidth(2); f.setframerate(16000)
         f.writeframes(np.stack([pcm[:100], -pcm[:100]], 1).astype("<i2").tobytes())
     assert np.abs(Inferencer.load_wav(tmp_path / "st.wav", 16000)).max() == 0.0
+
+
+def test_every_environment_switch_is_documented():
+    """Each FSN_* variable the library, the Python host or the bench scripts read appears in DESIGN.md (appendix
+    "diagnostic switches"), so a maintainer can find what a switch does without reading the kernels."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "fullsubnet_b200", "csrc", "*.cu")) + glob.glob(os.path.join(root, "fullsubnet_b200", "csrc", "*.cuh"))
+    files += glob.glob(os.path.join(root, "fullsubnet_b200", "**", "*.py"), recursive=True)
+    files += [os.path.join(root, "bench.py"), os.path.join(root, "bench_train.py")]
+    names = set()
+    for f in files:
+        text = open(f).read()
+        names |= set(re.findall(r'getenv\("(FSN_[A-Z0-9_]+)"', text))
+        names |= set(re.findall(r'environ(?:\.get)?[\(\[]"(FSN_[A-Z0-9_]+)"', text))
+    assert len(names) > 20, names
+    doc = open(os.path.join(root, "DESIGN.md")).read()
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, missing
